@@ -1,0 +1,75 @@
+"""Pin the CPU oracle against golden vectors minted from the unmodified reference."""
+import pytest
+import torch
+
+from oracle import mmssl_oracle as O
+from tests.golden_util import CASES, Golden, rel_err
+
+TOL = 2e-6  # oracle and reference are both torch-CPU fp32: only summation-order noise is allowed
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("variant", ["literal", "closed"])
+def test_forward_losses_grads(case, variant):
+    g = Golden(case)
+    cfg = g.oracle_cfg()
+    params = {k: v.clone().requires_grad_(True) for k, v in g.params.items()}
+    fwd = O.forward_literal if variant == "literal" else O.forward_closed
+    outs = fwd(params, g.image_feats, g.text_feats, g.graphs(), cfg,
+               dropout_masks=g.masks if g.train else None, training=g.train)
+    assert outs[0] is outs[6] and outs[1] is outs[7]
+    for j in range(12):
+        assert rel_err(outs[j], g.outs[j]) < TOL, (case, variant, j)
+    total, parts = O.hot_loss(outs, g.users, g.pos, g.neg, g.cfg["I"], cfg, literal=(variant == "literal"))
+    assert abs(float(parts["mf"]) - g.losses["mf"]) < 1e-6
+    assert abs(float(parts["emb"]) - g.losses["emb"]) < 1e-9
+    assert abs(float(parts["feat_reg"]) - g.losses["feat_reg"]) < 1e-9
+    assert abs(float(parts["cl"]) - (g.losses["cl1"] + g.losses["cl2"])) < 1e-4 * abs(g.losses["cl1"] + g.losses["cl2"])
+    assert abs(float(total) - g.losses["total"]) < 1e-6 * max(1.0, abs(g.losses["total"]))
+    total.backward()
+    for k, ref in g.grads.items():
+        if k == "weight_dict.w_q":   # reference gets only rounding noise here
+            got = params[k].grad
+            assert got is None or float(got.abs().max()) < 1e-10
+            continue
+        got = params[k].grad
+        assert got is not None, k
+        assert rel_err(got, ref) < 5e-5, (case, variant, k, rel_err(got, ref))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_infonce_block_independent(case):
+    g = Golden(case)
+    cfg = g.oracle_cfg()
+    z1, z2 = g.outs[8][g.users], g.outs[6][g.users]
+    a = O.infonce(z1, z2, cfg, block=16)
+    b = O.infonce_literal(z1, z2, cfg, block=16)
+    assert abs(float(a) - g.losses["cl_small_block"]) < 1e-5
+    assert abs(float(b) - g.losses["cl_small_block"]) < 1e-5
+    assert abs(float(a) - g.losses["cl1"]) < 1e-5
+
+
+def test_graph_normalisation_matches_golden():
+    import numpy as np
+    import scipy.sparse as sp
+    g = Golden("case_eval_alias_k2")
+    U, I = g.cfg["U"], g.cfg["I"]
+    r = sp.csr_matrix((np.ones(len(g.z["train_rows"]), np.float32), (g.z["train_rows"], g.z["train_cols"])), shape=(U, I))
+    ui, iu = O.build_graphs(r)
+    gui, giu = g.graphs()[:2]
+    assert rel_err(ui.to_dense(), gui.to_dense()) < 1e-7
+    assert rel_err(iu.to_dense(), giu.to_dense()) < 1e-7
+
+
+def test_adamw_matches_torch():
+    torch.manual_seed(0)
+    p = torch.randn(37, 5)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref], lr=5.5e-4)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        gr = torch.randn_like(p)
+        ref.grad = gr.clone()
+        opt.step()
+        O.adamw_step(p, gr, m, v, step, lr=5.5e-4)
+        assert rel_err(p, ref) < 1e-6
