@@ -1,0 +1,202 @@
+/* mmssl_b200 -- C ABI of the B200-native MMSSL hot path (libmmssl_b200.so, sm_100a only).
+ *
+ * Plain pointers and sizes; no torch types.  Every pointer is a DEVICE pointer unless it is a
+ * small descriptor struct/array marked "host".  `stream` is a cudaStream_t passed as void*.
+ * All functions are asynchronous on `stream`, never synchronise, are CUDA-graph capturable, and
+ * return 0 on success / non-zero on failure (message: mmssl_last_error()).  Matrices are
+ * row-major fp32 with an explicit leading dimension (in floats).
+ *
+ * Each entry point names the reference code it replaces (paths relative to
+ * /root/reference/MMSSL/).  The reference itself is Python on stock torch ops, so the
+ * "reference-side binding" is the ctypes stub in mmssl_b200/_lib.py.
+ */
+#ifndef MMSSL_B200_H
+#define MMSSL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMSSL_ABI_VERSION 1
+#define MMSSL_SPMM_MAX_RHS 3
+#define MMSSL_SPMM_SEG_LEN 256 /* default segment length for long rows */
+
+int mmssl_abi_version(void);
+const char* mmssl_last_error(void);
+/* 0 if the current device is compute capability 10.x (B200); fails loudly otherwise. */
+int mmssl_device_check(void);
+
+/* ------------------------------------------------------------------ graph preparation
+ * Replaces the per-call coalesce + COO->CSR conversion ATen performs inside torch.sparse.mm
+ * (Models.py:69-73, :203-208) and restates the graph normalisation of main.py:89-103. */
+int64_t mmssl_csr_workspace_bytes(int64_t nnz, int64_t n_rows);
+/* COO (int64 row/col, fp32 values; unsorted and duplicate coordinates allowed) -> CSR sorted by
+ * (row, col), stable for duplicates.  transpose != 0 builds the CSR of A^T (n_rows/n_cols are
+ * then those of A^T). */
+int mmssl_csr_from_coo(const int64_t* rows, const int64_t* cols, const float* vals, int64_t nnz,
+                       int64_t n_rows, int64_t n_cols, int transpose, int32_t* rowptr, int32_t* colidx,
+                       float* out_vals, void* workspace, int64_t workspace_bytes, void* stream);
+/* vals[e] *= (rowsum + 1e-8)^-1/2  -- csr_norm(mean_flag=True), main.py:89-103 */
+int mmssl_csr_row_normalize(const int32_t* rowptr, int64_t n_rows, float* vals, void* stream);
+
+/* nnz-balanced work plan: rows longer than 2*seg_len are cut into seg_len segments. */
+int64_t mmssl_spmm_plan_items_cap(int64_t n_rows, int64_t nnz, int seg_len);
+int64_t mmssl_spmm_plan_splits_cap(int64_t nnz, int seg_len);
+int64_t mmssl_spmm_plan_segs_cap(int64_t nnz, int seg_len);
+int64_t mmssl_spmm_plan_workspace_bytes(int64_t n_rows);
+int mmssl_spmm_plan(const int32_t* rowptr, int64_t n_rows, int64_t nnz, int seg_len, int32_t* items4 /*[items_cap][4]*/,
+                    int64_t items_cap, int32_t* split_table2 /*[splits_cap][2]*/, int32_t* counters /*[splits_cap]*/,
+                    int64_t splits_cap, int32_t* totals3, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* host descriptor of a prepared sparse operand */
+typedef struct {
+    const int32_t* rowptr; /* [n_rows+1] */
+    const int32_t* colidx; /* [nnz] */
+    const float* vals;     /* [nnz] */
+    int64_t n_rows, n_cols, nnz;
+    const int32_t* items; /* work plan, [n_items][4] = {row, begin, end, split or -1}; row<0 = unused */
+    int64_t n_items;      /* capacity actually launched over */
+    const int32_t* split_table;
+    int32_t* counters;
+    int64_t segs_cap; /* partial-sum slots the plan may use */
+    int32_t seg_len;
+} mmssl_csr_t;
+
+/* ------------------------------------------------------------------ SpMM (the propagation operator)
+ * Y_r = epi( A * X_r [+ alpha * C_r] ),   optional S_r (+)= Y_r.
+ * Replaces MMSSL.mm / torch.sparse.mm (Models.py:69-73,177-186) and torch.mm(sparse,dense)
+ * (Models.py:203-208) incl. the row softmax of the last layer (Models.py:203-204), the layer sum of
+ * Models.py:213-214 and, with the CSR of A^T, the transposed products autograd derives. */
+#define MMSSL_EPI_NONE 0
+#define MMSSL_EPI_SOFTMAX 1     /* y = softmax_d(v) */
+#define MMSSL_EPI_SOFTMAX_BWD 2 /* y = ysaved * (v - <v, ysaved>) */
+typedef struct {
+    const float* x; int64_t ldx;
+    float* y; int64_t ldy;
+    const float* c; int64_t ldc;           /* optional; may alias y */
+    const float* ysaved; int64_t ldysaved; /* MMSSL_EPI_SOFTMAX_BWD only */
+    float* s; int64_t lds;                 /* optional running sum */
+    const float* sbase; int64_t ldsbase;   /* s_mode 2: S = sbase + y */
+} mmssl_spmm_rhs_t;
+/* d in {64,128,256}; nrhs in 1..3 (all right-hand sides share A and d).  s_mode: 0 none, 1 S += y, 2 S = sbase + y.
+ * `partials` = scratch for split rows, >= a->segs_cap * nrhs * d floats.  impl: 0 = LDG gather, 1 = TMA-staged gather. */
+int mmssl_spmm_csr_f32(const mmssl_csr_t* a /*host*/, int d, int nrhs, const mmssl_spmm_rhs_t* rhs /*host*/,
+                       int epilogue, float alpha, int s_mode, float* partials, int64_t partials_floats, int impl, void* stream);
+
+/* ------------------------------------------------------------------ dense fp32 GEMM (CUDA-core path)
+ * C = alpha * op(A) * op(B) + beta * C, row-major.  Used for the d x d "attention" mixing
+ * (Models.py:139-169 == v * sum_h Wcat[h]) and as the verification path of the
+ * projection.  split_k > 1 accumulates with float atomics (C must hold beta*C already; beta is then ignored). */
+int mmssl_sgemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, float alpha, const float* a, int64_t lda,
+                const float* b, int64_t ldb, float beta, float* c, int64_t ldc, int split_k, void* stream);
+
+/* ------------------------------------------------------------------ projection (tcgen05 + TMA)
+ * X = F * W^T + b  and  dW = dX^T * F, fp32 semantics via a bf16 hi/lo split (3 MMAs per product),
+ * replaces nn.Linear image_trans/text_trans forward and weight gradient (Models.py:28-31,173-174).
+ * Declared in the "projection" section below once built (mmssl_proj_*). */
+
+/* ------------------------------------------------------------------ row-wise fused glue
+ * out = e + rate * z / max(||z||, 1e-12)          (Models.py:196-197)
+ * zn = normalised z (contiguous [n,d]), nrm[n] = ||z|| */
+int mmssl_id_fuse_fwd(const float* z, int64_t ldz, const float* e, int64_t lde, int64_t n, int d, float rate,
+                      float* out, int64_t ldo, float* zn, float* nrm, void* stream);
+/* dz = rate * d(normalize)(g)   (backward of the above w.r.t. z; the gradient w.r.t. e is g itself) */
+int mmssl_id_fuse_bwd(const float* g, int64_t ldg, const float* zn, const float* nrm, int64_t n, int d, float rate,
+                      float* dz, int64_t lddz, void* stream);
+/* out = s * inv_layers + rate * (normalize(a) + normalize(b))   (Models.py:213-218)
+ * sumsq_partials[blocks] receives per-block sum(a^2 + b^2) (feeds feat_reg, main.py:252-257). */
+int mmssl_combine_fwd(const float* s, int64_t lds, const float* a, int64_t lda, const float* b, int64_t ldb, int64_t n,
+                      int d, float inv_layers, float rate, float* out, int64_t ldo, float* sumsq_partials,
+                      int64_t n_partials, void* stream);
+int64_t mmssl_combine_partials(int64_t n, int d);
+/* ga = ga_ext + rate * d(normalize)(a; g) + reg_coef * a   (and the same for b); ga_ext may be NULL */
+int mmssl_combine_bwd(const float* g, int64_t ldg, const float* a, int64_t lda, const float* b, int64_t ldb,
+                      const float* ga_ext, int64_t ldgae, const float* gb_ext, int64_t ldgbe, int64_t n, int d,
+                      float rate, float reg_coef, float* ga, int64_t ldga, float* gb, int64_t ldgb, void* stream);
+/* t = y * (alpha*g - <alpha*g, y>)  (softmax backward for one tensor) */
+int mmssl_softmax_bwd(const float* y, int64_t ldy, const float* g, int64_t ldg, int64_t n, int d, float alpha,
+                      float* t, int64_t ldt, void* stream);
+/* y = alpha * (alpha_dev ? *alpha_dev : 1) * x + beta * y, strided rows (alpha_dev: optional device scalar) */
+int mmssl_axpby(const float* x, int64_t ldx, int64_t n, int d, float alpha, const float* alpha_dev, float beta, float* y, int64_t ldy, void* stream);
+/* dropout apply: y = x * mask (mask holds 0 or 1/(1-p)) ; mask may be NULL (copy) */
+int mmssl_mul_mask(const float* x, int64_t ldx, const float* mask, int64_t ldm, int64_t n, int d, float* y, int64_t ldy, void* stream);
+/* per-block sums of squares of an [n,d] matrix: partials[mmssl_sumsq_blocks(n,d)] */
+int64_t mmssl_sumsq_blocks(int64_t n, int d);
+int mmssl_sumsq(const float* x, int64_t ldx, int64_t n, int d, float* partials, void* stream);
+
+/* ------------------------------------------------------------------ BPR   (main.py:368-371, :499-511)
+ * rows: u = UF[users[k]], p = IF[pos[k]], n = IF[neg[k]]  (index arrays may be NULL = identity).
+ * mode bit 0: write per-block partial sums  part[2*b] = sum softplus(-(u.p-u.n)),  part[2*b+1] = sum (|u|^2+|p|^2+|n|^2)/2
+ * mode bit 1: accumulate gradients  (atomic adds when indices are given, plain adds otherwise):
+ *     d/du = -sigmoid(-x)*(p-n)*w_mf + w_reg*u, ...  with w_mf = g_mf/B, w_reg = g_emb*reg_coef,
+ *     g_mf / g_emb read from device scalars (NULL = 1.0). */
+int64_t mmssl_bpr_blocks(int64_t batch, int d);
+int mmssl_bpr(const float* uf, int64_t ldu, const float* itf, int64_t ldi, const float* itf_neg, int64_t ldin,
+              const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t batch, int d, int mode,
+              float reg_coef, const float* g_mf, const float* g_emb, float* part, float* g_uf, int64_t ldgu,
+              float* g_pos, int64_t ldgp, float* g_neg, int64_t ldgn, void* stream);
+
+/* ------------------------------------------------------------------ InfoNCE  (main.py:211-249)
+ * loss = mean_i -log( B_ii / (sum_j R_ij + sum_j B_ij - R_ii) + 1e-8 ),  R = exp(a a^T/tau), B = exp(a b^T/tau),
+ * a = normalize(z1[idx]), b = normalize(z2[idx]).  Work buffers are caller-provided:
+ *   a,b [n,d]; na,nb [n]; stats [4*n + 2*n*ceil(n/64)] ; coef [2*n]; ga,gb [n,d] (zeroed by prepare). */
+int mmssl_infonce_prepare(const float* z1, int64_t ldz1, const float* z2, int64_t ldz2, const int64_t* idx, int64_t n,
+                          int d, float* a, float* b, float* na, float* nb, float* ga, float* gb, void* stream);
+int64_t mmssl_infonce_stats_floats(int64_t n);
+int64_t mmssl_infonce_loss_blocks(int64_t n);
+/* row statistics + per-row loss partials (loss_part[mmssl_infonce_loss_blocks(n)] = block sums of loss_i)
+ * and backward coefficients coef[2n] scaled by g_loss (device scalar, NULL = 1) / n. */
+int mmssl_infonce_stats(const float* a, const float* b, int64_t n, int d, float inv_tau, float* stats, float* coef,
+                        const float* g_loss, float* loss_part, void* stream);
+int mmssl_infonce_grad(const float* a, const float* b, int64_t n, int d, float inv_tau, const float* coef, float* ga,
+                       float* gb, void* stream);
+/* through the normalisation, then (atomic) scatter-add into the tables: g_z1[idx[i]] += ..., g_z2[idx[i]] += ... */
+int mmssl_infonce_scatter(const float* ga, const float* gb, const float* a, const float* b, const float* na,
+                          const float* nb, const int64_t* idx, int64_t n, int d, float* g_z1, int64_t ldg1, float* g_z2,
+                          int64_t ldg2, void* stream);
+
+/* ------------------------------------------------------------------ loss assembly  (main.py:420 without the GAN term)
+ * out[0]=total, [1]=mf, [2]=emb, [3]=feat_reg, [4]=cl.  Sums the partial arrays in index order (deterministic).
+ * total = mf + emb + feat + cl_rate*cl ; mf = sum(bpr_part[2b])/batch ; emb = reg_coef*sum(bpr_part[2b+1]) ;
+ * feat = feat_coef * (sum fr_u + sum fr_i) ; cl = cl_mult * (sum nce1)/n_nce + (sum nce2)/n_nce  */
+int mmssl_loss_assemble(const float* bpr_part, int64_t n_bpr_blocks, int64_t batch, float reg_coef, const float* fr_u,
+                        int64_t n_fr_u, const float* fr_i, int64_t n_fr_i, float feat_coef, const float* nce1,
+                        int64_t n_nce1, const float* nce2, int64_t n_nce2, int64_t n_nce_rows, float cl_rate,
+                        float* out5, void* stream);
+
+/* ------------------------------------------------------------------ AdamW  (main.py:76-80, :427-429; torch.optim.AdamW semantics)
+ * Up to 16 tensors per call.  *step_dev (device int32) is the 1-based step number to use (see mmssl_step_tick). */
+#define MMSSL_ADAMW_MAX_TENSORS 16
+int mmssl_step_tick(int32_t* step_dev, void* stream);
+int mmssl_adamw(int n_tensors, float* const* p /*host array of device ptrs*/, const float* const* g, float* const* m,
+                float* const* v, const int64_t* numel /*host*/, const int32_t* step_dev, float lr, float beta1,
+                float beta2, float eps, float weight_decay, void* stream);
+
+/* ------------------------------------------------------------------ projection (tcgen05 + TMA), see proj_tc.cu */
+int mmssl_split_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo, int64_t ldo,
+                     void* stream);
+/* transposed split: hi/lo [cols][ldo] from x [rows][cols] (optionally multiplied by mask [rows][cols]) */
+int mmssl_split_bf16_t(const float* x, int64_t ldx, const float* mask, int64_t ldm, int64_t rows, int64_t cols,
+                       uint16_t* hi, uint16_t* lo, int64_t ldo, void* stream);
+int64_t mmssl_gemm_bf16x3_workspace_floats(int64_t m, int64_t n, int64_t k, int* split_k_out);
+/* partial[s][m][n] (fp32) = sum over the s-th K slice of (Ahi+Alo)[m,k] * (Bhi+Blo)[n,k]  (lo*lo dropped).
+ * A: [m][lda] bf16 K-major, B: [n][ldb] bf16 K-major; n in {64,128,256}. */
+int mmssl_gemm_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi,
+                      const uint16_t* b_lo, int64_t ldb, int64_t m, int64_t n, int64_t k, int split_k, float* partial,
+                      void* stream);
+/* y[m][ldy + col_off] = (sum_s partial[s][m][n] + bias[n]) * mask[m][n]     (bias / mask may be NULL) */
+int mmssl_proj_epilogue(const float* partial, int split_k, int64_t m, int64_t n, const float* bias, const float* mask,
+                        int64_t ldm, float* y, int64_t ldy, float* y_pre, int64_t ldyp, void* stream);
+/* dw[n][ldw] (+)= sum_s partial[s][m][n]^T  (m = feature dim, n = embed dim) */
+int mmssl_wgrad_epilogue(const float* partial, int split_k, int64_t m, int64_t n, float* dw, int64_t ldw, int accumulate,
+                         void* stream);
+/* column sums: db[n] (+)= sum_rows (g * mask)[rows][n] */
+int mmssl_colsum(const float* g, int64_t ldg, const float* mask, int64_t ldm, int64_t rows, int n, float* out,
+                 int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMSSL_B200_H */

@@ -1,0 +1,140 @@
+"""ctypes binding of libmmssl_b200.so (the C ABI declared in include/mmssl_b200.h).
+
+This is the "reference-side binding" of the drop-in: the reference is Python, so the FFI a
+maintainer would add is this ctypes stub.  The library is the ONLY compute back-end: if it is
+missing, or the device is not a B200, loading fails loudly -- there is no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmssl_b200.so")
+
+c_i64, c_i32, c_f32, c_vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
+
+
+class CsrDesc(C.Structure):
+    """mmssl_csr_t"""
+    _fields_ = [("rowptr", c_vp), ("colidx", c_vp), ("vals", c_vp),
+                ("n_rows", c_i64), ("n_cols", c_i64), ("nnz", c_i64),
+                ("items", c_vp), ("n_items", c_i64), ("split_table", c_vp), ("counters", c_vp),
+                ("segs_cap", c_i64), ("seg_len", C.c_int32)]
+
+
+class SpmmRhs(C.Structure):
+    """mmssl_spmm_rhs_t"""
+    _fields_ = [("x", c_vp), ("ldx", c_i64), ("y", c_vp), ("ldy", c_i64), ("c", c_vp), ("ldc", c_i64),
+                ("ysaved", c_vp), ("ldysaved", c_i64), ("s", c_vp), ("lds", c_i64), ("sbase", c_vp), ("ldsbase", c_i64)]
+
+
+_SIGS = {
+    "mmssl_abi_version": (C.c_int, []),
+    "mmssl_last_error": (C.c_char_p, []),
+    "mmssl_device_check": (C.c_int, []),
+    "mmssl_csr_workspace_bytes": (c_i64, [c_i64, c_i64]),
+    "mmssl_csr_from_coo": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "mmssl_csr_row_normalize": (C.c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "mmssl_spmm_plan_items_cap": (c_i64, [c_i64, c_i64, c_i32]),
+    "mmssl_spmm_plan_splits_cap": (c_i64, [c_i64, c_i32]),
+    "mmssl_spmm_plan_segs_cap": (c_i64, [c_i64, c_i32]),
+    "mmssl_spmm_plan_workspace_bytes": (c_i64, [c_i64]),
+    "mmssl_spmm_plan": (C.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "mmssl_spmm_csr_f32": (C.c_int, [C.POINTER(CsrDesc), c_i32, c_i32, C.POINTER(SpmmRhs), c_i32, c_f32, c_i32, c_vp,
+                                     c_i64, c_i32, c_vp]),
+    "mmssl_sgemm": (C.c_int, [c_i32, c_i32, c_i64, c_i64, c_i64, c_f32, c_vp, c_i64, c_vp, c_i64, c_f32, c_vp, c_i64,
+                              c_i32, c_vp]),
+    "mmssl_id_fuse_fwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "mmssl_id_fuse_bwd": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_i64, c_vp]),
+    "mmssl_combine_fwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_f32, c_f32, c_vp, c_i64,
+                                    c_vp, c_i64, c_vp]),
+    "mmssl_combine_partials": (c_i64, [c_i64, c_i32]),
+    "mmssl_combine_bwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i32,
+                                    c_f32, c_f32, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "mmssl_softmax_bwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_i64, c_vp]),
+    "mmssl_axpby": (C.c_int, [c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_f32, c_vp, c_i64, c_vp]),
+    "mmssl_mul_mask": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_vp, c_i64, c_vp]),
+    "mmssl_sumsq_blocks": (c_i64, [c_i64, c_i32]),
+    "mmssl_sumsq": (C.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp]),
+    "mmssl_bpr_blocks": (c_i64, [c_i64, c_i32]),
+    "mmssl_bpr": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_f32, c_vp,
+                            c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "mmssl_infonce_prepare": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mmssl_infonce_stats_floats": (c_i64, [c_i64]),
+    "mmssl_infonce_loss_blocks": (c_i64, [c_i64]),
+    "mmssl_infonce_stats": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mmssl_infonce_grad": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "mmssl_infonce_scatter": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "mmssl_loss_assemble": (C.c_int, [c_vp, c_i64, c_i64, c_f32, c_vp, c_i64, c_vp, c_i64, c_f32, c_vp, c_i64, c_vp,
+                                      c_i64, c_i64, c_f32, c_vp, c_vp]),
+    "mmssl_step_tick": (C.c_int, [c_vp, c_vp]),
+    "mmssl_adamw": (C.c_int, [c_i32, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp),
+                              C.POINTER(c_i64), c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp]),
+    "mmssl_split_bf16": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "mmssl_split_bf16_t": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "mmssl_gemm_bf16x3_workspace_floats": (c_i64, [c_i64, c_i64, c_i64, C.POINTER(c_i32)]),
+    "mmssl_gemm_bf16x3": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp]),
+    "mmssl_proj_epilogue": (C.c_int, [c_vp, c_i32, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "mmssl_wgrad_epilogue": (C.c_int, [c_vp, c_i32, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp]),
+    "mmssl_colsum": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_vp, c_i32, c_vp]),
+}
+
+_lib = None
+
+
+class MmsslLibraryError(RuntimeError):
+    pass
+
+
+def load(require_device: bool = False) -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built -- no fallback path exists."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MmsslLibraryError(
+                f"{LIB_PATH} is missing: build it with `python -m mmssl_b200.build` (nvcc, sm_100a). "
+                "mmssl_b200 has no CPU or eager-PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        missing = []
+        for name, (res, args) in _SIGS.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                missing.append(name)
+                continue
+            fn.restype = res
+            fn.argtypes = args
+        if missing:
+            raise MmsslLibraryError(f"{LIB_PATH} does not export: {missing}")
+        if lib.mmssl_abi_version() != 1:
+            raise MmsslLibraryError("ABI version mismatch between _lib.py and libmmssl_b200.so")
+        _lib = lib
+    if require_device:
+        if not torch.cuda.is_available():
+            raise MmsslLibraryError("mmssl_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        check(_lib.mmssl_device_check())
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGS.keys())
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = _lib.mmssl_last_error().decode() if _lib is not None else "?"
+        raise MmsslLibraryError(f"libmmssl_b200 call failed (rc={rc}): {msg}")
+
+
+def ptr(t) -> c_vp:
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return c_vp(0)
+    return c_vp(t.data_ptr())
+
+
+def stream() -> c_vp:
+    return c_vp(torch.cuda.current_stream().cuda_stream)

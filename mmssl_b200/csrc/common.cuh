@@ -1,0 +1,90 @@
+// Shared helpers for the mmssl_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace mmssl {
+
+// ---- error reporting (thread-local message, C-ABI functions return non-zero on failure) ----
+char* last_error_buffer();
+int fail(const char* where, const char* what);
+int fail_cuda(const char* where, cudaError_t e);
+
+#define MMSSL_REQUIRE(cond, msg)                                   \
+    do {                                                           \
+        if (!(cond)) return ::mmssl::fail(__func__, msg);          \
+    } while (0)
+
+#define MMSSL_CUDA(call)                                           \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return ::mmssl::fail_cuda(__func__, e__); \
+    } while (0)
+
+// Launch check that is legal during stream capture (no sync).
+#define MMSSL_LAUNCH_OK()                                          \
+    do {                                                           \
+        cudaError_t e__ = cudaPeekAtLastError();                   \
+        if (e__ != cudaSuccess) { cudaGetLastError(); return ::mmssl::fail_cuda(__func__, e__); } \
+    } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kNumSMs = 148;   // B200
+
+// ---- device helpers ----
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void fma4(float4& a, float s, const float4& x) {
+    a.x = fmaf(s, x.x, a.x); a.y = fmaf(s, x.y, a.y); a.z = fmaf(s, x.z, a.z); a.w = fmaf(s, x.w, a.w);
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 scale4(const float4& a, float s) {
+    return make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
+}
+__device__ __forceinline__ float max4(const float4& a) { return fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)); }
+
+// Reduction over a group of G consecutive lanes (G = 16 or 32) using a group-local mask.
+template <int G>
+__device__ __forceinline__ unsigned group_mask() {
+    if (G == 32) return 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    return ((1u << G) - 1u) << (lane & ~(unsigned)(G - 1));
+}
+template <int G>
+__device__ __forceinline__ float group_sum(float v, unsigned mask) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ float group_max(float v, unsigned mask) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o, G));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) { return group_sum<32>(v, 0xffffffffu); }
+
+// Block-wide sum for blockDim.x <= 1024 (result valid in thread 0).
+__device__ __forceinline__ float block_sum(float v, float* smem32) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) smem32[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? smem32[threadIdx.x] : 0.f;
+    if (w == 0) v = warp_sum(v);
+    return v;
+}
+
+}  // namespace mmssl

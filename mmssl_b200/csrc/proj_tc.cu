@@ -1,0 +1,316 @@
+// Projection GEMM on the 5th-gen tensor cores (tcgen05) fed by TMA, accumulators in TMEM.
+//
+//   partial[s][m][n] = sum_{k in slice s} (A_hi + A_lo)[m][k] * (B_hi + B_lo)[n][k]      (lo*lo dropped)
+//
+// replaces nn.Linear image_trans / text_trans forward (X = F W^T, Models.py:173-174) and its weight
+// gradient (dW^T = F^T dX, autograd of the same lines).  fp32 contract (1e-4 rel) is met with a
+// bf16 hi/lo operand split: three kind::f16 MMAs per product, fp32 accumulation in TMEM.  The
+// feature matrix is constant (Models.py:46-47), so its split (and its transposed split for the
+// weight gradient) is made once; both GEMMs then run the SAME K-major kernel.
+//
+// Shape of the work: HBM-bound (AI = 3*2*N/4 flop per byte of A at N = d), M is small (items) or
+// medium (feature dim) -> split-K so that >= 2 waves of CTAs pull from HBM; partials are reduced in
+// a fixed order by the epilogue kernels in proj_common.cu (deterministic, no float atomics).
+//
+// Kernel anatomy (one CTA = one 128 x N output tile of one K slice, 192 threads):
+//   warp 0  : TMA producer   (cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier complete_tx)
+//   warp 1  : TMEM alloc + single-thread tcgen05.mma issuer, tcgen05.commit frees smem stages
+//   warps 2-5: epilogue       (tcgen05.ld 32x32b -> registers -> 128-bit global stores)
+#include <cuda.h>
+
+#include "common.cuh"
+#include "../../include/mmssl_b200.h"
+
+namespace mmssl {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle span
+constexpr int kTileABytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr int kThreads = 192;
+constexpr int kKbPerSplitTarget = 8;              // 512 K-elements per CTA by default
+constexpr int kMaxSplit = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1u << 24)) __trap();   // never hang the GPU on a protocol bug
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "l"(hint) : "memory");
+}
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t saddr) {
+    // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major) |
+    // SBO>>4 [32,46) = 8 rows * 128 B | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // streamed operand (features)
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // operand shared by every CTA (weights)
+
+template <int N>
+struct GemmCfg {
+    static constexpr int kTileBBytes = N * kBlockK * 2;
+    static constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;
+    static constexpr int kStages = (N == 64) ? 4 : (N == 128 ? 3 : 2);
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
+                                       ((uint32_t)(kBlockM >> 4) << 24);   // F32 acc, BF16 x BF16, K-major both
+};
+
+template <int N>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                   float* __restrict__ partial, int M, int total_kb, int kb_per_split) {
+    using Cfg = GemmCfg<N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStages;
+    uint64_t* accum_bar = empty_bar + Cfg::kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, split = blockIdx.y;
+    const int kb0 = split * kb_per_split;
+    const int nkb = max(0, min(total_kb, kb0 + kb_per_split) - kb0);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_lo) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            mbar_init(accum_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % Cfg::kStages;
+                const uint32_t ph = (uint32_t)(i / Cfg::kStages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t* st = smem + s * Cfg::kStageBytes;
+                mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                const int kx = (kb0 + i) * kBlockK;
+                tma_load_2d(&tm_a_hi, &full_bar[s], st, kx, m_tile * kBlockM, kEvictFirst);
+                tma_load_2d(&tm_a_lo, &full_bar[s], st + kTileABytes, kx, m_tile * kBlockM, kEvictFirst);
+                tma_load_2d(&tm_b_hi, &full_bar[s], st + 2 * kTileABytes, kx, 0, kEvictLast);
+                tma_load_2d(&tm_b_lo, &full_bar[s], st + 2 * kTileABytes + Cfg::kTileBBytes, kx, 0, kEvictLast);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % Cfg::kStages;
+                const uint32_t ph = (uint32_t)(i / Cfg::kStages) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
+                const uint32_t a_lo = a_hi + kTileABytes;
+                const uint32_t b_hi = a_hi + 2 * kTileABytes;
+                const uint32_t b_lo = b_hi + Cfg::kTileBBytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint32_t off = k * 32;   // 16 bf16 = 32 bytes inside the 128-byte swizzle span
+                    const uint64_t dah = make_sw128_kmajor_desc(a_hi + off), dal = make_sw128_kmajor_desc(a_lo + off);
+                    const uint64_t dbh = make_sw128_kmajor_desc(b_hi + off), dbl = make_sw128_kmajor_desc(b_lo + off);
+                    umma_bf16(tmem_base, dah, dbh, Cfg::kIdesc, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16(tmem_base, dah, dbl, Cfg::kIdesc, 1u);
+                    umma_bf16(tmem_base, dal, dbh, Cfg::kIdesc, 1u);
+                }
+                umma_commit(&empty_bar[s]);   // frees the smem stage once the MMAs have read it
+            }
+            umma_commit(accum_bar);           // accumulator complete
+        }
+    } else {
+        const int q = warp & 3;               // TMEM lane quarter this warp may access
+        const int64_t row = (int64_t)m_tile * kBlockM + q * 32 + lane;
+        float* out = partial + ((int64_t)split * M + row) * N;
+        if (nkb > 0) {
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < N; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+                if (row < M) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        st4(out + c + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                     __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+                }
+            }
+        } else if (row < M) {
+            for (int c = 0; c < N; c += 4) st4(out + c, f4zero());
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(N) : "memory");
+    }
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, const uint16_t* base, int64_t rows, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    MMSSL_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(last_error_buffer(), 512, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld ld=%lld box=%d)", (int)r,
+                 (long long)rows, (long long)ld, box_rows);
+        return 3;
+    }
+    return 0;
+}
+
+static int choose_split(int64_t m, int64_t k) {
+    const int64_t total_kb = (k + kBlockK - 1) / kBlockK;
+    const int64_t m_tiles = (m + kBlockM - 1) / kBlockM;
+    int64_t split = (total_kb + kKbPerSplitTarget - 1) / kKbPerSplitTarget;
+    // enough CTAs for >= 2 waves, but never slices shorter than 2 k-blocks
+    while (m_tiles * split < 2 * kNumSMs && split * 2 <= total_kb && split < kMaxSplit) split *= 2;
+    if (split > kMaxSplit) split = kMaxSplit;
+    if (split > total_kb) split = total_kb;
+    if (split < 1) split = 1;
+    // make every slice non-empty
+    const int64_t per = (total_kb + split - 1) / split;
+    split = (total_kb + per - 1) / per;
+    return (int)split;
+}
+
+template <int N>
+static int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                       float* partial, int64_t m, int64_t k, int split_k, cudaStream_t st) {
+    using Cfg = GemmCfg<N>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MMSSL_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_done = true;
+    }
+    const int total_kb = (int)((k + kBlockK - 1) / kBlockK);
+    const int per = (total_kb + split_k - 1) / split_k;
+    dim3 grid((unsigned)((m + kBlockM - 1) / kBlockM), (unsigned)split_k);
+    gemm_bf16x3_kernel<N><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ah, al, bh, bl, partial, (int)m, total_kb, per);
+    MMSSL_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace mmssl
+
+using namespace mmssl;
+
+extern "C" int64_t mmssl_gemm_bf16x3_workspace_floats(int64_t m, int64_t n, int64_t k, int* split_k_out) {
+    const int split = choose_split(m, k);
+    if (split_k_out) *split_k_out = split;
+    return (int64_t)split * m * n;
+}
+
+extern "C" int mmssl_gemm_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi,
+                                 const uint16_t* b_lo, int64_t ldb, int64_t m, int64_t n, int64_t k, int split_k,
+                                 float* partial, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    MMSSL_REQUIRE(n == 64 || n == 128 || n == 256, "n (embedding width) must be 64, 128 or 256");
+    MMSSL_REQUIRE(m >= 1 && k >= 1 && m < (1ll << 31) && k < (1ll << 31), "bad m / k");
+    MMSSL_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= k && ldb >= k, "lda/ldb must be >= k and multiples of 8 (16-byte TMA strides)");
+    MMSSL_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(b_hi) && aligned16(b_lo) && aligned16(partial), "alignment");
+    const int total_kb = (int)((k + kBlockK - 1) / kBlockK);
+    MMSSL_REQUIRE(split_k >= 1 && split_k <= total_kb, "split_k out of range");
+    {
+        const int per = (total_kb + split_k - 1) / split_k;
+        MMSSL_REQUIRE((int64_t)per * (split_k - 1) < total_kb, "split_k leaves an empty K slice (use mmssl_gemm_bf16x3_workspace_floats)");
+    }
+    CUtensorMap ah, al, bh, bl;
+    if (int rc = make_map(&ah, a_hi, m, lda, kBlockM)) return rc;
+    if (int rc = make_map(&al, a_lo, m, lda, kBlockM)) return rc;
+    if (int rc = make_map(&bh, b_hi, n, ldb, (int)n)) return rc;
+    if (int rc = make_map(&bl, b_lo, n, ldb, (int)n)) return rc;
+    if (n == 64) return launch_gemm<64>(ah, al, bh, bl, partial, m, k, split_k, st);
+    if (n == 128) return launch_gemm<128>(ah, al, bh, bl, partial, m, k, split_k, st);
+    return launch_gemm<256>(ah, al, bh, bl, partial, m, k, split_k, st);
+}

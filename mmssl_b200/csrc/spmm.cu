@@ -1,0 +1,254 @@
+// CSR SpMM  Y_r = epilogue( A * X_r ),  r < nrhs  -- the propagation operator of the MMSSL hot
+// path (reference: MMSSL.mm / torch.sparse.mm, Models.py:69-73, and torch.mm(sparse, dense),
+// Models.py:203-208; the transposed products autograd derives from them use the CSR of A^T).
+//
+// B200 design (HBM / L2 bound sparse gather, no tensor cores):
+//  * one lane *group* (16 lanes for d=64, 32 lanes for d>=128) owns one work item = one row or one
+//    fixed-length segment of a long row (plan built by mmssl_spmm_plan); every lane owns one
+//    float4 column slice per right-hand side, so a neighbour row is fetched with one coalesced
+//    128-bit load per lane (256 B .. 1 KB contiguous per neighbour).
+//  * column indices / values of the row are loaded coalesced (one per lane) and broadcast with
+//    warp shuffles; 4 neighbour gathers per right-hand side are kept in flight per lane.
+//  * up to 3 right-hand sides share one pass over the sparsity pattern (e.g. image|text features),
+//    which divides the index traffic and the launch count.
+//  * long rows (power-law item degrees) are cut into segments handled by different groups; the
+//    last group to arrive sums the partials in segment order -> deterministic, no float atomics.
+//  * fused epilogues: + alpha*C[row], row softmax over d (last GCN layer, Models.py:203-204),
+//    softmax backward y*(g - <g,y>), running layer sum S (+)= out (Models.py:213-214).
+#include "common.cuh"
+#include "../../include/mmssl_b200.h"
+
+namespace mmssl {
+
+constexpr int kMaxRhs = MMSSL_SPMM_MAX_RHS;
+
+struct SpmmParams {
+    const int32_t* rowptr;
+    const int32_t* colidx;
+    const float* vals;
+    const int4* items;
+    int64_t n_items;
+    const int2* split_table;
+    int32_t* counters;
+    float* partials;
+    const float* x[kMaxRhs];  int64_t ldx[kMaxRhs];
+    float* y[kMaxRhs];        int64_t ldy[kMaxRhs];
+    const float* c[kMaxRhs];  int64_t ldc[kMaxRhs];   // optional addend (alpha * C[row])
+    const float* ys[kMaxRhs]; int64_t ldys[kMaxRhs];  // saved softmax output (softmax-backward epilogue)
+    float* s[kMaxRhs];        int64_t lds[kMaxRhs];   // optional running sum
+    const float* sb[kMaxRhs]; int64_t ldsb[kMaxRhs];  // s_mode 2: S = SB[row] + out
+    float alpha;
+    int epilogue;   // MMSSL_EPI_*
+    int s_mode;     // 0 none, 1: S += out, 2: S = SB + out
+    int has_c;
+    int seg_len;
+};
+
+// G lanes per group, C float4 chunks per lane per rhs (d = 4*G*C), R right-hand sides.
+template <int G, int C, int R>
+__global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
+    const unsigned gmask = group_mask<G>();
+    const int lane = threadIdx.x & (G - 1);
+    const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    int4 item = make_int4(-1, 0, 0, -1);
+    if (gid < p.n_items) item = __ldg(&p.items[gid]);
+    const int row = item.x;
+    if (row < 0) return;   // whole group exits together (items are per group)
+    const int begin = item.y, end = item.z;
+
+    float4 acc[R][C];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[r][c] = f4zero();
+
+    for (int base = begin; base < end; base += G) {
+        const int e = base + lane;
+        int c_l = 0;
+        float v_l = 0.f;
+        if (e < end) { c_l = __ldg(p.colidx + e); v_l = __ldg(p.vals + e); }
+        const int cnt = min(G, end - base);
+        for (int j = 0; j < cnt; j += 4) {
+            int cc[4];
+            float vv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                cc[k] = __shfl_sync(gmask, c_l, j + k, G);
+                vv[k] = __shfl_sync(gmask, v_l, j + k, G);
+            }
+            float4 xv[4][R][C];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool on = (j + k) < cnt;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float* xr = p.x[r] + (int64_t)cc[k] * p.ldx[r] + lane * 4;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) xv[k][r][c] = on ? ldg4(xr + c * (4 * G)) : f4zero();
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) fma4(acc[r][c], vv[k], xv[k][r][c]);
+        }
+    }
+
+    // ---- split rows: publish the partial, the last arriver reduces in segment order ----
+    if (item.w >= 0) {
+        const int2 st = __ldg(&p.split_table[item.w]);   // {first partial slot, #segments}
+        const int W = R * C * G * 4;
+        // a row's segments are laid out consecutively and all but the last are seg_len long
+        const int k = (begin - __ldg(p.rowptr + row)) / p.seg_len;
+        float* part = p.partials + ((int64_t)st.x + k) * W;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) st4(part + (r * C + c) * (4 * G) + lane * 4, acc[r][c]);
+        __threadfence();
+        __syncwarp(gmask);
+        int old = 0;
+        if (lane == 0) old = atomicAdd(p.counters + item.w, 1);
+        old = __shfl_sync(gmask, old, 0, G);
+        if (old != st.y - 1) return;
+        __threadfence();
+        if (lane == 0) p.counters[item.w] = 0;   // self-cleaning for the next launch
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[r][c] = f4zero();
+        for (int s = 0; s < st.y; ++s) {
+            const float* ps = p.partials + ((int64_t)st.x + s) * W;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    acc[r][c] = add4(acc[r][c], ldcg4(ps + (r * C + c) * (4 * G) + lane * 4));
+        }
+    }
+
+    // ---- epilogue ----
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t col0 = lane * 4;
+        if (p.has_c && p.c[r] != nullptr) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float4 cv = ld4(p.c[r] + (int64_t)row * p.ldc[r] + col0 + c * (4 * G));   // may alias Y
+                fma4(acc[r][c], p.alpha, cv);
+            }
+        }
+        if (p.epilogue == MMSSL_EPI_SOFTMAX) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < C; ++c) m = fmaxf(m, max4(acc[r][c]));
+            m = group_max<G>(m, gmask);
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                acc[r][c].x = __expf(acc[r][c].x - m); acc[r][c].y = __expf(acc[r][c].y - m);
+                acc[r][c].z = __expf(acc[r][c].z - m); acc[r][c].w = __expf(acc[r][c].w - m);
+                sum += (acc[r][c].x + acc[r][c].y) + (acc[r][c].z + acc[r][c].w);
+            }
+            sum = group_sum<G>(sum, gmask);
+            const float inv = 1.f / sum;
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[r][c] = scale4(acc[r][c], inv);
+        } else if (p.epilogue == MMSSL_EPI_SOFTMAX_BWD) {
+            float4 yv[C];
+            float dotp = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                yv[c] = ldg4(p.ys[r] + (int64_t)row * p.ldys[r] + col0 + c * (4 * G));
+                dotp += dot4(acc[r][c], yv[c]);
+            }
+            dotp = group_sum<G>(dotp, gmask);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                acc[r][c].x = yv[c].x * (acc[r][c].x - dotp); acc[r][c].y = yv[c].y * (acc[r][c].y - dotp);
+                acc[r][c].z = yv[c].z * (acc[r][c].z - dotp); acc[r][c].w = yv[c].w * (acc[r][c].w - dotp);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) st4(p.y[r] + (int64_t)row * p.ldy[r] + col0 + c * (4 * G), acc[r][c]);
+        if (p.s_mode != 0 && p.s[r] != nullptr) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float* sp = p.s[r] + (int64_t)row * p.lds[r] + col0 + c * (4 * G);
+                const float4 prev = (p.s_mode == 1) ? ld4(sp)
+                                                    : ldg4(p.sb[r] + (int64_t)row * p.ldsb[r] + col0 + c * (4 * G));
+                st4(sp, add4(prev, acc[r][c]));
+            }
+        }
+    }
+}
+
+template <int G, int C, int R>
+static int launch_spmm(const SpmmParams& p, cudaStream_t stream) {
+    const int T = 256;
+    const int64_t groups_per_block = T / G;
+    const int64_t blocks = (p.n_items + groups_per_block - 1) / groups_per_block;
+    if (blocks == 0) return 0;
+    if (blocks > 0x7fffffffll) return fail("mmssl_spmm_csr_f32", "grid too large");
+    spmm_csr_kernel<G, C, R><<<(unsigned)blocks, T, 0, stream>>>(p);
+    MMSSL_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace mmssl
+
+using namespace mmssl;
+
+extern "C" int mmssl_spmm_csr_f32(const mmssl_csr_t* a, int d, int nrhs, const mmssl_spmm_rhs_t* rhs,
+                                  int epilogue, float alpha, int s_mode, float* partials, int64_t partials_floats,
+                                  int impl, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MMSSL_REQUIRE(a != nullptr && rhs != nullptr, "null argument");
+    MMSSL_REQUIRE(nrhs >= 1 && nrhs <= kMaxRhs, "nrhs must be 1..3");
+    MMSSL_REQUIRE(d == 64 || d == 128 || d == 256, "embedding width must be 64, 128 or 256");
+    MMSSL_REQUIRE(epilogue >= MMSSL_EPI_NONE && epilogue <= MMSSL_EPI_SOFTMAX_BWD, "bad epilogue");
+    MMSSL_REQUIRE(s_mode >= 0 && s_mode <= 2, "bad s_mode");
+    MMSSL_REQUIRE(a->n_items >= 0 && a->items != nullptr && a->seg_len >= 32, "missing work plan");
+    MMSSL_REQUIRE(a->segs_cap * (int64_t)nrhs * d <= partials_floats || a->segs_cap == 0,
+                  "partials buffer too small for the split rows");
+    SpmmParams p;
+    memset(&p, 0, sizeof(p));
+    p.rowptr = a->rowptr; p.colidx = a->colidx; p.vals = a->vals;
+    p.items = (const int4*)a->items; p.n_items = a->n_items;
+    p.split_table = (const int2*)a->split_table; p.counters = a->counters; p.partials = partials;
+    p.alpha = alpha; p.epilogue = epilogue; p.s_mode = s_mode; p.seg_len = a->seg_len;
+    for (int r = 0; r < nrhs; ++r) {
+        const mmssl_spmm_rhs_t& q = rhs[r];
+        MMSSL_REQUIRE(q.x && q.y, "null X or Y");
+        MMSSL_REQUIRE(aligned16(q.x) && aligned16(q.y) && q.ldx % 4 == 0 && q.ldy % 4 == 0, "X/Y must be 16-byte aligned with ld % 4 == 0");
+        p.x[r] = q.x; p.ldx[r] = q.ldx; p.y[r] = q.y; p.ldy[r] = q.ldy;
+        if (q.c) {
+            MMSSL_REQUIRE(aligned16(q.c) && q.ldc % 4 == 0, "C alignment");
+            p.c[r] = q.c; p.ldc[r] = q.ldc; p.has_c = 1;
+        }
+        if (epilogue == MMSSL_EPI_SOFTMAX_BWD) {
+            MMSSL_REQUIRE(q.ysaved && aligned16(q.ysaved) && q.ldysaved % 4 == 0, "softmax-backward epilogue needs ysaved");
+            p.ys[r] = q.ysaved; p.ldys[r] = q.ldysaved;
+        }
+        if (s_mode != 0 && q.s) {
+            MMSSL_REQUIRE(aligned16(q.s) && q.lds % 4 == 0, "S alignment");
+            p.s[r] = q.s; p.lds[r] = q.lds;
+            if (s_mode == 2) {
+                MMSSL_REQUIRE(q.sbase && aligned16(q.sbase) && q.ldsbase % 4 == 0, "s_mode 2 needs sbase");
+                p.sb[r] = q.sbase; p.ldsb[r] = q.ldsbase;
+            }
+        }
+    }
+#define MMSSL_SPMM_CASE(G, C)                                           \
+    switch (nrhs) {                                                     \
+        case 1: return launch_spmm<G, C, 1>(p, stream);                 \
+        case 2: return launch_spmm<G, C, 2>(p, stream);                 \
+        default: return launch_spmm<G, C, 3>(p, stream);                \
+    }
+    if (d == 64) { MMSSL_SPMM_CASE(16, 1) }
+    if (d == 128) { MMSSL_SPMM_CASE(32, 1) }
+    MMSSL_SPMM_CASE(32, 2)
+#undef MMSSL_SPMM_CASE
+}

@@ -1,0 +1,313 @@
+"""Forward / backward schedule of the MMSSL hot path on the CUDA library.
+
+Implements the closed form of ``MMSSL.forward`` (reference Models.py:171-220)
+and its hand-derived backward as an explicit sequence of library kernels.  No autograd inside:
+``functional.MMSSLForwardFn`` wraps it for the drop-in ``Models.MMSSL`` and ``hotstep.HotStep``
+drives it directly (fused with the loss kernels and AdamW, CUDA-graph captured).
+
+Launch inventory of one forward (K GCN layers, modality graphs aliasing ui/iu as at step 0,
+main.py:68-69):  2 projections x (split, GEMM, epilogue) + 2 two-RHS SpMM (image|text batched)
++ 2 id SpMM + 4 small GEMM/row kernels + 2K SpMM (softmax / layer-sum fused) + 2 combine kernels.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .graph import BipartiteGraph
+
+P_WV, P_BV, P_WT, P_BT = "image_trans.weight", "image_trans.bias", "text_trans.weight", "text_trans.bias"
+P_EU, P_EI, P_WCAT = "user_id_embedding.weight", "item_id_embedding.weight", "weight_dict.w_self_attention_cat"
+LIVE = (P_WV, P_BV, P_WT, P_BT, P_EU, P_EI, P_WCAT)
+
+
+class FeatureStore:
+    """Constant modality features (Models.py:46-47) prepared once for the tensor-core projection:
+    bf16 hi/lo split of F [I, D] (forward operand) and of F^T [D, I] (weight-gradient operand)."""
+
+    def __init__(self, feats: torch.Tensor, keep_fp32: bool = True):
+        assert feats.is_cuda and feats.dtype == torch.float32 and feats.dim() == 2
+        self.n_items, self.dim = feats.shape
+        self.hi, self.lo = ops.split_bf16(feats)            # [I, ceil8(D)]
+        self.t_hi, self.t_lo = ops.split_bf16_t(feats)      # [D, ceil8(I)]
+        self.fp32 = feats if keep_fp32 else None
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.hi, self.lo, self.t_hi, self.t_lo))
+
+
+@dataclass
+class FwdState:
+    graphs: tuple
+    masks: Optional[tuple]
+    X2: torch.Tensor
+    U2: torch.Tensor
+    I2: torch.Tensor
+    id_out: tuple                      # (Uvid, Utid, Ivid, Itid)
+    fused: bool
+    wsum: Optional[torch.Tensor] = None
+    zn_u: Optional[torch.Tensor] = None
+    nrm_u: Optional[torch.Tensor] = None
+    zn_i: Optional[torch.Tensor] = None
+    nrm_i: Optional[torch.Tensor] = None
+    u_last: Optional[torch.Tensor] = None   # softmax outputs of the last GCN layer
+    i_last: Optional[torch.Tensor] = None
+    sumsq_u: Optional[torch.Tensor] = None  # per-block sum(Uv^2+Ut^2) / (Iv^2+It^2) for feat_reg
+    sumsq_i: Optional[torch.Tensor] = None
+
+
+def _same(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return a.data_ptr() == b.data_ptr() and a.shape == b.shape and a.stride() == b.stride()
+
+
+class Engine:
+    def __init__(self, embed_size: int, n_layers: int, head_num: int = 4, id_cat_rate: float = 0.36,
+                 model_cat_rate: float = 0.55, proj_impl: str = "tc"):
+        if embed_size not in (64, 128, 256):
+            raise ValueError("mmssl_b200 kernels are built for embed_size 64, 128 or 256")
+        self.d, self.K, self.H = embed_size, n_layers, head_num
+        self.id_rate, self.cat_rate = id_cat_rate, model_cat_rate
+        self.proj_impl = proj_impl
+        self._tile_id: Dict[Tuple, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _tile(self, dev) -> torch.Tensor:
+        """[d, H*d] = H identities side by side:  Wsum = T @ Wcat,  dWcat = T^T @ dWsum."""
+        key = (dev.type, dev.index)
+        t = self._tile_id.get(key)
+        if t is None:
+            t = torch.eye(self.d, device=dev, dtype=torch.float32).repeat(1, self.H).contiguous()
+            self._tile_id[key] = t
+        return t
+
+    def _new(self, *shape, dev):
+        return torch.empty(*shape, dtype=torch.float32, device=dev)
+
+    # ------------------------------------------------------------------ projection
+    def _project(self, w, b, fs: FeatureStore, mask, y, y_pre=None):
+        I, d, D = fs.n_items, self.d, fs.dim
+        if self.proj_impl == "tc":
+            w_hi, w_lo = ops.split_bf16(w)
+            floats, sk = ops.gemm_bf16x3_plan(I, d, D)
+            part = self._new(floats, dev=y.device)
+            ops.gemm_bf16x3(fs.hi, fs.lo, w_hi, w_lo, I, d, D, sk, part)
+        else:
+            if fs.fp32 is None:
+                raise RuntimeError("proj_impl='simt' needs the fp32 features (keep_fp32=True)")
+            sk = 1
+            part = self._new(I, d, dev=y.device)
+            ops.sgemm(fs.fp32, w, part, trans_b=True)
+        ops.proj_epilogue(part, sk, I, d, b, mask, y, y_pre)
+
+    def _project_bwd(self, gx, mask, fs: FeatureStore, dw, db):
+        """dW[d,D] = (gx*mask)^T F ; db = colsum(gx*mask)."""
+        I, d, D = fs.n_items, self.d, fs.dim
+        if self.proj_impl == "tc":
+            g_hi, g_lo = ops.split_bf16_t(gx, mask, ldo=fs.t_hi.shape[1])   # [d, ceil8(I)]
+            floats, sk = ops.gemm_bf16x3_plan(D, d, I)
+            part = self._new(floats, dev=gx.device)
+            ops.gemm_bf16x3(fs.t_hi, fs.t_lo, g_hi, g_lo, D, d, I, sk, part)
+            ops.wgrad_epilogue(part, sk, D, d, dw)
+        else:
+            gm = self._new(I, d, dev=gx.device)
+            ops.mul_mask(gx, mask, gm)
+            ops.sgemm(gm, fs.fp32, dw, trans_a=True)
+        ops.colsum(gx, mask, db)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, P: Dict[str, torch.Tensor], feats: Tuple[FeatureStore, FeatureStore],
+                graphs: Sequence[BipartiteGraph], masks: Optional[Tuple[torch.Tensor, torch.Tensor]],
+                want_sumsq: bool = True):
+        g_ui, g_iu, g_vui, g_viu, g_tui, g_tiu = graphs
+        U, I = g_ui.shape
+        d, K = self.d, self.K
+        e_u, e_i = P[P_EU], P[P_EI]
+        dev = e_u.device
+        X2, U2, I2 = self._new(I, 2 * d, dev=dev), self._new(U, 2 * d, dev=dev), self._new(I, 2 * d, dev=dev)
+        xv, xt = X2[:, :d], X2[:, d:]
+        uv, ut = U2[:, :d], U2[:, d:]
+        iv, it = I2[:, :d], I2[:, d:]
+        self._project(P[P_WV], P[P_BV], feats[0], masks[0] if masks else None, xv)     # Models.py:173
+        self._project(P[P_WT], P[P_BT], feats[1], masks[1] if masks else None, xt)     # Models.py:174
+        ops.spmm(g_ui.fwd, [xv, xt], [uv, ut])                                         # :177,182
+        ops.spmm(g_iu.fwd, [uv, ut], [iv, it])                                         # :178,183
+
+        def id_prop(ga, gb, e, rows):                                                  # :179-180,185-186
+            def one(g):
+                if g.nnz == 0:
+                    return torch.zeros(rows, d, dtype=torch.float32, device=dev)
+                return ops.spmm(g.fwd, [e])[0]
+            ya = one(ga)
+            return (ya, ya) if ga is gb else (ya, one(gb))
+
+        uvid, utid = id_prop(g_vui, g_tui, e_i, U)
+        ivid, itid = id_prop(g_viu, g_tiu, e_u, I)
+        st = FwdState(tuple(graphs), masks, X2, U2, I2, (uvid, utid, ivid, itid),
+                      fused=any(g.nnz > 0 for g in (g_vui, g_viu, g_tui, g_tiu)))
+        if st.fused:                                                                   # :188-197 (closed form)
+            st.wsum = ops.sgemm(self._tile(dev), P[P_WCAT], self._new(d, d, dev=dev))
+
+            def fuse(ya, yb, e):
+                z = self._new(e.shape[0], d, dev=dev)
+                if ya is yb:
+                    ops.sgemm(ya, st.wsum, z)
+                else:
+                    ops.sgemm(ya, st.wsum, z, alpha=0.5)
+                    ops.sgemm(yb, st.wsum, z, alpha=0.5, beta=1.0)
+                out = self._new(e.shape[0], d, dev=dev)
+                return ops.id_fuse_fwd(z, e, self.id_rate, out)
+
+            u0, st.zn_u, st.nrm_u = fuse(uvid, utid, e_u)
+            i0, st.zn_i, st.nrm_i = fuse(ivid, itid, e_i)
+        else:
+            u0, i0 = e_u, e_i
+        # GCN layers: u_{k+1} = A_ui i_k ; i_{k+1} = A_iu u_{k+1}; softmax on the last one (:201-211);
+        # the layer sums S_u, S_i accumulate in the SpMM epilogue (:213-214)
+        s_u, s_i = self._new(U, d, dev=dev), self._new(I, d, dev=dev)
+        cur_i = i0
+        if K == 0:
+            ops.axpby(u0, 1.0, 0.0, s_u)
+            ops.axpby(i0, 1.0, 0.0, s_i)
+        for k in range(K):
+            last = k == K - 1
+            epi = ops.EPI_SOFTMAX if last else ops.EPI_NONE
+            mode = 2 if k == 0 else 1
+            u_n = ops.spmm(g_ui.fwd, [cur_i], epilogue=epi, ss=[s_u], s_mode=mode, sbases=[u0] if k == 0 else None)[0]
+            i_n = ops.spmm(g_iu.fwd, [u_n], epilogue=epi, ss=[s_i], s_mode=mode, sbases=[i0] if k == 0 else None)[0]
+            if last:
+                st.u_last, st.i_last = u_n, i_n
+            cur_i = i_n
+        inv = 1.0 / (K + 1)
+        u_f, st.sumsq_u = ops.combine_fwd(s_u, uv, ut, inv, self.cat_rate, self._new(U, d, dev=dev), want_sumsq)   # :213,217
+        i_f, st.sumsq_i = ops.combine_fwd(s_i, iv, it, inv, self.cat_rate, self._new(I, d, dev=dev), want_sumsq)   # :214,218
+        outs = (u_f, i_f, iv, it, uv, ut, uvid, utid, ivid, itid)
+        return outs, st
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, st: FwdState, P: Dict[str, torch.Tensor], feats, grads: Sequence[Optional[torch.Tensor]],
+                 feat_reg_coef: float = 0.0, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """grads: d loss / d (u_f, i_f, Iv, It, Uv, Ut, Uvid, Utid, Ivid, Itid), entries may be None.
+        feat_reg_coef folds d(feat_reg)/d(Uv,Ut,Iv,It) = coef * x into the combine-backward kernel.
+        Returns gradients for the live parameters (written into `out` when given)."""
+        g_ui, g_iu, g_vui, g_viu, g_tui, g_tiu = st.graphs
+        U, I = g_ui.shape
+        d, K = self.d, self.K
+        dev = st.X2.device
+        inv = 1.0 / (K + 1)
+
+        def prep(g, rows):
+            if g is None:
+                return None
+            if g.dtype != torch.float32 or g.stride(1) != 1 or g.stride(0) % 4 or g.data_ptr() % 16:
+                g = g.contiguous().float()
+            assert g.shape == (rows, d)
+            return g
+
+        g_uf, g_if = prep(grads[0], U), prep(grads[1], I)
+        g_iv, g_it, g_uv, g_ut = prep(grads[2], I), prep(grads[3], I), prep(grads[4], U), prep(grads[5], U)
+        g_uvid, g_utid, g_ivid, g_itid = prep(grads[6], U), prep(grads[7], U), prep(grads[8], I), prep(grads[9], I)
+        if g_uf is None:
+            g_uf = torch.zeros(U, d, dtype=torch.float32, device=dev)
+        if g_if is None:
+            g_if = torch.zeros(I, d, dtype=torch.float32, device=dev)
+        res = out if out is not None else {}
+
+        def slot(name, like):
+            t = res.get(name)
+            if t is None:
+                t = torch.empty_like(like)
+                res[name] = t
+            return t
+
+        uv, ut = st.U2[:, :d], st.U2[:, d:]
+        iv, it = st.I2[:, :d], st.I2[:, d:]
+        # ---- combine backward (Models.py:213-218): through the two normalisations (+ feat_reg)
+        gU2, gI2 = self._new(U, 2 * d, dev=dev), self._new(I, 2 * d, dev=dev)
+        ops.combine_bwd(g_uf, uv, ut, g_uv, g_ut, self.cat_rate, feat_reg_coef, gU2[:, :d], gU2[:, d:])
+        ops.combine_bwd(g_if, iv, it, g_iv, g_it, self.cat_rate, feat_reg_coef, gI2[:, :d], gI2[:, d:])
+        # ---- GCN backward.  every u_k, i_k receives inv * g_uf / inv * g_if from the layer mean.
+        if K >= 1:
+            t = ops.softmax_bwd(st.i_last, g_if, inv, self._new(I, d, dev=dev))
+            for k in range(K - 1, -1, -1):
+                last = k == K - 1
+                tu = ops.spmm(g_iu.bwd, [t], cs=[g_uf], alpha=inv,
+                              epilogue=ops.EPI_SOFTMAX_BWD if last else ops.EPI_NONE,
+                              ysaved=[st.u_last] if last else None)[0]
+                t = ops.spmm(g_ui.bwd, [tu], cs=[g_if], alpha=inv)[0]
+            g_i0 = t                                            # d loss / d i_0
+        else:
+            g_i0 = ops.axpby(g_if, inv, 0.0, self._new(I, d, dev=dev))
+        # d loss / d u_0 = inv * g_uf (u_0 only feeds the layer mean)
+        g_eu = slot(P_EU, P[P_EU])
+        g_ei = slot(P_EI, P[P_EI])
+        ops.axpby(g_uf, inv, 0.0, g_eu)
+        if g_i0.data_ptr() != g_ei.data_ptr():
+            ops.axpby(g_i0, 1.0, 0.0, g_ei)
+        # ---- id fusion backward (Models.py:188-197)
+        uvid, utid, ivid, itid = st.id_out
+        g_wcat = slot(P_WCAT, P[P_WCAT])
+        if st.fused:
+            d_wsum = torch.zeros(d, d, dtype=torch.float32, device=dev)
+
+            def fuse_bwd(g0, zn, nrm, ya, yb, g_ya, g_yb, rows):
+                dz = ops.id_fuse_bwd(g0, zn, nrm, self.id_rate, self._new(rows, d, dev=dev))
+                sk = max(1, min(64, rows // 2048))
+                if ya is yb:
+                    ops.sgemm(ya, dz, d_wsum, trans_a=True, alpha=1.0, beta=1.0, split_k=sk)
+                    tot = self._new(rows, d, dev=dev)
+                    ops.sgemm(dz, st.wsum, tot, trans_b=True)                    # dz @ Wsum^T
+                    for g in (g_ya, g_yb):
+                        if g is not None:
+                            ops.axpby(g, 1.0, 1.0, tot)
+                    return tot, tot
+                ops.sgemm(ya, dz, d_wsum, trans_a=True, alpha=0.5, beta=1.0, split_k=sk)
+                ops.sgemm(yb, dz, d_wsum, trans_a=True, alpha=0.5, beta=1.0, split_k=sk)
+                ta = self._new(rows, d, dev=dev)
+                ops.sgemm(dz, st.wsum, ta, trans_b=True, alpha=0.5)
+                tb = ta
+                if g_ya is not None or g_yb is not None:
+                    tb = ta.clone() if g_yb is not None or g_ya is not None else ta
+                    if g_ya is not None:
+                        ops.axpby(g_ya, 1.0, 1.0, ta)
+                    if g_yb is not None:
+                        ops.axpby(g_yb, 1.0, 1.0, tb)
+                return ta, tb
+
+            gt_uvid, gt_utid = fuse_bwd(g_eu, st.zn_u, st.nrm_u, uvid, utid, g_uvid, g_utid, U)
+            gt_ivid, gt_itid = fuse_bwd(g_ei, st.zn_i, st.nrm_i, ivid, itid, g_ivid, g_itid, I)
+            ops.sgemm(self._tile(dev), d_wsum, g_wcat, trans_a=True)            # dWcat[h] = dWsum for every head
+        else:
+            g_wcat.zero_()
+            gt_uvid, gt_utid, gt_ivid, gt_itid = g_uvid, g_utid, g_ivid, g_itid
+
+        def id_prop_bwd(ga, gb, gya, gyb, g_e, same_out):
+            # E-gradient += A^T g  for each modality graph (same_out: both modalities share graph and output)
+            if ga is gb:
+                if ga.nnz == 0:
+                    return
+                if same_out and gya is not None:
+                    ops.spmm(ga.bwd, [gya], [g_e], cs=[g_e], alpha=1.0)
+                    return
+                for g in (gya, gyb):
+                    if g is not None:
+                        ops.spmm(ga.bwd, [g], [g_e], cs=[g_e], alpha=1.0)
+                return
+            for gr, g in ((ga, gya), (gb, gyb)):
+                if g is not None and gr.nnz > 0:
+                    ops.spmm(gr.bwd, [g], [g_e], cs=[g_e], alpha=1.0)
+
+        # Uvid = A_vui E_i, Utid = A_tui E_i -> gradient flows to E_i; Ivid/Itid -> E_u
+        id_prop_bwd(g_vui, g_tui, gt_uvid, gt_utid, g_ei, st.fused and uvid is utid)
+        id_prop_bwd(g_viu, g_tiu, gt_ivid, gt_itid, g_eu, st.fused and ivid is itid)
+        # ---- modality propagation backward (Models.py:177-178,182-183), image|text batched
+        ops.spmm(g_iu.bwd, [gI2[:, :d], gI2[:, d:]], [gU2[:, :d], gU2[:, d:]], cs=[gU2[:, :d], gU2[:, d:]], alpha=1.0)
+        gX2 = self._new(I, 2 * d, dev=dev)
+        ops.spmm(g_ui.bwd, [gU2[:, :d], gU2[:, d:]], [gX2[:, :d], gX2[:, d:]])
+        # ---- projection backward (dropout mask folded into the operand split)
+        m = st.masks
+        self._project_bwd(gX2[:, :d], m[0] if m else None, feats[0], slot(P_WV, P[P_WV]), slot(P_BV, P[P_BV]))
+        self._project_bwd(gX2[:, d:], m[1] if m else None, feats[1], slot(P_WT, P[P_WT]), slot(P_BT, P[P_BT]))
+        return res

@@ -1,0 +1,138 @@
+"""Prepared sparse operands for the SpMM operator.
+
+The reference hands ``MMSSL.forward`` six torch sparse COO tensors (int64 indices, fp32 values,
+flagged uncoalesced; built by ``matrix_to_tensor`` / ``sparse_mx_to_torch_sparse_tensor``,
+main.py:105-112, :513-520) and lets ATen re-coalesce and convert them on every ``torch.sparse.mm``.
+Here each distinct tensor is converted ONCE, on the device, into
+  * CSR of A     (forward products  A @ X),
+  * CSR of A^T   (backward products A^T @ dY; A_ui^T != A_iu because each side is normalised by
+                  its own row degree, main.py:66-67),
+  * an nnz-balanced work plan for each,
+and cached by tensor identity (the static ui/iu graphs live for the whole run; the modality graphs
+are rebuilt by the trainer and simply miss the cache).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import CsrDesc, ptr, stream
+
+SEG_LEN = 256
+
+
+class SparseOperand:
+    """CSR matrix + SpMM work plan living on one CUDA device."""
+
+    def __init__(self, rows: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, n_rows: int, n_cols: int,
+                 transpose: bool = False, seg_len: int = SEG_LEN):
+        lib = _lib.load(require_device=True)
+        dev = vals.device
+        nnz = int(vals.numel())
+        if transpose:
+            n_rows, n_cols = n_cols, n_rows
+        self.n_rows, self.n_cols, self.nnz, self.seg_len = int(n_rows), int(n_cols), nnz, seg_len
+        self.device = dev
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.rowptr = torch.empty(n_rows + 1, **i32)
+        self.colidx = torch.empty(max(nnz, 1), **i32)
+        self.vals = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+        ws_bytes = lib.mmssl_csr_workspace_bytes(nnz, n_rows)
+        if ws_bytes < 0:
+            raise _lib.MmsslLibraryError("mmssl_csr_workspace_bytes failed")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        rows = rows.contiguous()
+        cols = cols.contiguous()
+        vals = vals.contiguous().to(torch.float32)
+        _lib.check(lib.mmssl_csr_from_coo(ptr(rows), ptr(cols), ptr(vals), nnz, n_rows, n_cols, int(transpose),
+                                          ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), ptr(ws), ws_bytes, stream()))
+        # work plan
+        self.items_cap = lib.mmssl_spmm_plan_items_cap(n_rows, nnz, seg_len)
+        self.splits_cap = lib.mmssl_spmm_plan_splits_cap(nnz, seg_len)
+        self.segs_cap = lib.mmssl_spmm_plan_segs_cap(nnz, seg_len)
+        self.items = torch.empty(self.items_cap * 4, **i32)
+        self.split_table = torch.empty(self.splits_cap * 2, **i32)
+        self.counters = torch.empty(self.splits_cap, **i32)
+        self.totals = torch.empty(3, **i32)
+        pws_bytes = lib.mmssl_spmm_plan_workspace_bytes(n_rows)
+        pws = torch.empty(pws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.mmssl_spmm_plan(ptr(self.rowptr), n_rows, nnz, seg_len, ptr(self.items), self.items_cap,
+                                       ptr(self.split_table), ptr(self.counters), self.splits_cap, ptr(self.totals),
+                                       ptr(pws), pws_bytes, stream()))
+        self._keepalive = (ws, pws, rows, cols, vals)   # until the stream has consumed them
+        # without split rows the launch only needs n_rows items; with them we launch over the
+        # capacity (unused entries are row=-1).  Resolved lazily (first host read of `totals`).
+        self._n_items_exact: Optional[int] = None
+        self.desc = CsrDesc(ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), n_rows, n_cols, nnz, ptr(self.items),
+                            self.items_cap, ptr(self.split_table), ptr(self.counters), self.segs_cap, seg_len)
+
+    def tighten(self) -> None:
+        """Optional: read the exact item count back (one host sync) so launches are not padded."""
+        if self._n_items_exact is None:
+            t = self.totals.cpu()
+            self._n_items_exact = int(t[0])
+            self.n_split_rows, self.n_segs = int(t[1]), int(t[2])
+            self.desc.n_items = self._n_items_exact
+            self.desc.segs_cap = max(self.n_segs, 0)
+            self.segs_cap = self.n_segs
+            self._keepalive = ()
+
+    def to_scipy(self):
+        import numpy as np
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.vals[:self.nnz].cpu().numpy(), self.colidx[:self.nnz].cpu().numpy(),
+                              self.rowptr.cpu().numpy().astype(np.int64)), shape=(self.n_rows, self.n_cols))
+
+
+class BipartiteGraph:
+    """A and A^T prepared for SpMM.  ``fwd`` multiplies by A, ``bwd`` by A^T."""
+
+    def __init__(self, rows, cols, vals, shape: Tuple[int, int], tighten: bool = True):
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.nnz = int(vals.numel())
+        self.fwd = SparseOperand(rows, cols, vals, shape[0], shape[1], transpose=False)
+        self.bwd = SparseOperand(rows, cols, vals, shape[0], shape[1], transpose=True)
+        if tighten:
+            self.fwd.tighten()
+            self.bwd.tighten()
+
+    @classmethod
+    def from_torch_sparse(cls, t: torch.Tensor, tighten: bool = True) -> "BipartiteGraph":
+        if t.layout != torch.sparse_coo:
+            raise TypeError("expected a torch sparse COO tensor (as built by the reference's matrix_to_tensor)")
+        if not t.is_cuda:
+            raise _lib.MmsslLibraryError("graph tensors must live on the CUDA device; there is no CPU path")
+        idx = t._indices()
+        return cls(idx[0], idx[1], t._values(), tuple(t.shape), tighten=tighten)
+
+    @classmethod
+    def from_scipy(cls, mat, device="cuda", tighten: bool = True) -> "BipartiteGraph":
+        coo = mat.tocoo()
+        rows = torch.from_numpy(coo.row.astype("int64")).to(device)
+        cols = torch.from_numpy(coo.col.astype("int64")).to(device)
+        vals = torch.from_numpy(coo.data.astype("float32")).to(device)
+        return cls(rows, cols, vals, coo.shape, tighten=tighten)
+
+
+# ---- cache keyed by tensor identity -------------------------------------------------------------
+_cache: Dict[int, Tuple[weakref.ref, BipartiteGraph]] = {}
+
+
+def prepare(t) -> BipartiteGraph:
+    """BipartiteGraph for a torch sparse tensor (cached by object identity) or pass-through."""
+    if isinstance(t, BipartiteGraph):
+        return t
+    key = id(t)
+    hit = _cache.get(key)
+    if hit is not None and hit[0]() is t:
+        return hit[1]
+    g = BipartiteGraph.from_torch_sparse(t)
+    if len(_cache) > 64:   # drop entries whose tensors died
+        for k in [k for k, (r, _) in _cache.items() if r() is None]:
+            del _cache[k]
+    _cache[key] = (weakref.ref(t), g)
+    return g

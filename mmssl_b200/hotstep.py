@@ -1,0 +1,146 @@
+"""Fused hot training step: forward -> BPR + 2x InfoNCE + feat_reg (value and gradient seeds in the
+same kernels) -> hand-written backward -> multi-tensor AdamW, all on one stream with static buffers
+so the whole step is captured once into a CUDA graph and replayed (no Python / launch overhead in
+the steady state, no host synchronisation besides reading the loss).
+
+Reference unit of work: main.py:363-371 (forward + BPR), :408-414 (feat_reg, InfoNCE),
+:420 (loss without the GAN term), :427-429 (zero_grad / backward / AdamW step).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .engine import LIVE, P_EI, P_EU, Engine, FeatureStore
+from .graph import BipartiteGraph
+
+
+@dataclass
+class HotStepConfig:
+    embed_size: int = 64
+    n_layers: int = 2
+    head_num: int = 4
+    id_cat_rate: float = 0.36
+    model_cat_rate: float = 0.55
+    drop_rate: float = 0.2
+    tau: float = 0.5
+    cl_rate: float = 0.03
+    emb_decay: float = 1e-5
+    feat_reg_decay: float = 1e-5
+    batch_size: int = 1024          # the *configured* batch size the BPR regulariser divides by (main.py:504)
+    lr: float = 5.5e-4
+    weight_decay: float = 1e-2
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+    proj_impl: str = "tc"
+
+
+class HotStep:
+    def __init__(self, params: Dict[str, torch.Tensor], feats: Sequence[FeatureStore], graphs: Sequence[BipartiteGraph],
+                 cfg: HotStepConfig, batch: int, optimizer_step: bool = True):
+        self.cfg = cfg
+        self.P = {k: params[k] for k in LIVE}
+        for k, t in self.P.items():
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), k
+        self.feats, self.graphs = tuple(feats), tuple(graphs)
+        self.engine = Engine(cfg.embed_size, cfg.n_layers, cfg.head_num, cfg.id_cat_rate, cfg.model_cat_rate, cfg.proj_impl)
+        self.U, self.I = graphs[0].shape
+        self.batch = batch
+        self.optimizer_step = optimizer_step
+        dev = self.P[P_EU].device
+        d = cfg.embed_size
+        f = dict(dtype=torch.float32, device=dev)
+        self.idx = torch.zeros(3, batch, dtype=torch.int64, device=dev)     # users / pos / neg (static input)
+        self.g_uf, self.g_if = torch.zeros(self.U, d, **f), torch.zeros(self.I, d, **f)
+        self.alias_id = graphs[2] is graphs[4]
+        self.g_uvid = torch.zeros(self.U, d, **f)
+        self.g_utid = self.g_uvid if self.alias_id else torch.zeros(self.U, d, **f)
+        self.nce = [ops.InfoNCEWork(batch, d, dev) for _ in range(1 if self.alias_id else 2)]
+        self.cl_seed = torch.full((1,), cfg.cl_rate * (2.0 if self.alias_id else 1.0), **f)
+        self.out5 = torch.zeros(5, **f)
+        self.grads = {k: torch.zeros_like(t) for k, t in self.P.items()}
+        self.m = {k: torch.zeros_like(t) for k, t in self.P.items()}
+        self.v = {k: torch.zeros_like(t) for k, t in self.P.items()}
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.masks: Optional[tuple] = None          # injected dropout masks (tests); None -> torch RNG
+        self.training = True
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self.kernel_launches = 0
+
+    # ------------------------------------------------------------------ one step on the current stream
+    def _masks(self):
+        if not self.training or self.cfg.drop_rate <= 0:
+            return None
+        if self.masks is not None:
+            return self.masks
+        ones = torch.ones(self.I, self.cfg.embed_size, dtype=torch.float32, device=self.idx.device)
+        p = self.cfg.drop_rate
+        return (F.dropout(ones, p, True), F.dropout(ones, p, True))     # image first, like Models.py:173-174
+
+    def run(self) -> torch.Tensor:
+        """Executes one hot step with the indices currently in ``self.idx``; returns the device
+        tensor [total, mf, emb, feat_reg, cl]."""
+        cfg = self.cfg
+        users, pos, neg = self.idx[0], self.idx[1], self.idx[2]
+        self.g_uf.zero_(); self.g_if.zero_(); self.g_uvid.zero_()
+        if not self.alias_id:
+            self.g_utid.zero_()
+        outs, st = self.engine.forward(self.P, self.feats, self.graphs, self._masks(), want_sumsq=True)
+        u_f, i_f, _, _, _, _, u_vid, u_tid, _, _ = outs
+        reg_coef = cfg.emb_decay / cfg.batch_size
+        # BPR: value partials + gradient rows scattered straight into the dense table gradients
+        bpr_part, n_bpr = ops.bpr(u_f, i_f, i_f, users, pos, neg, mode=3, reg_coef=reg_coef,
+                                  g_u=self.g_uf, g_p=self.g_if, g_n=self.g_if)
+        # InfoNCE(Uvid[users], u_f[users]) + InfoNCE(Utid[users], u_f[users])   (main.py:411-412)
+        inv_tau = 1.0 / cfg.tau
+        parts = []
+        for w, z1, gz1 in zip(self.nce, (u_vid, u_tid), (self.g_uvid, self.g_utid)):
+            parts.append(ops.infonce_forward(z1, u_f, users, inv_tau, w, g_loss=self.cl_seed))
+            if st.fused:    # with empty modality graphs z1 == 0: the loss is a constant, all gradients vanish
+                ops.infonce_backward(users, inv_tau, w, gz1, self.g_uf)
+        nce1 = parts[0]
+        nce2 = parts[0] if self.alias_id else parts[1]
+        ops.loss_assemble(bpr_part, n_bpr, self.batch, reg_coef, st.sumsq_u, st.sumsq_i, 0.5 * cfg.feat_reg_decay / self.I,
+                          nce1, nce2, self.batch, cfg.cl_rate, self.out5)
+        grads = [self.g_uf, self.g_if, None, None, None, None,
+                 self.g_uvid if st.fused else None, (None if self.alias_id else self.g_utid) if st.fused else None, None, None]
+        self.engine.backward(st, self.P, self.feats, grads, feat_reg_coef=cfg.feat_reg_decay / self.I, out=self.grads)
+        if self.optimizer_step:
+            ops.step_tick(self.step_dev)
+            keys = list(LIVE)
+            ops.adamw([self.P[k] for k in keys], [self.grads[k] for k in keys], [self.m[k] for k in keys],
+                      [self.v[k] for k in keys], self.step_dev, cfg.lr, cfg.beta1, cfg.beta2, cfg.eps, cfg.weight_decay)
+        return self.out5
+
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self, warmup: int = 2) -> None:
+        """Capture ``run`` into a CUDA graph (static buffers; update ``self.idx`` between replays).
+        Warm-up steps run on a side stream first and DO advance the optimiser state."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.run()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self._graph = g
+
+    def replay(self) -> torch.Tensor:
+        if self._graph is None:
+            raise RuntimeError("call capture() first")
+        self._graph.replay()
+        return self.out5
+
+    def set_indices(self, users, pos, neg) -> None:
+        """Device-side copy of one batch of triples into the static index buffer."""
+        self.idx[0].copy_(torch.as_tensor(users, dtype=torch.int64), non_blocking=True)
+        self.idx[1].copy_(torch.as_tensor(pos, dtype=torch.int64), non_blocking=True)
+        self.idx[2].copy_(torch.as_tensor(neg, dtype=torch.int64), non_blocking=True)
