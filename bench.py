@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the MMSSL hot training step on B200 (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config baby] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): BPR-triples/sec of the hot step = 1x MMSSL.forward (train mode) + BPR +
+2x InfoNCE + feat_reg + backward + AdamW on a synthetic bipartite graph of the named shape, B = 1024
+triples per GPU per step.  Prints ONE JSON line (rank 0).
+
+  value     : whole-job triples/s, inputs resident in HBM (batch indices staged on the device),
+              K steps timed with CUDA events on the launching stream, max over ranks.
+  e2e       : the same through the public API `HotStepTrainer.train_step(users, pos, neg) -> loss`,
+              each step copying the batch from pinned host memory and reading the loss back.
+  roofline  : dominant kernel, algorithmic bytes / CUDA-event duration (measured here, cold L2)
+              vs the measured HBM peak in MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference : the oracle port of the reference's CPU path
+              (oracle/mmssl_oracle.py, stock torch CPU ops, all host threads) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BATCH = 1024
+METRIC = "bpr_triples_per_sec_hot_step"
+UNIT = "triples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="baby")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--proj", default="tc", choices=["tc", "simt"])
+    ap.add_argument("--spmm-impl", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--seed", type=int, default=2022)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_problem(name: str, seed: int, device):
+    """Synthetic dataset + parameters + prepared graphs on `device`."""
+    from mmssl_b200.engine import LIVE, FeatureStore
+    from mmssl_b200.graph import BipartiteGraph
+    from mmssl_b200.synthetic import make_dataset
+    ds = make_dataset(name, seed=seed)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    d = ds.embed_size
+
+    def xavier(r, c):
+        b = (6.0 / (r + c)) ** 0.5
+        return ((torch.rand(r, c, generator=g) * 2 - 1) * b)
+
+    P = {
+        "image_trans.weight": xavier(d, ds.dv), "image_trans.bias": (torch.rand(d, generator=g) * 2 - 1) / ds.dv ** 0.5,
+        "text_trans.weight": xavier(d, ds.dt), "text_trans.bias": (torch.rand(d, generator=g) * 2 - 1) / ds.dt ** 0.5,
+        "user_id_embedding.weight": xavier(ds.n_users, d), "item_id_embedding.weight": xavier(ds.n_items, d),
+        "weight_dict.w_self_attention_cat": xavier(4 * d, d),
+        "weight_dict.w_q": xavier(d, d), "weight_dict.w_k": xavier(d, d),
+    }
+    feats_cpu = (torch.randn(ds.n_items, ds.dv, generator=g), torch.randn(ds.n_items, ds.dt, generator=g))
+    if device is None:
+        return ds, P, feats_cpu, None, None
+    Pd = {k: v.to(device).contiguous() for k, v in P.items()}
+    feats = tuple(FeatureStore(f.to(device), keep_fp32=True) for f in feats_cpu)
+    g_ui = BipartiteGraph.from_scipy(ds.ui_norm, device=device)
+    g_iu = BipartiteGraph.from_scipy(ds.iu_norm, device=device)
+    graphs = (g_ui, g_iu, g_ui, g_iu, g_ui, g_iu)        # modality graphs alias ui/iu (state at step 0, main.py:68-69)
+    return ds, Pd, feats, graphs, feats_cpu
+
+
+class HotStepTrainer:
+    """Public API of the fused path: ``train_step(users, pos, neg) -> float loss`` (host in, host out)."""
+
+    def __init__(self, P, feats, graphs, cfg, batch, world=1):
+        from mmssl_b200.hotstep import HotStep
+        self.world = world
+        self.hs = HotStep(P, feats, graphs, cfg, batch=batch, optimizer_step=(world == 1))
+        self.pin_idx = torch.empty(3, batch, dtype=torch.int64).pin_memory()
+        self.pin_out = torch.empty(5, dtype=torch.float32).pin_memory()
+        if world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+            keys = list(self.hs.grads.keys())
+            flat = torch.zeros(sum(self.hs.grads[k].numel() for k in keys), dtype=torch.float32, device=self.hs.idx.device)
+            off = 0
+            for k in keys:       # point the persistent gradient buffers into one flat all-reduce bucket
+                n = self.hs.grads[k].numel()
+                self.hs.grads[k] = flat[off:off + n].view_as(self.hs.grads[k])
+                off += n
+            self.flat = flat
+        self.hs.capture(warmup=2)
+
+    def _finish_step(self):
+        if self.world > 1:
+            from mmssl_b200 import ops
+            from mmssl_b200.engine import LIVE
+            self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM)
+            self.flat.mul_(1.0 / self.world)
+            hs = self.hs
+            ops.step_tick(hs.step_dev)
+            keys = list(LIVE)
+            ops.adamw([hs.P[k] for k in keys], [hs.grads[k] for k in keys], [hs.m[k] for k in keys], [hs.v[k] for k in keys],
+                      hs.step_dev, hs.cfg.lr, hs.cfg.beta1, hs.cfg.beta2, hs.cfg.eps, hs.cfg.weight_decay)
+
+    def step_device(self, idx_dev):
+        """One step with the batch already on the device."""
+        self.hs.idx.copy_(idx_dev, non_blocking=True)
+        self.hs.replay()
+        self._finish_step()
+
+    def train_step(self, users, pos, neg) -> float:
+        self.pin_idx[0].copy_(torch.as_tensor(users)); self.pin_idx[1].copy_(torch.as_tensor(pos)); self.pin_idx[2].copy_(torch.as_tensor(neg))
+        self.hs.idx.copy_(self.pin_idx, non_blocking=True)
+        self.hs.replay()
+        self._finish_step()
+        self.pin_out.copy_(self.hs.out5, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.pin_out[0])
+
+
+def l2_flush(buf):
+    buf.add_(1.0)
+
+
+def time_kernel(fn, flush_buf, reps=7):
+    """Median CUDA-event duration (ms) of one launch of `fn` with a cold L2."""
+    ts = []
+    for _ in range(reps):
+        l2_flush(flush_buf)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+def roofline_objects(ds, P, feats, graphs, hbm_peak, peak_src, dev):
+    """Time the two kernel classes that dominate the step, in isolation and with a cold L2."""
+    from mmssl_b200 import ops
+    d, I, U, nnz = ds.embed_size, ds.n_items, ds.n_users, ds.nnz
+    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 192 MiB > 126 MB L2
+    out = {}
+    # --- projection GEMM (image modality, forward): tcgen05 + TMA, HBM-bound on reading F
+    fs = feats[0]
+    w_hi, w_lo = ops.split_bf16(P["image_trans.weight"])
+    floats, sk = ops.gemm_bf16x3_plan(I, d, fs.dim)
+    part = torch.empty(floats, dtype=torch.float32, device=dev)
+    ms = time_kernel(lambda: ops.gemm_bf16x3(fs.hi, fs.lo, w_hi, w_lo, I, d, fs.dim, sk, part), flush)
+    alg = 4 * I * fs.dim + 4 * d * fs.dim + 4 * I * d
+    gbs = alg / (ms * 1e-3) / 1e9
+    out["projection"] = {"kernel": "gemm_bf16x3_kernel<64> (image_trans forward, tcgen05+TMA)", "bound": "hbm",
+                         "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4),
+                         "algorithmic_bytes": alg, "ms": round(ms, 5), "split_k": sk, "peak_source": peak_src,
+                         "tflops_bf16_issued": round(3 * 2 * I * fs.dim * d / (ms * 1e-3) / 1e12, 2), "traffic": None}
+    # --- SpMM (ui-type propagation, 1 RHS, d=64)
+    x = torch.randn(I, d, device=dev)
+    y = torch.empty(U, d, device=dev)
+    ms = time_kernel(lambda: ops.spmm(graphs[0].fwd, [x], [y]), flush)
+    alg = 8 * nnz + 4 * (U + 1) + 4 * d * I + 4 * d * U
+    gather = 8 * nnz + 4 * (U + 1) + 4 * d * nnz + 4 * d * U
+    gbs = alg / (ms * 1e-3) / 1e9
+    out["spmm"] = {"kernel": "spmm_csr_kernel<16,1,1> (A_ui @ X, d=64)", "bound": "hbm", "achieved": round(gbs, 1),
+                   "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4), "algorithmic_bytes": alg,
+                   "gather_model_gbs_effective": round(gather / (ms * 1e-3) / 1e9, 1), "ms": round(ms, 5),
+                   "peak_source": peak_src, "traffic": None,
+                   "note": "compulsory bytes are %.1f MB: at HBM peak that is %.1f us, below launch latency -> latency-bound at this scale"
+                           % (alg / 1e6, alg / hbm_peak / 1e3)}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            t = json.load(open(tpath))
+            for k in out:
+                if k in t:
+                    out[k]["traffic"] = t[k]
+        except Exception:
+            pass
+    del flush
+    return out
+
+
+def cpu_baseline(name, seed, steps, batch):
+    """The oracle port of the reference's CPU path (stock torch CPU ops), all host threads."""
+    from oracle import mmssl_oracle as O
+    from mmssl_b200.synthetic import TripleSampler
+    ds, P, feats_cpu, _, _ = build_problem(name, seed, None)
+    torch.set_num_threads(os.cpu_count())
+    cfg = O.HotPathConfig(embed_size=ds.embed_size, n_layers=ds.n_layers, batch_size=batch)
+    ui, iu = O.to_torch_coo(ds.ui_norm), O.to_torch_coo(ds.iu_norm)
+    graphs = (ui, iu, ui, iu, ui, iu)
+    cpu = O.CpuHotStep(P, feats_cpu[0], feats_cpu[1], graphs, ds.n_items, cfg)
+    smp = TripleSampler(ds.train, seed=seed)
+    times = []
+    for i in range(steps + 1):
+        u, p, n = smp.sample(batch)
+        t0 = time.perf_counter()
+        cpu.step(u, p, n)
+        if i > 0:
+            times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    model = ""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return {"value": round(batch / med, 1), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} hot steps of config '{name}' (B={batch}) after 1 warm-up, median; min {min(times):.3f}s max {max(times):.3f}s",
+            "cpu_model": model, "os_cpu_count": os.cpu_count(), "s_per_step": round(med, 4)}
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from mmssl_b200.synthetic import CONFIGS
+    U, I, nnz, d, K, dv, dt = CONFIGS[a.config]
+    config = {"workload": f"{a.config}: synthetic bipartite {U}x{I}, {nnz} edges, d={d}, {K}-layer GCN, V{dv}/T{dt} features, "
+                          f"B={BATCH} triples per GPU per step, modality graphs alias ui/iu",
+              "global_batch": BATCH * max(world, 1), "parallelism": "single GPU" if world == 1 else f"dp{world} (replicated graph, gradient all-reduce)",
+              "l2_policy": "working set per step (%.0f MB of features) exceeds the 126 MB L2; isolated kernels timed after a 192 MiB L2 flush" % (4 * I * (dv + dt) / 1e6)}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_baseline(a.config, a.seed, max(a.steps, 1), BATCH)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": 1, "ms_per_step": round(cb["s_per_step"] * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from mmssl_b200 import _lib, ops
+    from mmssl_b200.hotstep import HotStepConfig
+    from mmssl_b200.synthetic import TripleSampler
+    _lib.load(require_device=True)
+    if a.spmm_impl is not None:
+        ops.set_default_spmm_impl(a.spmm_impl)
+
+    ds, P, feats, graphs, _ = build_problem(a.config, a.seed, dev)
+    cfg = HotStepConfig(embed_size=d, n_layers=K, batch_size=BATCH, proj_impl=a.proj)
+    trainer = HotStepTrainer(P, feats, graphs, cfg, BATCH, world=world)
+    smp = TripleSampler(ds.train, seed=a.seed + 17 * rank)
+    n_batches = a.steps + a.warmup
+    host_batches = [np.stack(smp.sample(BATCH)) for _ in range(n_batches)]
+    dev_batches = torch.from_numpy(np.stack(host_batches)).to(dev)               # [n, 3, B] resident in HBM
+
+    # launches per step (our kernels only): count one eager step that leaves the optimiser state alone
+    c0 = _lib.launch_count
+    saved = trainer.hs.optimizer_step
+    trainer.hs.optimizer_step = False
+    trainer.hs.run()
+    trainer.hs.optimizer_step = saved
+    launches_per_step = (_lib.launch_count - c0) + 2     # + step_tick + adamw
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- (A) device-resident timing
+    for w in range(a.warmup):
+        trainer.step_device(dev_batches[w])
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for s in range(a.steps):
+        trainer.step_device(dev_batches[a.warmup + s])
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---------------- (B) end to end through the public API (pinned host -> device, loss read back)
+    for w in range(min(3, a.warmup)):
+        trainer.train_step(*host_batches[w])
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    last_loss = 0.0
+    for s in range(a.steps):
+        last_loss = trainer.train_step(*host_batches[a.warmup + s])
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        roofs = roofline_objects(ds, P, feats, graphs, hbm_peak, peak_src, dev)
+        # the dominant kernel by time in the step: 4 projection-class GEMM launches vs (16 + 4K) SpMM launches
+        n_spmm = 2 * (4 + 2 * K)
+        t_proj = roofs["projection"]["ms"] * 2 * (1 + dt / dv)      # fwd + wgrad, image + text (bytes-scaled)
+        t_spmm = roofs["spmm"]["ms"] * n_spmm
+        dom = "projection" if t_proj >= t_spmm else "spmm"
+        roof = {k: roofs[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+        roof.update({"kernel": roofs[dom]["kernel"], "ms_per_launch": roofs[dom]["ms"], "peak_source": peak_src,
+                     "est_share_ms_per_step": {"projection": round(t_proj, 4), "spmm": round(t_spmm, 4)}})
+        total_triples = BATCH * world * a.steps
+        line = {"metric": METRIC, "value": round(total_triples / (ms_total * 1e-3), 1), "unit": UNIT, "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms_total / a.steps, 4), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "clocks": clk, "gpu_launches": launches_per_step * a.steps,
+                "e2e": {"value": round(total_triples / (ms_e2e * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": 3 * BATCH * 8,
+                        "d2h_bytes_per_step": 5 * 4, "ms_per_step": round(ms_e2e / a.steps, 4), "last_loss": round(last_loss, 6)},
+                "roofline": roof, "roofline_spmm": roofs["spmm"], "roofline_projection": roofs["projection"],
+                "launches_per_step": launches_per_step}
+        if not a.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(a.config, a.seed, a.cpu_steps, BATCH)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -84,6 +84,32 @@ _SIGS = {
 
 _lib = None
 
+# kernels launched by one call of each entry point (for bench.py's gpu_launches claim)
+KERNELS_PER_CALL = {
+    "mmssl_csr_from_coo": 6, "mmssl_csr_row_normalize": 1, "mmssl_spmm_plan": 8, "mmssl_spmm_csr_f32": 1, "mmssl_sgemm": 1,
+    "mmssl_id_fuse_fwd": 1, "mmssl_id_fuse_bwd": 1, "mmssl_combine_fwd": 1, "mmssl_combine_bwd": 1, "mmssl_softmax_bwd": 1,
+    "mmssl_axpby": 1, "mmssl_mul_mask": 1, "mmssl_sumsq": 1, "mmssl_bpr": 1, "mmssl_infonce_prepare": 1,
+    "mmssl_infonce_stats": 2, "mmssl_infonce_grad": 1, "mmssl_infonce_scatter": 1, "mmssl_loss_assemble": 1,
+    "mmssl_step_tick": 1, "mmssl_adamw": 1, "mmssl_split_bf16": 1, "mmssl_split_bf16_t": 1, "mmssl_gemm_bf16x3": 1,
+    "mmssl_proj_epilogue": 1, "mmssl_wgrad_epilogue": 1, "mmssl_colsum": 1,
+}
+launch_count = 0
+call_log = None   # set to a list to record (name) of every kernel-launching call
+
+
+class _Counted:
+    __slots__ = ("fn", "name", "k")
+
+    def __init__(self, fn, name, k):
+        self.fn, self.name, self.k = fn, name, k
+
+    def __call__(self, *a):
+        global launch_count
+        launch_count += self.k
+        if call_log is not None:
+            call_log.append(self.name)
+        return self.fn(*a)
+
 
 class MmsslLibraryError(RuntimeError):
     pass
@@ -107,6 +133,8 @@ def load(require_device: bool = False) -> C.CDLL:
                 continue
             fn.restype = res
             fn.argtypes = args
+            if name in KERNELS_PER_CALL:
+                setattr(lib, name, _Counted(fn, name, KERNELS_PER_CALL[name]))
         if missing:
             raise MmsslLibraryError(f"{LIB_PATH} does not export: {missing}")
         if lib.mmssl_abi_version() != 1:
