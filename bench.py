@@ -43,7 +43,7 @@ UNIT = "triples/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="baby")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -338,12 +338,12 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- (A) device-resident timing
-    for w in range(a.warmup):
-        trainer.step_device(dev_batches[w])
-    clocks = ClockSampler(local)
-    barrier()
+    clocks = ClockSampler(local)      # samples from the warm-up through both timed regions
     if rank == 0:
         clocks.start()
+    for w in range(a.warmup):
+        trainer.step_device(dev_batches[w])
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -352,7 +352,6 @@ def main():
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    clk = clocks.stop() if rank == 0 else None
 
     # ---------------- (B) end to end through the public API (pinned host -> device, loss read back)
     for w in range(min(3, a.warmup)):
@@ -366,6 +365,7 @@ def main():
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    clk = clocks.stop() if rank == 0 else None
 
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e], device=dev)

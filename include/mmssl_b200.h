@@ -21,7 +21,6 @@ extern "C" {
 
 #define MMSSL_ABI_VERSION 1
 #define MMSSL_SPMM_MAX_RHS 3
-#define MMSSL_SPMM_SEG_LEN 256 /* default segment length for long rows */
 
 int mmssl_abi_version(void);
 const char* mmssl_last_error(void);
@@ -41,13 +40,14 @@ int mmssl_csr_from_coo(const int64_t* rows, const int64_t* cols, const float* va
 /* vals[e] *= (rowsum + 1e-8)^-1/2  -- csr_norm(mean_flag=True), main.py:89-103 */
 int mmssl_csr_row_normalize(const int32_t* rowptr, int64_t n_rows, float* vals, void* stream);
 
-/* nnz-balanced work plan: rows longer than 2*seg_len are cut into seg_len segments. */
-int64_t mmssl_spmm_plan_items_cap(int64_t n_rows, int64_t nnz, int seg_len);
-int64_t mmssl_spmm_plan_splits_cap(int64_t nnz, int seg_len);
-int64_t mmssl_spmm_plan_segs_cap(int64_t nnz, int seg_len);
+/* nnz-balanced work plan: rows longer than 64 non-zeros are cut into segments (32..512 long,
+ * growing with the row) that different lane groups process concurrently. */
+int64_t mmssl_spmm_plan_items_cap(int64_t n_rows, int64_t nnz);
+int64_t mmssl_spmm_plan_splits_cap(int64_t nnz);
+int64_t mmssl_spmm_plan_segs_cap(int64_t nnz);
 int64_t mmssl_spmm_plan_workspace_bytes(int64_t n_rows);
-int mmssl_spmm_plan(const int32_t* rowptr, int64_t n_rows, int64_t nnz, int seg_len, int32_t* items4 /*[items_cap][4]*/,
-                    int64_t items_cap, int32_t* split_table2 /*[splits_cap][2]*/, int32_t* counters /*[splits_cap]*/,
+int mmssl_spmm_plan(const int32_t* rowptr, int64_t n_rows, int64_t nnz, int32_t* items4 /*[items_cap][4]*/,
+                    int64_t items_cap, int32_t* split_table4 /*[splits_cap][4]*/, int32_t* counters /*[splits_cap]*/,
                     int64_t splits_cap, int32_t* totals3, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* host descriptor of a prepared sparse operand */
@@ -58,10 +58,9 @@ typedef struct {
     int64_t n_rows, n_cols, nnz;
     const int32_t* items; /* work plan, [n_items][4] = {row, begin, end, split or -1}; row<0 = unused */
     int64_t n_items;      /* capacity actually launched over */
-    const int32_t* split_table;
+    const int32_t* split_table; /* [n_split_rows][4] = {first partial slot, #segments, segment length, 0} */
     int32_t* counters;
     int64_t segs_cap; /* partial-sum slots the plan may use */
-    int32_t seg_len;
 } mmssl_csr_t;
 
 /* ------------------------------------------------------------------ SpMM (the propagation operator)

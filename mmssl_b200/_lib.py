@@ -22,7 +22,7 @@ class CsrDesc(C.Structure):
     _fields_ = [("rowptr", c_vp), ("colidx", c_vp), ("vals", c_vp),
                 ("n_rows", c_i64), ("n_cols", c_i64), ("nnz", c_i64),
                 ("items", c_vp), ("n_items", c_i64), ("split_table", c_vp), ("counters", c_vp),
-                ("segs_cap", c_i64), ("seg_len", C.c_int32)]
+                ("segs_cap", c_i64)]
 
 
 class SpmmRhs(C.Structure):
@@ -38,11 +38,11 @@ _SIGS = {
     "mmssl_csr_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "mmssl_csr_from_coo": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "mmssl_csr_row_normalize": (C.c_int, [c_vp, c_i64, c_vp, c_vp]),
-    "mmssl_spmm_plan_items_cap": (c_i64, [c_i64, c_i64, c_i32]),
-    "mmssl_spmm_plan_splits_cap": (c_i64, [c_i64, c_i32]),
-    "mmssl_spmm_plan_segs_cap": (c_i64, [c_i64, c_i32]),
+    "mmssl_spmm_plan_items_cap": (c_i64, [c_i64, c_i64]),
+    "mmssl_spmm_plan_splits_cap": (c_i64, [c_i64]),
+    "mmssl_spmm_plan_segs_cap": (c_i64, [c_i64]),
     "mmssl_spmm_plan_workspace_bytes": (c_i64, [c_i64]),
-    "mmssl_spmm_plan": (C.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "mmssl_spmm_plan": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "mmssl_spmm_csr_f32": (C.c_int, [C.POINTER(CsrDesc), c_i32, c_i32, C.POINTER(SpmmRhs), c_i32, c_f32, c_i32, c_vp,
                                      c_i64, c_i32, c_vp]),
     "mmssl_sgemm": (C.c_int, [c_i32, c_i32, c_i64, c_i64, c_i64, c_f32, c_vp, c_i64, c_vp, c_i64, c_f32, c_vp, c_i64,

@@ -82,44 +82,51 @@ static cudaError_t carve_csr_ws(int64_t nnz, int64_t n_rows, void* base, CsrWs* 
 }
 
 // ---------------------------------------------------------------- SpMM work plan
-// item = {row, begin, end, split}: split = -1 -> the item covers the whole row; otherwise the
-// index of the row in the split-row table (the row is cut into segments of `seg_len` non-zeros
-// that different lane groups process; the last one to finish reduces the partial sums in
-// segment order, so results are deterministic).
-__global__ void plan_count_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, int seg_len, int split_thr,
+// item = {row, begin, end, split}: split = -1 -> the item covers the whole row (<= kSplitThreshold
+// non-zeros); otherwise the index of the row in the split-row table {first partial slot, #segments,
+// segment length, 0}.  Long rows are cut into segments that different lane groups process
+// concurrently (the critical path of a small graph is its longest serial row walk); the last group
+// to finish reduces the partial sums in segment order, so results stay deterministic.
+__host__ __device__ __forceinline__ int plan_seg_len(int len) {
+    return len <= 1024 ? 32 : (len <= 4096 ? 64 : (len <= 16384 ? 128 : (len <= 65536 ? 256 : 512)));
+}
+constexpr int kSplitThreshold = 64;
+
+__global__ void plan_count_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows,
                                   int32_t* __restrict__ n_items, int32_t* __restrict__ is_split,
                                   int32_t* __restrict__ n_segs) {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     const int len = rowptr[r + 1] - rowptr[r];
-    const bool split = len > split_thr;
-    const int segs = split ? (len + seg_len - 1) / seg_len : 0;
+    const bool split = len > kSplitThreshold;
+    const int sl = plan_seg_len(len);
+    const int segs = split ? (len + sl - 1) / sl : 0;
     n_items[r] = split ? segs : 1;
     is_split[r] = split ? 1 : 0;
     n_segs[r] = segs;
 }
 
-__global__ void plan_fill_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, int seg_len,
+__global__ void plan_fill_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows,
                                  const int32_t* __restrict__ item_off, const int32_t* __restrict__ split_off,
                                  const int32_t* __restrict__ seg_off, const int32_t* __restrict__ is_split,
-                                 int4* __restrict__ items, int2* __restrict__ split_table, int32_t* __restrict__ totals) {
+                                 int4* __restrict__ items, int4* __restrict__ split_table, int32_t* __restrict__ totals) {
     const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= n_rows) return;
     const int b = rowptr[r], e = rowptr[r + 1];
+    const int sl = plan_seg_len(e - b);
+    const int segs = is_split[r] ? (e - b + sl - 1) / sl : 0;
     if (!is_split[r]) {
         if (lane == 0) items[item_off[r]] = make_int4((int)r, b, e, -1);
     } else {
-        const int segs = (e - b + seg_len - 1) / seg_len;
         const int s = split_off[r];
         for (int k = lane; k < segs; k += 32) {
-            const int sb = b + k * seg_len;
-            items[item_off[r] + k] = make_int4((int)r, sb, min(e, sb + seg_len), s);
+            const int sb = b + k * sl;
+            items[item_off[r] + k] = make_int4((int)r, sb, min(e, sb + sl), s);
         }
-        if (lane == 0) split_table[s] = make_int2(seg_off[r], segs);
+        if (lane == 0) split_table[s] = make_int4(seg_off[r], segs, sl, 0);
     }
     if (r == n_rows - 1 && lane == 0) {
-        const int segs = is_split[r] ? (e - b + seg_len - 1) / seg_len : 0;
         totals[0] = item_off[r] + (is_split[r] ? segs : 1);   // number of work items
         totals[1] = split_off[r] + is_split[r];               // number of split rows
         totals[2] = seg_off[r] + segs;                        // number of partial-sum slots
@@ -181,11 +188,9 @@ extern "C" int mmssl_csr_from_coo(const int64_t* rows, const int64_t* cols, cons
     return 0;
 }
 
-extern "C" int64_t mmssl_spmm_plan_items_cap(int64_t n_rows, int64_t nnz, int seg_len) {
-    return n_rows + (3 * nnz) / (2 * (int64_t)seg_len) + 2;
-}
-extern "C" int64_t mmssl_spmm_plan_splits_cap(int64_t nnz, int seg_len) { return nnz / (2 * (int64_t)seg_len) + 2; }
-extern "C" int64_t mmssl_spmm_plan_segs_cap(int64_t nnz, int seg_len) { return (3 * nnz) / (2 * (int64_t)seg_len) + 2; }
+extern "C" int64_t mmssl_spmm_plan_segs_cap(int64_t nnz) { return nnz / 32 + nnz / kSplitThreshold + 2; }
+extern "C" int64_t mmssl_spmm_plan_splits_cap(int64_t nnz) { return nnz / kSplitThreshold + 2; }
+extern "C" int64_t mmssl_spmm_plan_items_cap(int64_t n_rows, int64_t nnz) { return n_rows + mmssl_spmm_plan_segs_cap(nnz); }
 
 extern "C" int64_t mmssl_spmm_plan_workspace_bytes(int64_t n_rows) {
     size_t cub_bytes = 0;
@@ -195,13 +200,12 @@ extern "C" int64_t mmssl_spmm_plan_workspace_bytes(int64_t n_rows) {
     return (int64_t)(6 * ((sizeof(int32_t) * n_rows + 255) & ~(size_t)255) + cub_bytes + 512);
 }
 
-extern "C" int mmssl_spmm_plan(const int32_t* rowptr, int64_t n_rows, int64_t nnz, int seg_len, int32_t* items4,
-                               int64_t items_cap, int32_t* split_table2, int32_t* counters, int64_t splits_cap,
+extern "C" int mmssl_spmm_plan(const int32_t* rowptr, int64_t n_rows, int64_t nnz, int32_t* items4,
+                               int64_t items_cap, int32_t* split_table4, int32_t* counters, int64_t splits_cap,
                                int32_t* totals3, void* workspace, int64_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    MMSSL_REQUIRE(seg_len >= 32, "seg_len must be >= 32");
-    MMSSL_REQUIRE(items_cap >= mmssl_spmm_plan_items_cap(n_rows, nnz, seg_len), "items_cap too small");
-    MMSSL_REQUIRE(splits_cap >= mmssl_spmm_plan_splits_cap(nnz, seg_len), "splits_cap too small");
+    MMSSL_REQUIRE(items_cap >= mmssl_spmm_plan_items_cap(n_rows, nnz), "items_cap too small");
+    MMSSL_REQUIRE(splits_cap >= mmssl_spmm_plan_splits_cap(nnz), "splits_cap too small");
     const int T = 256;
     // all items start as {-1,-1,-1,-1}: the SpMM kernel skips row < 0
     MMSSL_CUDA(cudaMemsetAsync(items4, 0xff, sizeof(int4) * items_cap, stream));
@@ -220,17 +224,15 @@ extern "C" int mmssl_spmm_plan(const int32_t* rowptr, int64_t n_rows, int64_t nn
     int32_t* split_off = (int32_t*)(b + 4 * arr);
     int32_t* seg_off = (int32_t*)(b + 5 * arr);
     void* cub_tmp = (void*)(b + 6 * arr);
-    const int split_thr = 2 * seg_len;
-    plan_count_kernel<<<(unsigned)((n_rows + T - 1) / T), T, 0, stream>>>(rowptr, n_rows, seg_len, split_thr, n_items,
-                                                                         is_split, n_segs);
+    plan_count_kernel<<<(unsigned)((n_rows + T - 1) / T), T, 0, stream>>>(rowptr, n_rows, n_items, is_split, n_segs);
     MMSSL_LAUNCH_OK();
     MMSSL_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, n_items, item_off, (int)n_rows, stream));
     MMSSL_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, is_split, split_off, (int)n_rows, stream));
     MMSSL_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, n_segs, seg_off, (int)n_rows, stream));
     const int64_t threads = n_rows * 32;
-    plan_fill_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, stream>>>(rowptr, n_rows, seg_len, item_off, split_off,
-                                                                         seg_off, is_split, (int4*)items4,
-                                                                         (int2*)split_table2, totals3);
+    plan_fill_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, stream>>>(rowptr, n_rows, item_off, split_off, seg_off,
+                                                                         is_split, (int4*)items4, (int4*)split_table4,
+                                                                         totals3);
     MMSSL_LAUNCH_OK();
     return 0;
 }

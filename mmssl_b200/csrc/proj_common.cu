@@ -65,7 +65,15 @@ __global__ void proj_epilogue_kernel(const float* __restrict__ partial, int spli
     const int c = (int)(i - r * n4) * 4;
     const int64_t n = (int64_t)n4 * 4;
     float4 acc = bias ? ld4(bias + c) : f4zero();
-    for (int s = 0; s < split_k; ++s) acc = add4(acc, ld4(partial + ((int64_t)s * m + r) * n + c));
+    int s = 0;
+    for (; s + 4 <= split_k; s += 4) {   // 4 independent loads in flight, summed in slice order
+        const float4 p0 = ld4(partial + ((int64_t)(s + 0) * m + r) * n + c);
+        const float4 p1 = ld4(partial + ((int64_t)(s + 1) * m + r) * n + c);
+        const float4 p2 = ld4(partial + ((int64_t)(s + 2) * m + r) * n + c);
+        const float4 p3 = ld4(partial + ((int64_t)(s + 3) * m + r) * n + c);
+        acc = add4(add4(add4(add4(acc, p0), p1), p2), p3);
+    }
+    for (; s < split_k; ++s) acc = add4(acc, ld4(partial + ((int64_t)s * m + r) * n + c));
     if (y_pre) st4(y_pre + r * ldyp + c, acc);
     if (mask) {
         const float4 mv = ld4(mask + r * ldm + c);
@@ -82,8 +90,17 @@ __global__ void wgrad_epilogue_kernel(const float* __restrict__ partial, int spl
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {
         const int64_t mm = m0 + k, nn = n0 + threadIdx.x;
         float v = 0.f;
-        if (mm < m && nn < n)
-            for (int s = 0; s < split_k; ++s) v += partial[((int64_t)s * m + mm) * n + nn];
+        if (mm < m && nn < n) {
+            int s = 0;
+            for (; s + 4 <= split_k; s += 4) {   // independent loads first, fixed summation order
+                const float p0 = partial[((int64_t)(s + 0) * m + mm) * n + nn];
+                const float p1 = partial[((int64_t)(s + 1) * m + mm) * n + nn];
+                const float p2 = partial[((int64_t)(s + 2) * m + mm) * n + nn];
+                const float p3 = partial[((int64_t)(s + 3) * m + mm) * n + nn];
+                v = (((v + p0) + p1) + p2) + p3;
+            }
+            for (; s < split_k; ++s) v += partial[((int64_t)s * m + mm) * n + nn];
+        }
         tile[k][threadIdx.x] = v;
     }
     __syncthreads();

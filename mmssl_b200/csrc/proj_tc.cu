@@ -27,7 +27,6 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle span
 constexpr int kTileABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kThreads = 192;
-constexpr int kKbPerSplitTarget = 8;              // 512 K-elements per CTA by default
 constexpr int kMaxSplit = 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -101,14 +100,17 @@ template <int N>
 struct GemmCfg {
     static constexpr int kTileBBytes = N * kBlockK * 2;
     static constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;
-    static constexpr int kStages = (N == 64) ? 4 : (N == 128 ? 3 : 2);
+    // N = 64: two CTAs are co-resident per SM (2 stages each = the same 192 KB of loads in flight),
+    // so one CTA's prologue / epilogue overlaps the other's main loop.
+    static constexpr int kCtasPerSm = (N == 64) ? 2 : 1;
+    static constexpr int kStages = (N == 64) ? 2 : (N == 128 ? 3 : 2);
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
                                        ((uint32_t)(kBlockM >> 4) << 24);   // F32 acc, BF16 x BF16, K-major both
 };
 
 template <int N>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, GemmCfg<N>::kCtasPerSm)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    float* __restrict__ partial, int M, int total_kb, int kb_per_split) {
@@ -249,12 +251,14 @@ static int make_map(CUtensorMap* map, const uint16_t* base, int64_t rows, int64_
     return 0;
 }
 
-static int choose_split(int64_t m, int64_t k) {
+static int choose_split(int64_t m, int64_t n, int64_t k) {
+    // HBM-bound streaming GEMM: what matters is that all SMs pull from HBM for the whole kernel.
+    // Pick the split-K that fills ONE wave of co-resident CTAs as completely as possible
+    // (e.g. 56 M-tiles x 5 slices = 280 of 296 slots) instead of leaving a nearly empty tail wave.
     const int64_t total_kb = (k + kBlockK - 1) / kBlockK;
     const int64_t m_tiles = (m + kBlockM - 1) / kBlockM;
-    int64_t split = (total_kb + kKbPerSplitTarget - 1) / kKbPerSplitTarget;
-    // enough CTAs for >= 2 waves, but never slices shorter than 2 k-blocks
-    while (m_tiles * split < 2 * kNumSMs && split * 2 <= total_kb && split < kMaxSplit) split *= 2;
+    const int64_t slots = (int64_t)kNumSMs * (n == 64 ? 2 : 1);
+    int64_t split = slots / m_tiles;
     if (split > kMaxSplit) split = kMaxSplit;
     if (split > total_kb) split = total_kb;
     if (split < 1) split = 1;
@@ -286,7 +290,7 @@ static int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUten
 using namespace mmssl;
 
 extern "C" int64_t mmssl_gemm_bf16x3_workspace_floats(int64_t m, int64_t n, int64_t k, int* split_k_out) {
-    const int split = choose_split(m, k);
+    const int split = choose_split(m, n, k);
     if (split_k_out) *split_k_out = split;
     return (int64_t)split * m * n;
 }

@@ -409,7 +409,7 @@ extern "C" int mmssl_colsum(const float* g, int64_t ldg, const float* mask, int6
     MMSSL_REQUIRE(n >= 1 && n <= 256 && 256 % n == 0, "n must divide 256");
     if (!accumulate) MMSSL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n, st));
     if (rows == 0) return 0;
-    const int rows_per_block = 512;
+    const int rows_per_block = 64;
     const unsigned blocks = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
     colsum_kernel<<<blocks, 256, 256 * sizeof(float), st>>>(g, ldg, mask, ldm, rows, n, rows_per_block, out);
     MMSSL_LAUNCH_OK();

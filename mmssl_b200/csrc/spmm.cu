@@ -13,6 +13,8 @@
 //    which divides the index traffic and the launch count.
 //  * long rows (power-law item degrees) are cut into segments handled by different groups; the
 //    last group to arrive sums the partials in segment order -> deterministic, no float atomics.
+//    Segment length grows with the row (32..512) so that neither the row walk nor the final
+//    reduction becomes the critical path of a small (latency-bound) graph.
 //  * fused epilogues: + alpha*C[row], row softmax over d (last GCN layer, Models.py:203-204),
 //    softmax backward y*(g - <g,y>), running layer sum S (+)= out (Models.py:213-214).
 #include "common.cuh"
@@ -28,7 +30,7 @@ struct SpmmParams {
     const float* vals;
     const int4* items;
     int64_t n_items;
-    const int2* split_table;
+    const int4* split_table;
     int32_t* counters;
     float* partials;
     const float* x[kMaxRhs];  int64_t ldx[kMaxRhs];
@@ -41,12 +43,16 @@ struct SpmmParams {
     int epilogue;   // MMSSL_EPI_*
     int s_mode;     // 0 none, 1: S += out, 2: S = SB + out
     int has_c;
-    int seg_len;
 };
 
 // G lanes per group, C float4 chunks per lane per rhs (d = 4*G*C), R right-hand sides.
+// UNR neighbour gathers are issued back to back before the first FMA consumes one, and the next
+// chunk of (col, val) pairs is prefetched while the current one is processed, so a row walk costs
+// about one memory round trip per UNR non-zeros instead of one per load.
 template <int G, int C, int R>
 __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
+    constexpr int RC = R * C;
+    constexpr int UNR = (8 / RC) >= 2 ? (8 / RC) : 2;
     const unsigned gmask = group_mask<G>();
     const int lane = threadIdx.x & (G - 1);
     const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
@@ -62,23 +68,27 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[r][c] = f4zero();
 
+    int c_nxt = 0;
+    float v_nxt = 0.f;
+    if (begin + lane < end) { c_nxt = __ldg(p.colidx + begin + lane); v_nxt = __ldg(p.vals + begin + lane); }
     for (int base = begin; base < end; base += G) {
-        const int e = base + lane;
-        int c_l = 0;
-        float v_l = 0.f;
-        if (e < end) { c_l = __ldg(p.colidx + e); v_l = __ldg(p.vals + e); }
+        const int c_l = c_nxt;
+        const float v_l = v_nxt;
+        const int e2 = base + G + lane;
+        c_nxt = 0; v_nxt = 0.f;
+        if (e2 < end) { c_nxt = __ldg(p.colidx + e2); v_nxt = __ldg(p.vals + e2); }   // prefetch the next chunk
         const int cnt = min(G, end - base);
-        for (int j = 0; j < cnt; j += 4) {
-            int cc[4];
-            float vv[4];
+        for (int j = 0; j < cnt; j += UNR) {
+            int cc[UNR];
+            float vv[UNR];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < UNR; ++k) {
                 cc[k] = __shfl_sync(gmask, c_l, j + k, G);
                 vv[k] = __shfl_sync(gmask, v_l, j + k, G);
             }
-            float4 xv[4][R][C];
+            float4 xv[UNR][R][C];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < UNR; ++k) {
                 const bool on = (j + k) < cnt;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -88,7 +98,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < UNR; ++k)
 #pragma unroll
                 for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -98,10 +108,9 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
 
     // ---- split rows: publish the partial, the last arriver reduces in segment order ----
     if (item.w >= 0) {
-        const int2 st = __ldg(&p.split_table[item.w]);   // {first partial slot, #segments}
+        const int4 st = __ldg(&p.split_table[item.w]);   // {first partial slot, #segments, segment length, 0}
         const int W = R * C * G * 4;
-        // a row's segments are laid out consecutively and all but the last are seg_len long
-        const int k = (begin - __ldg(p.rowptr + row)) / p.seg_len;
+        const int k = (begin - __ldg(p.rowptr + row)) / st.z;
         float* part = p.partials + ((int64_t)st.x + k) * W;
 #pragma unroll
         for (int r = 0; r < R; ++r)
@@ -119,13 +128,25 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
         for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int c = 0; c < C; ++c) acc[r][c] = f4zero();
-        for (int s = 0; s < st.y; ++s) {
-            const float* ps = p.partials + ((int64_t)st.x + s) * W;
+        constexpr int PB = (8 / RC) >= 1 ? (8 / RC) : 1;   // partial rows fetched per round trip
+        for (int s0 = 0; s0 < st.y; s0 += PB) {
+            float4 pv[PB][R][C];
 #pragma unroll
-            for (int r = 0; r < R; ++r)
+            for (int q = 0; q < PB; ++q) {
+                const bool on = (s0 + q) < st.y;
+                const float* ps = p.partials + ((int64_t)st.x + s0 + q) * W;
 #pragma unroll
-                for (int c = 0; c < C; ++c)
-                    acc[r][c] = add4(acc[r][c], ldcg4(ps + (r * C + c) * (4 * G) + lane * 4));
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        pv[q][r][c] = on ? ldcg4(ps + (r * C + c) * (4 * G) + lane * 4) : f4zero();
+            }
+#pragma unroll
+            for (int q = 0; q < PB; ++q)      // fixed (segment) order -> deterministic sum
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[r][c] = add4(acc[r][c], pv[q][r][c]);
         }
     }
 
@@ -210,15 +231,15 @@ extern "C" int mmssl_spmm_csr_f32(const mmssl_csr_t* a, int d, int nrhs, const m
     MMSSL_REQUIRE(d == 64 || d == 128 || d == 256, "embedding width must be 64, 128 or 256");
     MMSSL_REQUIRE(epilogue >= MMSSL_EPI_NONE && epilogue <= MMSSL_EPI_SOFTMAX_BWD, "bad epilogue");
     MMSSL_REQUIRE(s_mode >= 0 && s_mode <= 2, "bad s_mode");
-    MMSSL_REQUIRE(a->n_items >= 0 && a->items != nullptr && a->seg_len >= 32, "missing work plan");
+    MMSSL_REQUIRE(a->n_items >= 0 && a->items != nullptr, "missing work plan");
     MMSSL_REQUIRE(a->segs_cap * (int64_t)nrhs * d <= partials_floats || a->segs_cap == 0,
                   "partials buffer too small for the split rows");
     SpmmParams p;
     memset(&p, 0, sizeof(p));
     p.rowptr = a->rowptr; p.colidx = a->colidx; p.vals = a->vals;
     p.items = (const int4*)a->items; p.n_items = a->n_items;
-    p.split_table = (const int2*)a->split_table; p.counters = a->counters; p.partials = partials;
-    p.alpha = alpha; p.epilogue = epilogue; p.s_mode = s_mode; p.seg_len = a->seg_len;
+    p.split_table = (const int4*)a->split_table; p.counters = a->counters; p.partials = partials;
+    p.alpha = alpha; p.epilogue = epilogue; p.s_mode = s_mode;
     for (int r = 0; r < nrhs; ++r) {
         const mmssl_spmm_rhs_t& q = rhs[r];
         MMSSL_REQUIRE(q.x && q.y, "null X or Y");

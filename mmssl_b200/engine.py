@@ -254,7 +254,7 @@ class Engine:
 
             def fuse_bwd(g0, zn, nrm, ya, yb, g_ya, g_yb, rows):
                 dz = ops.id_fuse_bwd(g0, zn, nrm, self.id_rate, self._new(rows, d, dev=dev))
-                sk = max(1, min(64, rows // 2048))
+                sk = max(1, min(256, rows // 128))
                 if ya is yb:
                     ops.sgemm(ya, dz, d_wsum, trans_a=True, alpha=1.0, beta=1.0, split_k=sk)
                     tot = self._new(rows, d, dev=dev)

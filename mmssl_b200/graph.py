@@ -22,20 +22,18 @@ import torch
 from . import _lib
 from ._lib import CsrDesc, ptr, stream
 
-SEG_LEN = 256
-
 
 class SparseOperand:
     """CSR matrix + SpMM work plan living on one CUDA device."""
 
     def __init__(self, rows: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, n_rows: int, n_cols: int,
-                 transpose: bool = False, seg_len: int = SEG_LEN):
+                 transpose: bool = False):
         lib = _lib.load(require_device=True)
         dev = vals.device
         nnz = int(vals.numel())
         if transpose:
             n_rows, n_cols = n_cols, n_rows
-        self.n_rows, self.n_cols, self.nnz, self.seg_len = int(n_rows), int(n_cols), nnz, seg_len
+        self.n_rows, self.n_cols, self.nnz = int(n_rows), int(n_cols), nnz
         self.device = dev
         i32 = dict(dtype=torch.int32, device=dev)
         self.rowptr = torch.empty(n_rows + 1, **i32)
@@ -51,16 +49,16 @@ class SparseOperand:
         _lib.check(lib.mmssl_csr_from_coo(ptr(rows), ptr(cols), ptr(vals), nnz, n_rows, n_cols, int(transpose),
                                           ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), ptr(ws), ws_bytes, stream()))
         # work plan
-        self.items_cap = lib.mmssl_spmm_plan_items_cap(n_rows, nnz, seg_len)
-        self.splits_cap = lib.mmssl_spmm_plan_splits_cap(nnz, seg_len)
-        self.segs_cap = lib.mmssl_spmm_plan_segs_cap(nnz, seg_len)
+        self.items_cap = lib.mmssl_spmm_plan_items_cap(n_rows, nnz)
+        self.splits_cap = lib.mmssl_spmm_plan_splits_cap(nnz)
+        self.segs_cap = lib.mmssl_spmm_plan_segs_cap(nnz)
         self.items = torch.empty(self.items_cap * 4, **i32)
-        self.split_table = torch.empty(self.splits_cap * 2, **i32)
+        self.split_table = torch.empty(self.splits_cap * 4, **i32)
         self.counters = torch.empty(self.splits_cap, **i32)
         self.totals = torch.empty(3, **i32)
         pws_bytes = lib.mmssl_spmm_plan_workspace_bytes(n_rows)
         pws = torch.empty(pws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(lib.mmssl_spmm_plan(ptr(self.rowptr), n_rows, nnz, seg_len, ptr(self.items), self.items_cap,
+        _lib.check(lib.mmssl_spmm_plan(ptr(self.rowptr), n_rows, nnz, ptr(self.items), self.items_cap,
                                        ptr(self.split_table), ptr(self.counters), self.splits_cap, ptr(self.totals),
                                        ptr(pws), pws_bytes, stream()))
         self._keepalive = (ws, pws, rows, cols, vals)   # until the stream has consumed them
@@ -68,7 +66,7 @@ class SparseOperand:
         # capacity (unused entries are row=-1).  Resolved lazily (first host read of `totals`).
         self._n_items_exact: Optional[int] = None
         self.desc = CsrDesc(ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), n_rows, n_cols, nnz, ptr(self.items),
-                            self.items_cap, ptr(self.split_table), ptr(self.counters), self.segs_cap, seg_len)
+                            self.items_cap, ptr(self.split_table), ptr(self.counters), self.segs_cap)
 
     def tighten(self) -> None:
         """Optional: read the exact item count back (one host sync) so launches are not padded."""
