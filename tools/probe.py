@@ -1,0 +1,94 @@
+"""GPU probe: in-graph (warm) latency of kernel chains at small scale, SpMM throughput at large scale.
+Usage (under gpurun): python tools/probe.py [small] [large]"""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+from mmssl_b200 import ops
+from mmssl_b200.graph import BipartiteGraph
+from mmssl_b200.synthetic import make_dataset, make_bipartite, csr_norm
+
+dev = torch.device("cuda")
+PEAK = 6489.3
+
+
+def graph_time(fn, reps=20, inner=1):
+    """us per call of fn when `inner` calls are captured in a CUDA graph and replayed."""
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fn()
+    torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(inner):
+            fn()
+    g.replay(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        g.replay()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e3 / (reps * inner)
+
+
+def cold_time(fn, flush, reps=5):
+    ts = []
+    for _ in range(reps):
+        flush.add_(1.0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    return sorted(ts)[len(ts) // 2]
+
+
+def small(name):
+    ds = make_dataset(name)
+    d = ds.embed_size
+    g_ui = BipartiteGraph.from_scipy(ds.ui_norm); g_iu = BipartiteGraph.from_scipy(ds.iu_norm)
+    U, I = ds.n_users, ds.n_items
+    xi = torch.randn(I, d, device=dev); yu = torch.empty(U, d, device=dev); yi = torch.empty(I, d, device=dev)
+    x2 = torch.randn(I, 2 * d, device=dev); y2 = torch.empty(U, 2 * d, device=dev)
+    out = {"config": name, "fwd_items": g_ui.fwd.desc.n_items, "iu_items": g_iu.fwd.desc.n_items,
+           "ui_split_rows": g_ui.fwd.n_split_rows, "iu_split_rows": g_iu.fwd.n_split_rows}
+
+    def chain():
+        ops.spmm(g_ui.fwd, [xi], [yu]); ops.spmm(g_iu.fwd, [yu], [yi])
+    out["spmm_pair_in_graph_us"] = graph_time(chain, inner=10)
+    out["spmm_ui_in_graph_us"] = graph_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu]), inner=20)
+    out["spmm_iu_in_graph_us"] = graph_time(lambda: ops.spmm(g_iu.fwd, [yu], [yi]), inner=20)
+    out["spmm_ui_2rhs_in_graph_us"] = graph_time(lambda: ops.spmm(g_ui.fwd, [x2[:, :d], x2[:, d:]], [y2[:, :d], y2[:, d:]]), inner=20)
+    out["axpby_in_graph_us"] = graph_time(lambda: ops.axpby(xi, 1.0, 0.0, yi), inner=40)     # ~launch floor
+    flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)
+    out["spmm_ui_cold_us"] = cold_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu]), flush)
+    out["spmm_iu_cold_us"] = cold_time(lambda: ops.spmm(g_iu.fwd, [yu], [yi]), flush)
+    print(json.dumps(out))
+
+
+def large(U, I, nnz, d, tag):
+    t0 = time.time()
+    r = make_bipartite(U, I, nnz, seed=1)
+    a_ui, a_iu = csr_norm(r), csr_norm(r.T.tocsr())
+    g_ui = BipartiteGraph.from_scipy(a_ui); g_iu = BipartiteGraph.from_scipy(a_iu)
+    gen_s = time.time() - t0
+    xi = torch.randn(I, d, device=dev); yu = torch.empty(U, d, device=dev); yi = torch.empty(I, d, device=dev)
+    res = {"config": tag, "U": U, "I": I, "nnz": nnz, "d": d, "gen_s": round(gen_s, 1),
+           "ui_items": g_ui.fwd.desc.n_items, "iu_items": g_iu.fwd.desc.n_items, "iu_split_rows": g_iu.fwd.n_split_rows}
+    flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)
+    for nm, g, x, y, M, N in (("ui", g_ui.fwd, xi, yu, U, I), ("iu", g_iu.fwd, yu, yi, I, U),
+                              ("uiT", g_ui.bwd, yu, yi, I, U), ("iuT", g_iu.bwd, yi, yu, U, I)):
+        us = cold_time(lambda: ops.spmm(g, [x], [y]), flush)
+        alg = 8 * nnz + 4 * (M + 1) + 4 * d * N + 4 * d * M
+        gat = 8 * nnz + 4 * (M + 1) + 4 * d * nnz + 4 * d * M
+        res[nm] = {"us": round(us, 1), "alg_MB": round(alg / 1e6, 1), "GBs": round(alg / us / 1e3, 1),
+                   "frac": round(alg / us / 1e3 / PEAK, 3), "gather_GBs": round(gat / us / 1e3, 1)}
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["small"]
+    if "small" in which:
+        small("baby"); small("sports")
+    if "large" in which:
+        large(1_000_000, 200_000, 20_000_000, 128, "syn1m")
+    if "mid" in which:
+        large(200_000, 50_000, 4_000_000, 64, "mid-d64")
