@@ -54,7 +54,7 @@ __device__ __forceinline__ float4 scale4(const float4& a, float s) {
 }
 __device__ __forceinline__ float max4(const float4& a) { return fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)); }
 
-// Reduction over a group of G consecutive lanes (G = 16 or 32) using a group-local mask.
+// Reduction over a group of G consecutive lanes (G = 8, 16 or 32) using a group-local mask.
 template <int G>
 __device__ __forceinline__ unsigned group_mask() {
     if (G == 32) return 0xffffffffu;

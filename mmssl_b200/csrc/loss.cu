@@ -232,7 +232,15 @@ __global__ void __launch_bounds__(256) nce_finalize_kernel(int64_t n, int64_t nt
     float li = 0.f;
     if (i < n) {
         float sr = 0.f, sb = 0.f;
-        for (int64_t t = 0; t < ntj; ++t) {
+        int64_t t = 0;
+        for (; t + 4 <= ntj; t += 4) {      // independent loads first, fixed summation order
+            float r_[4], b_[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { r_[q] = stats[4 * n + (t + q) * n + i]; b_[q] = stats[4 * n + ntj * n + (t + q) * n + i]; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { sr += r_[q]; sb += b_[q]; }
+        }
+        for (; t < ntj; ++t) {
             sr += stats[4 * n + t * n + i];
             sb += stats[4 * n + ntj * n + t * n + i];
         }

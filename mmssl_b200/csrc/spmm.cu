@@ -207,8 +207,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
 }
 
 template <int G, int C, int R>
-static int launch_spmm(const SpmmParams& p, cudaStream_t stream) {
-    const int T = 256;
+static int launch_spmm(const SpmmParams& p, cudaStream_t stream, int T) {
     const int64_t groups_per_block = T / G;
     const int64_t blocks = (p.n_items + groups_per_block - 1) / groups_per_block;
     if (blocks == 0) return 0;
@@ -262,12 +261,16 @@ extern "C" int mmssl_spmm_csr_f32(const mmssl_csr_t* a, int d, int nrhs, const m
             }
         }
     }
+    // impl: bit 1 -> 8-lane groups for d = 64 (each lane owns two float4 slices; twice as many rows
+    // resident per SM, so a small graph fits one wave); bit 2 -> 128-thread blocks.
+    const int T = (impl & 4) ? 128 : 256;
 #define MMSSL_SPMM_CASE(G, C)                                           \
     switch (nrhs) {                                                     \
-        case 1: return launch_spmm<G, C, 1>(p, stream);                 \
-        case 2: return launch_spmm<G, C, 2>(p, stream);                 \
-        default: return launch_spmm<G, C, 3>(p, stream);                \
+        case 1: return launch_spmm<G, C, 1>(p, stream, T);              \
+        case 2: return launch_spmm<G, C, 2>(p, stream, T);              \
+        default: return launch_spmm<G, C, 3>(p, stream, T);             \
     }
+    if (d == 64 && (impl & 2)) { MMSSL_SPMM_CASE(8, 2) }
     if (d == 64) { MMSSL_SPMM_CASE(16, 1) }
     if (d == 128) { MMSSL_SPMM_CASE(32, 1) }
     MMSSL_SPMM_CASE(32, 2)

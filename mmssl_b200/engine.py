@@ -72,6 +72,19 @@ class Engine:
         self.id_rate, self.cat_rate = id_cat_rate, model_cat_rate
         self.proj_impl = proj_impl
         self._tile_id: Dict[Tuple, torch.Tensor] = {}
+        # The modality branch (projection -> A_ui [Xv|Xt] -> A_iu [Uv|Ut]) and the id/GCN branch are
+        # independent until the final combine (and again after combine-backward), so they run on two
+        # streams; inside a CUDA graph they become parallel branches.  Set to False to serialise.
+        self.two_streams = True
+        self._side: Dict[Tuple, torch.cuda.Stream] = {}
+
+    def _side_stream(self, dev) -> torch.cuda.Stream:
+        key = (dev.type, dev.index)
+        st = self._side.get(key)
+        if st is None:
+            st = torch.cuda.Stream(device=dev)
+            self._side[key] = st
+        return st
 
     # ------------------------------------------------------------------ helpers
     def _tile(self, dev) -> torch.Tensor:
@@ -130,10 +143,21 @@ class Engine:
         xv, xt = X2[:, :d], X2[:, d:]
         uv, ut = U2[:, :d], U2[:, d:]
         iv, it = I2[:, :d], I2[:, d:]
-        self._project(P[P_WV], P[P_BV], feats[0], masks[0] if masks else None, xv)     # Models.py:173
-        self._project(P[P_WT], P[P_BT], feats[1], masks[1] if masks else None, xt)     # Models.py:174
-        ops.spmm(g_ui.fwd, [xv, xt], [uv, ut])                                         # :177,182
-        ops.spmm(g_iu.fwd, [uv, ut], [iv, it])                                         # :178,183
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev) if self.two_streams else main
+
+        def modal_branch():
+            self._project(P[P_WV], P[P_BV], feats[0], masks[0] if masks else None, xv)     # Models.py:173
+            self._project(P[P_WT], P[P_BT], feats[1], masks[1] if masks else None, xt)     # Models.py:174
+            ops.spmm(g_ui.fwd, [xv, xt], [uv, ut])                                         # :177,182
+            ops.spmm(g_iu.fwd, [uv, ut], [iv, it])                                         # :178,183
+
+        if side is not main:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                modal_branch()
+        else:
+            modal_branch()
 
         def id_prop(ga, gb, e, rows):                                                  # :179-180,185-186
             def one(g):
@@ -181,6 +205,8 @@ class Engine:
                 st.u_last, st.i_last = u_n, i_n
             cur_i = i_n
         inv = 1.0 / (K + 1)
+        if side is not main:
+            main.wait_stream(side)      # join: the combine needs Uv|Ut and Iv|It
         u_f, st.sumsq_u = ops.combine_fwd(s_u, uv, ut, inv, self.cat_rate, self._new(U, d, dev=dev), want_sumsq)   # :213,217
         i_f, st.sumsq_i = ops.combine_fwd(s_i, iv, it, inv, self.cat_rate, self._new(I, d, dev=dev), want_sumsq)   # :214,218
         outs = (u_f, i_f, iv, it, uv, ut, uvid, utid, ivid, itid)
@@ -228,6 +254,27 @@ class Engine:
         gU2, gI2 = self._new(U, 2 * d, dev=dev), self._new(I, 2 * d, dev=dev)
         ops.combine_bwd(g_uf, uv, ut, g_uv, g_ut, self.cat_rate, feat_reg_coef, gU2[:, :d], gU2[:, d:])
         ops.combine_bwd(g_if, iv, it, g_iv, g_it, self.cat_rate, feat_reg_coef, gI2[:, :d], gI2[:, d:])
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev) if self.two_streams else main
+        w_slots = (slot(P_WV, P[P_WV]), slot(P_BV, P[P_BV]), slot(P_WT, P[P_WT]), slot(P_BT, P[P_BT]))
+
+        def modal_backward():
+            # modality propagation backward (Models.py:177-178,182-183), image|text batched, then the
+            # projection backward (dropout mask folded into the operand split)
+            ops.spmm(g_iu.bwd, [gI2[:, :d], gI2[:, d:]], [gU2[:, :d], gU2[:, d:]], cs=[gU2[:, :d], gU2[:, d:]], alpha=1.0)
+            gX2 = self._new(I, 2 * d, dev=dev)
+            ops.spmm(g_ui.bwd, [gU2[:, :d], gU2[:, d:]], [gX2[:, :d], gX2[:, d:]])
+            m = st.masks
+            self._project_bwd(gX2[:, :d], m[0] if m else None, feats[0], w_slots[0], w_slots[1])
+            self._project_bwd(gX2[:, d:], m[1] if m else None, feats[1], w_slots[2], w_slots[3])
+            return gX2
+
+        if side is not main:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                keep = modal_backward()
+        else:
+            keep = modal_backward()
         # ---- GCN backward.  every u_k, i_k receives inv * g_uf / inv * g_if from the layer mean.
         if K >= 1:
             t = ops.softmax_bwd(st.i_last, g_if, inv, self._new(I, d, dev=dev))
@@ -302,12 +349,6 @@ class Engine:
         # Uvid = A_vui E_i, Utid = A_tui E_i -> gradient flows to E_i; Ivid/Itid -> E_u
         id_prop_bwd(g_vui, g_tui, gt_uvid, gt_utid, g_ei, st.fused and uvid is utid)
         id_prop_bwd(g_viu, g_tiu, gt_ivid, gt_itid, g_eu, st.fused and ivid is itid)
-        # ---- modality propagation backward (Models.py:177-178,182-183), image|text batched
-        ops.spmm(g_iu.bwd, [gI2[:, :d], gI2[:, d:]], [gU2[:, :d], gU2[:, d:]], cs=[gU2[:, :d], gU2[:, d:]], alpha=1.0)
-        gX2 = self._new(I, 2 * d, dev=dev)
-        ops.spmm(g_ui.bwd, [gU2[:, :d], gU2[:, d:]], [gX2[:, :d], gX2[:, d:]])
-        # ---- projection backward (dropout mask folded into the operand split)
-        m = st.masks
-        self._project_bwd(gX2[:, :d], m[0] if m else None, feats[0], slot(P_WV, P[P_WV]), slot(P_BV, P[P_BV]))
-        self._project_bwd(gX2[:, d:], m[1] if m else None, feats[1], slot(P_WT, P[P_WT]), slot(P_BT, P[P_BT]))
+        if side is not main:
+            main.wait_stream(side)
         return res

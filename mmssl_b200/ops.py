@@ -41,7 +41,7 @@ def _ld(t: Optional[torch.Tensor]) -> int:
 
 def scratch(dev: torch.device, floats: int) -> torch.Tensor:
     """Grow-only fp32 scratch shared by stream-ordered kernels (split-row partial sums)."""
-    key = (dev.type, dev.index)
+    key = (dev.type, dev.index, torch.cuda.current_stream(dev).cuda_stream)   # concurrent streams never share scratch
     buf = _scratch.get(key)
     if buf is None or buf.numel() < floats:
         buf = torch.empty(max(floats, 1024), dtype=torch.float32, device=dev)

@@ -93,6 +93,23 @@ def test_spmm_plain(d, nrhs):
     assert torch.equal(yt, yt2)   # deterministic (fixed reduction order, no float atomics)
 
 
+@pytest.mark.parametrize("impl", [2, 4, 6])
+@pytest.mark.parametrize("nrhs", [1, 2, 3])
+def test_spmm_impl_variants(impl, nrhs):
+    """8-lane groups (impl bit 1) and 128-thread blocks (bit 2) give the same results as the default."""
+    from mmssl_b200 import ops
+    g, ref = _graph(900, 400, 40000, seed=11 + nrhs, heavy_rows=2)
+    torch.manual_seed(0)
+    xs = [torch.randn(400, 64, device="cuda") for _ in range(nrhs)]
+    c = [torch.randn(900, 64, device="cuda") for _ in range(nrhs)]
+    base = ops.spmm(g.fwd, xs, cs=c, alpha=0.5, epilogue=ops.EPI_SOFTMAX, impl=0)
+    got = ops.spmm(g.fwd, xs, cs=c, alpha=0.5, epilogue=ops.EPI_SOFTMAX, impl=impl)
+    for a, b in zip(base, got):
+        assert rel_err(b, a) < 2e-6
+    for x, y in zip(xs, ops.spmm(g.fwd, xs, impl=impl)):
+        assert rel_err(y, torch.from_numpy(ref @ x.double().cpu().numpy())) < 2e-6
+
+
 def test_spmm_empty_and_tiny():
     from mmssl_b200 import ops
     from mmssl_b200.graph import BipartiteGraph
