@@ -49,6 +49,12 @@ _SIGS = {
                               c_i32, c_vp]),
     "mmssl_id_fuse_fwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "mmssl_id_fuse_bwd": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_i64, c_vp]),
+    "mmssl_wsum": (C.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "mmssl_id_fuse2_blocks": (C.c_int, [c_i64]),
+    "mmssl_id_fuse2_fwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_f32, c_vp, c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "mmssl_id_fuse2_bwd": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f32, c_vp, c_i64, c_i32, c_f32, c_vp, c_i64,
+                                     c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "mmssl_dwcat_reduce": (C.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "mmssl_combine_fwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_f32, c_f32, c_vp, c_i64,
                                     c_vp, c_i64, c_vp]),
     "mmssl_combine_partials": (c_i64, [c_i64, c_i32]),
@@ -87,7 +93,8 @@ _lib = None
 # kernels launched by one call of each entry point (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
     "mmssl_csr_from_coo": 6, "mmssl_csr_row_normalize": 1, "mmssl_spmm_plan": 8, "mmssl_spmm_csr_f32": 1, "mmssl_sgemm": 1,
-    "mmssl_id_fuse_fwd": 1, "mmssl_id_fuse_bwd": 1, "mmssl_combine_fwd": 1, "mmssl_combine_bwd": 1, "mmssl_softmax_bwd": 1,
+    "mmssl_id_fuse_fwd": 1, "mmssl_id_fuse_bwd": 1, "mmssl_wsum": 1, "mmssl_id_fuse2_fwd": 1, "mmssl_id_fuse2_bwd": 1,
+    "mmssl_dwcat_reduce": 1, "mmssl_combine_fwd": 1, "mmssl_combine_bwd": 1, "mmssl_softmax_bwd": 1,
     "mmssl_axpby": 1, "mmssl_mul_mask": 1, "mmssl_sumsq": 1, "mmssl_bpr": 1, "mmssl_infonce_prepare": 1,
     "mmssl_infonce_stats": 2, "mmssl_infonce_grad": 1, "mmssl_infonce_scatter": 1, "mmssl_loss_assemble": 1,
     "mmssl_step_tick": 1, "mmssl_adamw": 1, "mmssl_split_bf16": 1, "mmssl_split_bf16_t": 1, "mmssl_gemm_bf16x3": 1,

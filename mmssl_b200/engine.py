@@ -172,17 +172,23 @@ class Engine:
         st = FwdState(tuple(graphs), masks, X2, U2, I2, (uvid, utid, ivid, itid),
                       fused=any(g.nnz > 0 for g in (g_vui, g_viu, g_tui, g_tiu)))
         if st.fused:                                                                   # :188-197 (closed form)
-            st.wsum = ops.sgemm(self._tile(dev), P[P_WCAT], self._new(d, d, dev=dev))
+            if d in (64, 128):      # fused row x matrix kernels, Wsum in shared memory
+                st.wsum = ops.wsum(P[P_WCAT], d, self.H)
 
-            def fuse(ya, yb, e):
-                z = self._new(e.shape[0], d, dev=dev)
-                if ya is yb:
-                    ops.sgemm(ya, st.wsum, z)
-                else:
-                    ops.sgemm(ya, st.wsum, z, alpha=0.5)
-                    ops.sgemm(yb, st.wsum, z, alpha=0.5, beta=1.0)
-                out = self._new(e.shape[0], d, dev=dev)
-                return ops.id_fuse_fwd(z, e, self.id_rate, out)
+                def fuse(ya, yb, e):
+                    return ops.id_fuse2_fwd(ya, None if ya is yb else yb, 1.0 if ya is yb else 0.5, st.wsum, e, self.id_rate)
+            else:                   # d = 256: the d x d matrix does not fit shared memory -> GEMM path
+                st.wsum = ops.sgemm(self._tile(dev), P[P_WCAT], self._new(d, d, dev=dev))
+
+                def fuse(ya, yb, e):
+                    z = self._new(e.shape[0], d, dev=dev)
+                    if ya is yb:
+                        ops.sgemm(ya, st.wsum, z)
+                    else:
+                        ops.sgemm(ya, st.wsum, z, alpha=0.5)
+                        ops.sgemm(yb, st.wsum, z, alpha=0.5, beta=1.0)
+                    out = self._new(e.shape[0], d, dev=dev)
+                    return ops.id_fuse_fwd(z, e, self.id_rate, out)
 
             u0, st.zn_u, st.nrm_u = fuse(uvid, utid, e_u)
             i0, st.zn_i, st.nrm_i = fuse(ivid, itid, e_i)
@@ -296,7 +302,17 @@ class Engine:
         # ---- id fusion backward (Models.py:188-197)
         uvid, utid, ivid, itid = st.id_out
         g_wcat = slot(P_WCAT, P[P_WCAT])
-        if st.fused:
+        if st.fused and d in (64, 128):
+            def fuse_bwd2(g0, zn, nrm, ya, yb, g_ya, g_yb):
+                same = ya is yb
+                oa, ob, part = ops.id_fuse2_bwd(g0, zn, nrm, ya, None if same else yb, 1.0 if same else 0.5, st.wsum,
+                                                self.id_rate, g_ya, g_yb, two_outputs=not same)
+                return oa, (oa if same else ob), part
+
+            gt_uvid, gt_utid, part_u = fuse_bwd2(g_eu, st.zn_u, st.nrm_u, uvid, utid, g_uvid, g_utid)
+            gt_ivid, gt_itid, part_i = fuse_bwd2(g_ei, st.zn_i, st.nrm_i, ivid, itid, g_ivid, g_itid)
+            ops.dwcat_reduce(part_u, part_i, d, self.H, g_wcat)
+        elif st.fused:
             d_wsum = torch.zeros(d, d, dtype=torch.float32, device=dev)
 
             def fuse_bwd(g0, zn, nrm, ya, yb, g_ya, g_yb, rows):

@@ -112,6 +112,43 @@ def id_fuse_bwd(g, zn, nrm, rate: float, dz):
     return dz
 
 
+def wsum(wcat, d: int, heads: int):
+    out = torch.empty(d, d, dtype=torch.float32, device=wcat.device)
+    _lib.check(_lib_().mmssl_wsum(ptr(wcat), d, heads, ptr(out), stream()))
+    return out
+
+
+def id_fuse2_fwd(ya, yb, coef: float, w, e, rate: float):
+    """out = e + rate * normalize(coef*(ya [+ yb]) @ w); returns (out, zn, nrm)."""
+    lib = _lib_()
+    n, d = ya.shape
+    f = dict(dtype=torch.float32, device=ya.device)
+    out, zn, nrm = torch.empty(n, d, **f), torch.empty(n, d, **f), torch.empty(n, **f)
+    _lib.check(lib.mmssl_id_fuse2_fwd(ptr(ya), _ld(ya), ptr(yb), _ld(yb), float(coef), ptr(w), ptr(e), _ld(e), n, d, float(rate),
+                                      ptr(out), _ld(out), ptr(zn), ptr(nrm), stream()))
+    return out, zn, nrm
+
+
+def id_fuse2_bwd(g, zn, nrm, ya, yb, coef: float, w, rate: float, ext_a, ext_b, two_outputs: bool):
+    """Returns (out_a, out_b or None, dw_partials[blocks, d*d])."""
+    lib = _lib_()
+    n, d = g.shape
+    f = dict(dtype=torch.float32, device=g.device)
+    nb = lib.mmssl_id_fuse2_blocks(n)
+    part = torch.empty(nb, d * d, **f)
+    out_a = torch.empty(n, d, **f)
+    out_b = torch.empty(n, d, **f) if two_outputs else None
+    _lib.check(lib.mmssl_id_fuse2_bwd(ptr(g), _ld(g), ptr(zn), ptr(nrm), ptr(ya), _ld(ya), ptr(yb), _ld(yb), float(coef), ptr(w), n, d,
+                                      float(rate), ptr(ext_a), _ld(ext_a), ptr(ext_b), _ld(ext_b), ptr(out_a), _ld(out_a),
+                                      ptr(out_b), _ld(out_b), ptr(part), stream()))
+    return out_a, out_b, part
+
+
+def dwcat_reduce(part_u, part_i, d: int, heads: int, dwcat):
+    _lib.check(_lib_().mmssl_dwcat_reduce(ptr(part_u), part_u.shape[0], ptr(part_i), part_i.shape[0], d, heads, ptr(dwcat), stream()))
+    return dwcat
+
+
 def combine_fwd(s, a, b, inv_layers: float, rate: float, out, want_sumsq: bool = True):
     lib = _lib_()
     n, d = s.shape

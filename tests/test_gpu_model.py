@@ -138,3 +138,56 @@ def test_hot_step_graph_replay_and_adamw_vs_oracle():
     for k in LIVE:
         assert rel_err(P[k], cpu.params[k]) < TOL, (k, rel_err(P[k], cpu.params[k]))
     assert int(hs.step_dev) == 3
+
+
+@pytest.mark.parametrize("d,modal", [(128, "random"), (256, "random"), (128, "alias"), (64, "random")])
+def test_hot_step_other_widths_vs_oracle(d, modal):
+    """d = 128 / 256 code paths (32-lane SpMM groups, N=128/256 tcgen05 tiles, GEMM-path id fusion at 256)
+    against the oracle (itself pinned to the reference) on a fresh synthetic problem."""
+    import scipy.sparse as sp
+    from oracle import mmssl_oracle as O
+    from mmssl_b200.engine import LIVE, FeatureStore
+    from mmssl_b200.graph import prepare
+    from mmssl_b200.hotstep import HotStep, HotStepConfig
+    from mmssl_b200.synthetic import TripleSampler, make_bipartite
+    U, I, B, K = 310, 170, 96, 2
+    r = make_bipartite(U, I, 2400, seed=d)
+    ui, iu = O.build_graphs(r)
+    rng = np.random.default_rng(d)
+
+    def rand_graph(shape, nnz):
+        m = sp.csr_matrix((np.ones(nnz), (rng.integers(0, shape[0], nnz), rng.integers(0, shape[1], nnz))), shape=shape)
+        return O.to_torch_coo(O.csr_norm(m, mean_flag=True))
+
+    if modal == "alias":
+        graphs = [ui, iu, ui, iu, ui, iu]
+    else:
+        graphs = [ui, iu, rand_graph((U, I), 900), rand_graph((I, U), 700), rand_graph((U, I), 500), rand_graph((I, U), 400)]
+    cfg = O.HotPathConfig(embed_size=d, n_layers=K, batch_size=B)
+    params = O.init_params(U, I, 72, 40, cfg, seed=d)
+    g = torch.Generator().manual_seed(d)
+    fv, ft = torch.randn(I, 72, generator=g), torch.randn(I, 40, generator=g)
+    masks = tuple((torch.rand(I, d, generator=g) >= 0.2).float() / 0.8 for _ in range(2))
+    users, pos, neg = TripleSampler(r, seed=1).sample(B)
+    # oracle
+    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    outs = O.forward_closed(po, fv, ft, graphs, cfg, dropout_masks=masks)
+    total, parts = O.hot_loss(outs, users, pos, neg, I, cfg)
+    total.backward()
+    # CUDA
+    hcfg = HotStepConfig(embed_size=d, n_layers=K, batch_size=B)
+    P = {k: v.clone().cuda().contiguous() for k, v in params.items()}
+    cuda_graphs = [gr.cuda() for gr in graphs[:2]]
+    if modal == "alias":
+        sparse = [cuda_graphs[0], cuda_graphs[1]] * 3
+    else:
+        sparse = cuda_graphs + [gr.cuda() for gr in graphs[2:]]
+    hs = HotStep(P, (FeatureStore(fv.cuda()), FeatureStore(ft.cuda())), [prepare(t) for t in sparse], hcfg, batch=B,
+                 optimizer_step=False)
+    hs.masks = tuple(m.cuda() for m in masks)
+    hs.set_indices(users, pos, neg)
+    out5 = hs.run().cpu()
+    assert abs(float(out5[0]) - float(total)) < TOL * abs(float(total)), (float(out5[0]), float(total))
+    assert abs(float(out5[4]) - float(parts["cl"])) < TOL * abs(float(parts["cl"]))
+    for k in LIVE:
+        assert rel_err(hs.grads[k], po[k].grad) < TOL, (d, k, rel_err(hs.grads[k], po[k].grad))
