@@ -107,16 +107,16 @@ int mmssl_id_fuse_bwd(const float* g, int64_t ldg, const float* zn, const float*
 /* Fused id fusion (Models.py:139-169 closed form + :188-197), d in {64,128}:
  *   wsum[d][d] = sum_h wcat[h*d:(h+1)*d][:]
  *   fwd: m = coef*(ya [+ yb]); z = m*wsum; out = e + rate*z/max(|z|,1e-12); zn, nrm saved
- *   bwd: dz = rate*d(normalize)(g); out_a = coef*dz*wsum^T + ext_a (+ ext_b when out_b is NULL), out_b likewise;
+ *   bwd (takes wsum_t): dz = rate*d(normalize)(g); out_a = coef*dz*wsum^T + ext_a (+ ext_b when out_b is NULL), out_b likewise;
  *        dw_part[block][d*d] = per-block partial of m^T dz  (mmssl_id_fuse2_blocks(n) blocks)
  *   dwcat[h] = sum of all partial tiles, for every head h */
-int mmssl_wsum(const float* wcat, int d, int heads, float* wsum, void* stream);
+int mmssl_wsum(const float* wcat, int d, int heads, float* wsum, float* wsum_t /* transposed copy */, void* stream);
 int mmssl_id_fuse2_blocks(int64_t n);
 int mmssl_id_fuse2_fwd(const float* ya, int64_t lda, const float* yb, int64_t ldb, float coef, const float* wsum,
                        const float* e, int64_t lde, int64_t n, int d, float rate, float* out, int64_t ldo, float* zn,
                        float* nrm, void* stream);
 int mmssl_id_fuse2_bwd(const float* g, int64_t ldg, const float* zn, const float* nrm, const float* ya, int64_t lda,
-                       const float* yb, int64_t ldb, float coef, const float* wsum, int64_t n, int d, float rate,
+                       const float* yb, int64_t ldb, float coef, const float* wsum_t, int64_t n, int d, float rate,
                        const float* ext_a, int64_t ldea, const float* ext_b, int64_t ldeb, float* out_a, int64_t ldoa,
                        float* out_b, int64_t ldob, float* dw_part, void* stream);
 int mmssl_dwcat_reduce(const float* part_u, int nu, const float* part_i, int ni, int d, int heads, float* dwcat,

@@ -49,7 +49,7 @@ _SIGS = {
                               c_i32, c_vp]),
     "mmssl_id_fuse_fwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "mmssl_id_fuse_bwd": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_i64, c_vp]),
-    "mmssl_wsum": (C.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "mmssl_wsum": (C.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "mmssl_id_fuse2_blocks": (C.c_int, [c_i64]),
     "mmssl_id_fuse2_fwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_f32, c_vp, c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "mmssl_id_fuse2_bwd": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f32, c_vp, c_i64, c_i32, c_f32, c_vp, c_i64,

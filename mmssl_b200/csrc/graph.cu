@@ -87,10 +87,13 @@ static cudaError_t carve_csr_ws(int64_t nnz, int64_t n_rows, void* base, CsrWs* 
 // segment length, 0}.  Long rows are cut into segments that different lane groups process
 // concurrently (the critical path of a small graph is its longest serial row walk); the last group
 // to finish reduces the partial sums in segment order, so results stay deterministic.
-__host__ __device__ __forceinline__ int plan_seg_len(int len) {
-    return len <= 1024 ? 32 : (len <= 4096 ? 64 : (len <= 16384 ? 128 : (len <= 65536 ? 256 : 512)));
-}
+// Rows up to kHeavyThreshold: segments of 32, partial sums reduced in segment order (deterministic).
+// Heavier rows (the head of a power-law degree distribution): segments of 64 that accumulate with
+// 128-bit float atomics into a dedicated zeroed row -- a serial reduction over hundreds of partials
+// would otherwise be the kernel's critical path.  (Summation order of those few rows is not fixed.)
 constexpr int kSplitThreshold = 64;
+constexpr int kHeavyThreshold = 1024;
+__host__ __device__ __forceinline__ int plan_seg_len(int len) { return len <= kHeavyThreshold ? 32 : 64; }
 
 __global__ void plan_count_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows,
                                   int32_t* __restrict__ n_items, int32_t* __restrict__ is_split,
@@ -124,7 +127,7 @@ __global__ void plan_fill_kernel(const int32_t* __restrict__ rowptr, int64_t n_r
             const int sb = b + k * sl;
             items[item_off[r] + k] = make_int4((int)r, sb, min(e, sb + sl), s);
         }
-        if (lane == 0) split_table[s] = make_int4(seg_off[r], segs, sl, 0);
+        if (lane == 0) split_table[s] = make_int4(seg_off[r], segs, sl, (e - b) > kHeavyThreshold ? 1 : 0);
     }
     if (r == n_rows - 1 && lane == 0) {
         totals[0] = item_off[r] + (is_split[r] ? segs : 1);   // number of work items

@@ -108,8 +108,33 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
 
     // ---- split rows: publish the partial, the last arriver reduces in segment order ----
     if (item.w >= 0) {
-        const int4 st = __ldg(&p.split_table[item.w]);   // {first partial slot, #segments, segment length, 0}
+        const int4 st = __ldg(&p.split_table[item.w]);   // {first partial slot, #segments, segment length, heavy}
         const int W = R * C * G * 4;
+        if (st.w != 0) {
+            // heavy row: accumulate into the row's own zeroed slot with 128-bit reductions
+            float* slot = p.partials + (int64_t)st.x * W;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    atomicAdd(reinterpret_cast<float4*>(slot + (r * C + c) * (4 * G) + lane * 4), acc[r][c]);
+            __threadfence();
+            __syncwarp(gmask);
+            int old = 0;
+            if (lane == 0) old = atomicAdd(p.counters + item.w, 1);
+            old = __shfl_sync(gmask, old, 0, G);
+            if (old != st.y - 1) return;
+            __threadfence();
+            if (lane == 0) p.counters[item.w] = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    float* q = slot + (r * C + c) * (4 * G) + lane * 4;
+                    acc[r][c] = ldcg4(q);
+                    __stcg(reinterpret_cast<float4*>(q), f4zero());   // leave the slot clean for the next launch
+                }
+        } else {
         const int k = (begin - __ldg(p.rowptr + row)) / st.z;
         float* part = p.partials + ((int64_t)st.x + k) * W;
 #pragma unroll
@@ -147,6 +172,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
                 for (int r = 0; r < R; ++r)
 #pragma unroll
                     for (int c = 0; c < C; ++c) acc[r][c] = add4(acc[r][c], pv[q][r][c]);
+        }
         }
     }
 

@@ -49,6 +49,7 @@ class FwdState:
     id_out: tuple                      # (Uvid, Utid, Ivid, Itid)
     fused: bool
     wsum: Optional[torch.Tensor] = None
+    wsum_t: Optional[torch.Tensor] = None
     zn_u: Optional[torch.Tensor] = None
     nrm_u: Optional[torch.Tensor] = None
     zn_i: Optional[torch.Tensor] = None
@@ -132,8 +133,9 @@ class Engine:
 
     # ------------------------------------------------------------------ forward
     def forward(self, P: Dict[str, torch.Tensor], feats: Tuple[FeatureStore, FeatureStore],
-                graphs: Sequence[BipartiteGraph], masks: Optional[Tuple[torch.Tensor, torch.Tensor]],
-                want_sumsq: bool = True):
+                graphs: Sequence[BipartiteGraph], masks, want_sumsq: bool = True, side_pre=None):
+        """masks: None, a pair of [I, d] keep-masks (0 or 1/(1-p)), or a callable returning one -- the
+        callable and `side_pre` run at the head of the modality branch, i.e. off the critical path."""
         g_ui, g_iu, g_vui, g_viu, g_tui, g_tiu = graphs
         U, I = g_ui.shape
         d, K = self.d, self.K
@@ -146,9 +148,15 @@ class Engine:
         main = torch.cuda.current_stream(dev)
         side = self._side_stream(dev) if self.two_streams else main
 
+        resolved = [masks]
+
         def modal_branch():
-            self._project(P[P_WV], P[P_BV], feats[0], masks[0] if masks else None, xv)     # Models.py:173
-            self._project(P[P_WT], P[P_BT], feats[1], masks[1] if masks else None, xt)     # Models.py:174
+            if side_pre is not None:
+                side_pre()
+            m = masks() if callable(masks) else masks
+            resolved[0] = m
+            self._project(P[P_WV], P[P_BV], feats[0], m[0] if m else None, xv)             # Models.py:173
+            self._project(P[P_WT], P[P_BT], feats[1], m[1] if m else None, xt)             # Models.py:174
             ops.spmm(g_ui.fwd, [xv, xt], [uv, ut])                                         # :177,182
             ops.spmm(g_iu.fwd, [uv, ut], [iv, it])                                         # :178,183
 
@@ -169,11 +177,11 @@ class Engine:
 
         uvid, utid = id_prop(g_vui, g_tui, e_i, U)
         ivid, itid = id_prop(g_viu, g_tiu, e_u, I)
-        st = FwdState(tuple(graphs), masks, X2, U2, I2, (uvid, utid, ivid, itid),
+        st = FwdState(tuple(graphs), resolved[0], X2, U2, I2, (uvid, utid, ivid, itid),
                       fused=any(g.nnz > 0 for g in (g_vui, g_viu, g_tui, g_tiu)))
         if st.fused:                                                                   # :188-197 (closed form)
             if d in (64, 128):      # fused row x matrix kernels, Wsum in shared memory
-                st.wsum = ops.wsum(P[P_WCAT], d, self.H)
+                st.wsum, st.wsum_t = ops.wsum(P[P_WCAT], d, self.H)
 
                 def fuse(ya, yb, e):
                     return ops.id_fuse2_fwd(ya, None if ya is yb else yb, 1.0 if ya is yb else 0.5, st.wsum, e, self.id_rate)
@@ -305,7 +313,7 @@ class Engine:
         if st.fused and d in (64, 128):
             def fuse_bwd2(g0, zn, nrm, ya, yb, g_ya, g_yb):
                 same = ya is yb
-                oa, ob, part = ops.id_fuse2_bwd(g0, zn, nrm, ya, None if same else yb, 1.0 if same else 0.5, st.wsum,
+                oa, ob, part = ops.id_fuse2_bwd(g0, zn, nrm, ya, None if same else yb, 1.0 if same else 0.5, st.wsum_t,
                                                 self.id_rate, g_ya, g_yb, two_outputs=not same)
                 return oa, (oa if same else ob), part
 

@@ -65,8 +65,20 @@ class SparseOperand:
         # without split rows the launch only needs n_rows items; with them we launch over the
         # capacity (unused entries are row=-1).  Resolved lazily (first host read of `totals`).
         self._n_items_exact: Optional[int] = None
+        self._work = {}
         self.desc = CsrDesc(ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), n_rows, n_cols, nnz, ptr(self.items),
                             self.items_cap, ptr(self.split_table), ptr(self.counters), self.segs_cap)
+
+    def work_area(self, width: int):
+        """(partials, counters) for launches whose right-hand sides total `width` floats per row.
+        Zero-initialised once; the kernel leaves counters and heavy-row slots clean after every launch."""
+        w = self._work.get(width)
+        if w is None:
+            part = torch.zeros(max(self.segs_cap * width, 4), dtype=torch.float32, device=self.device)
+            cnt = torch.zeros(max(self.splits_cap, 1), dtype=torch.int32, device=self.device)
+            w = (part, cnt)
+            self._work[width] = w
+        return w
 
     def tighten(self) -> None:
         """Optional: read the exact item count back (one host sync) so launches are not padded."""

@@ -56,10 +56,15 @@ class HotStep:
         d = cfg.embed_size
         f = dict(dtype=torch.float32, device=dev)
         self.idx = torch.zeros(3, batch, dtype=torch.int64, device=dev)     # users / pos / neg (static input)
-        self.g_uf, self.g_if = torch.zeros(self.U, d, **f), torch.zeros(self.I, d, **f)
         self.alias_id = graphs[2] is graphs[4]
-        self.g_uvid = torch.zeros(self.U, d, **f)
-        self.g_utid = self.g_uvid if self.alias_id else torch.zeros(self.U, d, **f)
+        # gradient seeds of the loss kernels: one contiguous buffer -> one memset per step
+        n_u = 2 if self.alias_id else 3
+        self.gflat = torch.zeros((n_u * self.U + self.I) * d, **f)
+        self.g_uf = self.gflat[:self.U * d].view(self.U, d)
+        self.g_uvid = self.gflat[self.U * d:2 * self.U * d].view(self.U, d)
+        self.g_utid = self.g_uvid if self.alias_id else self.gflat[2 * self.U * d:3 * self.U * d].view(self.U, d)
+        self.g_if = self.gflat[n_u * self.U * d:].view(self.I, d)
+        self.ones = torch.ones(self.I, d, **f)
         self.nce = [ops.InfoNCEWork(batch, d, dev) for _ in range(1 if self.alias_id else 2)]
         self.cl_seed = torch.full((1,), cfg.cl_rate * (2.0 if self.alias_id else 1.0), **f)
         self.out5 = torch.zeros(5, **f)
@@ -78,24 +83,29 @@ class HotStep:
             return None
         if self.masks is not None:
             return self.masks
-        ones = torch.ones(self.I, self.cfg.embed_size, dtype=torch.float32, device=self.idx.device)
         p = self.cfg.drop_rate
-        return (F.dropout(ones, p, True), F.dropout(ones, p, True))     # image first, like Models.py:173-174
+        return (F.dropout(self.ones, p, True), F.dropout(self.ones, p, True))     # image first, like Models.py:173-174
 
     def run(self) -> torch.Tensor:
         """Executes one hot step with the indices currently in ``self.idx``; returns the device
         tensor [total, mf, emb, feat_reg, cl]."""
         cfg = self.cfg
         users, pos, neg = self.idx[0], self.idx[1], self.idx[2]
-        self.g_uf.zero_(); self.g_if.zero_(); self.g_uvid.zero_()
-        if not self.alias_id:
-            self.g_utid.zero_()
-        outs, st = self.engine.forward(self.P, self.feats, self.graphs, self._masks(), want_sumsq=True)
+        # the seed-buffer memset and the dropout masks are only needed by the modality branch / the
+        # loss kernels, so they run at the head of the side stream, off the critical path
+        outs, st = self.engine.forward(self.P, self.feats, self.graphs, self._masks, want_sumsq=True,
+                                       side_pre=self.gflat.zero_)
         u_f, i_f, _, _, _, _, u_vid, u_tid, _, _ = outs
         reg_coef = cfg.emb_decay / cfg.batch_size
         # BPR: value partials + gradient rows scattered straight into the dense table gradients
-        bpr_part, n_bpr = ops.bpr(u_f, i_f, i_f, users, pos, neg, mode=3, reg_coef=reg_coef,
-                                  g_u=self.g_uf, g_p=self.g_if, g_n=self.g_if)
+        dev = u_f.device
+        main = torch.cuda.current_stream(dev)
+        side = self.engine._side_stream(dev) if self.engine.two_streams else main
+        if side is not main:        # BPR runs next to InfoNCE (both only add into the seed buffers, atomically)
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            bpr_part, n_bpr = ops.bpr(u_f, i_f, i_f, users, pos, neg, mode=3, reg_coef=reg_coef,
+                                      g_u=self.g_uf, g_p=self.g_if, g_n=self.g_if)
         # InfoNCE(Uvid[users], u_f[users]) + InfoNCE(Utid[users], u_f[users])   (main.py:411-412)
         inv_tau = 1.0 / cfg.tau
         parts = []
@@ -103,6 +113,8 @@ class HotStep:
             parts.append(ops.infonce_forward(z1, u_f, users, inv_tau, w, g_loss=self.cl_seed))
             if st.fused:    # with empty modality graphs z1 == 0: the loss is a constant, all gradients vanish
                 ops.infonce_backward(users, inv_tau, w, gz1, self.g_uf)
+        if side is not main:
+            main.wait_stream(side)
         nce1 = parts[0]
         nce2 = parts[0] if self.alias_id else parts[1]
         ops.loss_assemble(bpr_part, n_bpr, self.batch, reg_coef, st.sumsq_u, st.sumsq_i, 0.5 * cfg.feat_reg_decay / self.I,

@@ -74,9 +74,12 @@ def spmm(a: SparseOperand, xs: Sequence[torch.Tensor], ys: Optional[Sequence[tor
             if t is not None:
                 _row_ok(t)
         rhs[r] = SpmmRhs(ptr(x), _ld(x), ptr(y), _ld(y), ptr(c), _ld(c), ptr(yv), _ld(yv), ptr(s), _ld(s), ptr(sb), _ld(sb))
-    need = a.segs_cap * nrhs * d
-    part = scratch(xs[0].device, need)
-    _lib.check(lib.mmssl_spmm_csr_f32(C.byref(a.desc), d, nrhs, rhs, epilogue, float(alpha), s_mode, ptr(part),
+    # split-row work area (partial sums + arrival counters), private to (operand, total width): launches
+    # of different widths may run concurrently on two streams, and heavy rows need zeroed slots
+    part, counters = a.work_area(nrhs * d)
+    desc = type(a.desc).from_buffer_copy(a.desc)
+    desc.counters = counters.data_ptr()
+    _lib.check(lib.mmssl_spmm_csr_f32(C.byref(desc), d, nrhs, rhs, epilogue, float(alpha), s_mode, ptr(part),
                                       part.numel(), _default_spmm_impl if impl is None else impl, stream()))
     return list(ys)
 
@@ -113,9 +116,9 @@ def id_fuse_bwd(g, zn, nrm, rate: float, dz):
 
 
 def wsum(wcat, d: int, heads: int):
-    out = torch.empty(d, d, dtype=torch.float32, device=wcat.device)
-    _lib.check(_lib_().mmssl_wsum(ptr(wcat), d, heads, ptr(out), stream()))
-    return out
+    out = torch.empty(2, d, d, dtype=torch.float32, device=wcat.device)
+    _lib.check(_lib_().mmssl_wsum(ptr(wcat), d, heads, ptr(out[0]), ptr(out[1]), stream()))
+    return out[0], out[1]          # Wsum, Wsum^T
 
 
 def id_fuse2_fwd(ya, yb, coef: float, w, e, rate: float):
@@ -129,7 +132,7 @@ def id_fuse2_fwd(ya, yb, coef: float, w, e, rate: float):
     return out, zn, nrm
 
 
-def id_fuse2_bwd(g, zn, nrm, ya, yb, coef: float, w, rate: float, ext_a, ext_b, two_outputs: bool):
+def id_fuse2_bwd(g, zn, nrm, ya, yb, coef: float, w_t, rate: float, ext_a, ext_b, two_outputs: bool):
     """Returns (out_a, out_b or None, dw_partials[blocks, d*d])."""
     lib = _lib_()
     n, d = g.shape
@@ -138,7 +141,7 @@ def id_fuse2_bwd(g, zn, nrm, ya, yb, coef: float, w, rate: float, ext_a, ext_b, 
     part = torch.empty(nb, d * d, **f)
     out_a = torch.empty(n, d, **f)
     out_b = torch.empty(n, d, **f) if two_outputs else None
-    _lib.check(lib.mmssl_id_fuse2_bwd(ptr(g), _ld(g), ptr(zn), ptr(nrm), ptr(ya), _ld(ya), ptr(yb), _ld(yb), float(coef), ptr(w), n, d,
+    _lib.check(lib.mmssl_id_fuse2_bwd(ptr(g), _ld(g), ptr(zn), ptr(nrm), ptr(ya), _ld(ya), ptr(yb), _ld(yb), float(coef), ptr(w_t), n, d,
                                       float(rate), ptr(ext_a), _ld(ext_a), ptr(ext_b), _ld(ext_b), ptr(out_a), _ld(out_a),
                                       ptr(out_b), _ld(out_b), ptr(part), stream()))
     return out_a, out_b, part

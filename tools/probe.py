@@ -96,3 +96,38 @@ if __name__ == "__main__":
         large(1_000_000, 200_000, 20_000_000, 128, "syn1m")
     if "mid" in which:
         large(200_000, 50_000, 4_000_000, 64, "mid-d64")
+
+
+def kernels(name="baby"):
+    """Isolated in-graph latency of the small kernels on the main-stream critical path."""
+    ds = make_dataset(name)
+    d, U, I = ds.embed_size, ds.n_users, ds.n_items
+    f = dict(device=dev)
+    ya, e, g = torch.randn(U, d, **f), torch.randn(U, d, **f), torch.randn(U, d, **f)
+    wcat = torch.randn(4 * d, d, **f) * 0.1
+    w, w_t = ops.wsum(wcat, d, 4)
+    out = {"config": name}
+    out["id_fuse2_fwd_U_us"] = round(graph_time(lambda: ops.id_fuse2_fwd(ya, None, 1.0, w, e, 0.36), inner=10), 2)
+    o, zn, nrm = ops.id_fuse2_fwd(ya, None, 1.0, w, e, 0.36)
+    out["id_fuse2_bwd_U_us"] = round(graph_time(lambda: ops.id_fuse2_bwd(g, zn, nrm, ya, None, 1.0, w_t, 0.36, None, None, False), inner=10), 2)
+    _, _, pu = ops.id_fuse2_bwd(g, zn, nrm, ya, None, 1.0, w_t, 0.36, None, None, False)
+    dw = torch.empty(4 * d, d, **f)
+    out["dwcat_reduce_us"] = round(graph_time(lambda: ops.dwcat_reduce(pu, pu[:111], d, 4, dw), inner=10), 2)
+    B = 1024
+    users = torch.randperm(U, device=dev)[:B]; pos = torch.randint(0, I, (B,), device=dev); neg = torch.randint(0, I, (B,), device=dev)
+    uf, itf = torch.randn(U, d, **f), torch.randn(I, d, **f)
+    gu, gi = torch.zeros(U, d, **f), torch.zeros(I, d, **f)
+    part = torch.empty(2 * 64, **f)
+    out["bpr_us"] = round(graph_time(lambda: ops.bpr(uf, itf, itf, users, pos, neg, mode=3, reg_coef=1e-8, part=part, g_u=gu, g_p=gi, g_n=gi), inner=10), 2)
+    wk = ops.InfoNCEWork(B, d, dev)
+    seed = torch.ones(1, **f)
+    out["nce_fwd_us"] = round(graph_time(lambda: ops.infonce_forward(ya, uf, users, 2.0, wk, g_loss=seed), inner=10), 2)
+    out["nce_bwd_us"] = round(graph_time(lambda: ops.infonce_backward(users, 2.0, wk, gu, gu), inner=10), 2)
+    s = torch.randn(U, d, **f); a2 = torch.randn(U, 2 * d, **f); o2 = torch.empty(U, d, **f)
+    out["combine_fwd_us"] = round(graph_time(lambda: ops.combine_fwd(s, a2[:, :d], a2[:, d:], 1 / 3, 0.55, o2), inner=10), 2)
+    out["fill_us"] = round(graph_time(lambda: gu.zero_(), inner=20), 2)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__" and "kernels" in sys.argv[1:]:
+    kernels("baby")
