@@ -49,12 +49,134 @@ struct SpmmParams {
 // UNR neighbour gathers are issued back to back before the first FMA consumes one, and the next
 // chunk of (col, val) pairs is prefetched while the current one is processed, so a row walk costs
 // about one memory round trip per UNR non-zeros instead of one per load.
-//
-// Persistent: the grid is one resident wave; every lane group strides over the work items.  The
-// next item descriptor and its first (col, val) chunk are fetched while the current row is being
-// processed, so the item -> indices -> gather dependency chain is paid once per group, not per row.
 template <int G, int C, int R>
-__device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, float4 (&acc)[R][C], int row, int lane, unsigned gmask) {
+__global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
+    constexpr int RC = R * C;
+    constexpr int UNR = (8 / RC) >= 2 ? (8 / RC) : 2;
+    const unsigned gmask = group_mask<G>();
+    const int lane = threadIdx.x & (G - 1);
+    const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    int4 item = make_int4(-1, 0, 0, -1);
+    if (gid < p.n_items) item = __ldg(&p.items[gid]);
+    const int row = item.x;
+    if (row < 0) return;   // whole group exits together (items are per group)
+    const int begin = item.y, end = item.z;
+
+    float4 acc[R][C];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[r][c] = f4zero();
+
+    int c_nxt = 0;
+    float v_nxt = 0.f;
+    if (begin + lane < end) { c_nxt = __ldg(p.colidx + begin + lane); v_nxt = __ldg(p.vals + begin + lane); }
+    for (int base = begin; base < end; base += G) {
+        const int c_l = c_nxt;
+        const float v_l = v_nxt;
+        const int e2 = base + G + lane;
+        c_nxt = 0; v_nxt = 0.f;
+        if (e2 < end) { c_nxt = __ldg(p.colidx + e2); v_nxt = __ldg(p.vals + e2); }   // prefetch the next chunk
+        const int cnt = min(G, end - base);
+        for (int j = 0; j < cnt; j += UNR) {
+            int cc[UNR];
+            float vv[UNR];
+#pragma unroll
+            for (int k = 0; k < UNR; ++k) {
+                cc[k] = __shfl_sync(gmask, c_l, j + k, G);
+                vv[k] = __shfl_sync(gmask, v_l, j + k, G);
+            }
+            float4 xv[UNR][R][C];
+#pragma unroll
+            for (int k = 0; k < UNR; ++k) {
+                const bool on = (j + k) < cnt;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float* xr = p.x[r] + (int64_t)cc[k] * p.ldx[r] + lane * 4;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) xv[k][r][c] = on ? ldg4(xr + c * (4 * G)) : f4zero();
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < UNR; ++k)
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) fma4(acc[r][c], vv[k], xv[k][r][c]);
+        }
+    }
+
+    // ---- split rows: publish the partial, the last arriver reduces in segment order ----
+    if (item.w >= 0) {
+        const int4 st = __ldg(&p.split_table[item.w]);   // {first partial slot, #segments, segment length, heavy}
+        const int W = R * C * G * 4;
+        if (st.w != 0) {
+            // heavy row: accumulate into the row's own zeroed slot with 128-bit reductions
+            float* slot = p.partials + (int64_t)st.x * W;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    atomicAdd(reinterpret_cast<float4*>(slot + (r * C + c) * (4 * G) + lane * 4), acc[r][c]);
+            __threadfence();
+            __syncwarp(gmask);
+            int old = 0;
+            if (lane == 0) old = atomicAdd(p.counters + item.w, 1);
+            old = __shfl_sync(gmask, old, 0, G);
+            if (old != st.y - 1) return;
+            __threadfence();
+            if (lane == 0) p.counters[item.w] = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    float* q = slot + (r * C + c) * (4 * G) + lane * 4;
+                    acc[r][c] = ldcg4(q);
+                    __stcg(reinterpret_cast<float4*>(q), f4zero());   // leave the slot clean for the next launch
+                }
+        } else {
+        const int k = (begin - __ldg(p.rowptr + row)) / st.z;
+        float* part = p.partials + ((int64_t)st.x + k) * W;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) st4(part + (r * C + c) * (4 * G) + lane * 4, acc[r][c]);
+        __threadfence();
+        __syncwarp(gmask);
+        int old = 0;
+        if (lane == 0) old = atomicAdd(p.counters + item.w, 1);
+        old = __shfl_sync(gmask, old, 0, G);
+        if (old != st.y - 1) return;
+        __threadfence();
+        if (lane == 0) p.counters[item.w] = 0;   // self-cleaning for the next launch
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[r][c] = f4zero();
+        constexpr int PB = (8 / RC) >= 1 ? (8 / RC) : 1;   // partial rows fetched per round trip
+        for (int s0 = 0; s0 < st.y; s0 += PB) {
+            float4 pv[PB][R][C];
+#pragma unroll
+            for (int q = 0; q < PB; ++q) {
+                const bool on = (s0 + q) < st.y;
+                const float* ps = p.partials + ((int64_t)st.x + s0 + q) * W;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        pv[q][r][c] = on ? ldcg4(ps + (r * C + c) * (4 * G) + lane * 4) : f4zero();
+            }
+#pragma unroll
+            for (int q = 0; q < PB; ++q)      // fixed (segment) order -> deterministic sum
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[r][c] = add4(acc[r][c], pv[q][r][c]);
+        }
+        }
+    }
+
+    // ---- epilogue ----
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int64_t col0 = lane * 4;
@@ -111,164 +233,11 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, float4 (&acc)
 }
 
 template <int G, int C, int R>
-__global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
-    constexpr int RC = R * C;
-    constexpr int UNR = (8 / RC) >= 2 ? (8 / RC) : 2;
-    constexpr int W = R * C * G * 4;
-    const unsigned gmask = group_mask<G>();
-    const int lane = threadIdx.x & (G - 1);
-    const int64_t gstride = (int64_t)gridDim.x * (blockDim.x / G);
-    int64_t it = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
-    int4 item = make_int4(-1, 0, 0, -1);
-    if (it < p.n_items) item = __ldg(&p.items[it]);
-    int c_nxt = 0;
-    float v_nxt = 0.f;
-    if (item.x >= 0 && item.y + lane < item.z) { c_nxt = __ldg(p.colidx + item.y + lane); v_nxt = __ldg(p.vals + item.y + lane); }
-
-    for (; it < p.n_items; it += gstride) {
-        const int row = item.x, begin = item.y, end = item.z, splitw = item.w;
-        int4 item2 = make_int4(-1, 0, 0, -1);            // next item: independent of everything below
-        if (it + gstride < p.n_items) item2 = __ldg(&p.items[it + gstride]);
-        int c_first2 = 0;
-        float v_first2 = 0.f;
-        bool first2_done = false;
-        if (row >= 0) {
-            float4 acc[R][C];
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int c = 0; c < C; ++c) acc[r][c] = f4zero();
-
-            for (int base = begin; base < end; base += G) {
-                const int c_l = c_nxt;
-                const float v_l = v_nxt;
-                c_nxt = 0; v_nxt = 0.f;
-                if (base + G < end) {                     // prefetch the next chunk of this row
-                    const int e2 = base + G + lane;
-                    if (e2 < end) { c_nxt = __ldg(p.colidx + e2); v_nxt = __ldg(p.vals + e2); }
-                } else if (item2.x >= 0) {                // last chunk: prefetch the next item's first chunk
-                    if (item2.y + lane < item2.z) { c_first2 = __ldg(p.colidx + item2.y + lane); v_first2 = __ldg(p.vals + item2.y + lane); }
-                    first2_done = true;
-                }
-                const int cnt = min(G, end - base);
-                for (int j = 0; j < cnt; j += UNR) {
-                    int cc[UNR];
-                    float vv[UNR];
-#pragma unroll
-                    for (int k = 0; k < UNR; ++k) {
-                        cc[k] = __shfl_sync(gmask, c_l, j + k, G);
-                        vv[k] = __shfl_sync(gmask, v_l, j + k, G);
-                    }
-                    float4 xv[UNR][R][C];
-#pragma unroll
-                    for (int k = 0; k < UNR; ++k) {
-                        const bool on = (j + k) < cnt;
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            const float* xr = p.x[r] + (int64_t)cc[k] * p.ldx[r] + lane * 4;
-#pragma unroll
-                            for (int c = 0; c < C; ++c) xv[k][r][c] = on ? ldg4(xr + c * (4 * G)) : f4zero();
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < UNR; ++k)
-#pragma unroll
-                        for (int r = 0; r < R; ++r)
-#pragma unroll
-                            for (int c = 0; c < C; ++c) fma4(acc[r][c], vv[k], xv[k][r][c]);
-                }
-            }
-
-            // ---- split rows: publish the partial, the last arriver completes the row ----
-            bool finish = true;
-            if (splitw >= 0) {
-                const int4 st = __ldg(&p.split_table[splitw]);   // {first slot, #segments, segment length, heavy}
-                if (st.w != 0) {
-                    // heavy row: accumulate into the row's own zeroed slot with 128-bit reductions
-                    float* slot = p.partials + (int64_t)st.x * W;
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-#pragma unroll
-                        for (int c = 0; c < C; ++c)
-                            atomicAdd(reinterpret_cast<float4*>(slot + (r * C + c) * (4 * G) + lane * 4), acc[r][c]);
-                } else {
-                    const int k = (begin - __ldg(p.rowptr + row)) / st.z;
-                    float* part = p.partials + ((int64_t)st.x + k) * W;
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-#pragma unroll
-                        for (int c = 0; c < C; ++c) st4(part + (r * C + c) * (4 * G) + lane * 4, acc[r][c]);
-                }
-                __threadfence();
-                __syncwarp(gmask);
-                int old = 0;
-                if (lane == 0) old = atomicAdd(p.counters + splitw, 1);
-                old = __shfl_sync(gmask, old, 0, G);
-                finish = (old == st.y - 1);
-                if (finish) {
-                    __threadfence();
-                    if (lane == 0) p.counters[splitw] = 0;   // self-cleaning for the next launch
-                    if (st.w != 0) {
-                        float* slot = p.partials + (int64_t)st.x * W;
-#pragma unroll
-                        for (int r = 0; r < R; ++r)
-#pragma unroll
-                            for (int c = 0; c < C; ++c) {
-                                float* q = slot + (r * C + c) * (4 * G) + lane * 4;
-                                acc[r][c] = ldcg4(q);
-                                __stcg(reinterpret_cast<float4*>(q), f4zero());   // leave the slot clean
-                            }
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < R; ++r)
-#pragma unroll
-                            for (int c = 0; c < C; ++c) acc[r][c] = f4zero();
-                        constexpr int PB = (8 / RC) >= 1 ? (8 / RC) : 1;   // partial rows fetched per round trip
-                        for (int s0 = 0; s0 < st.y; s0 += PB) {
-                            float4 pv[PB][R][C];
-#pragma unroll
-                            for (int q = 0; q < PB; ++q) {
-                                const bool on = (s0 + q) < st.y;
-                                const float* ps = p.partials + ((int64_t)st.x + s0 + q) * W;
-#pragma unroll
-                                for (int r = 0; r < R; ++r)
-#pragma unroll
-                                    for (int c = 0; c < C; ++c)
-                                        pv[q][r][c] = on ? ldcg4(ps + (r * C + c) * (4 * G) + lane * 4) : f4zero();
-                            }
-#pragma unroll
-                            for (int q = 0; q < PB; ++q)      // fixed (segment) order -> deterministic sum
-#pragma unroll
-                                for (int r = 0; r < R; ++r)
-#pragma unroll
-                                    for (int c = 0; c < C; ++c) acc[r][c] = add4(acc[r][c], pv[q][r][c]);
-                        }
-                    }
-                }
-            }
-            if (finish) spmm_epilogue<G, C, R>(p, acc, row, lane, gmask);
-        }
-        // hand over to the next item
-        if (!first2_done && item2.x >= 0 && item2.y + lane < item2.z) {
-            c_first2 = __ldg(p.colidx + item2.y + lane); v_first2 = __ldg(p.vals + item2.y + lane);
-        }
-        item = item2; c_nxt = c_first2; v_nxt = v_first2;
-    }
-}
-
-template <int G, int C, int R>
 static int launch_spmm(const SpmmParams& p, cudaStream_t stream, int T) {
     const int64_t groups_per_block = T / G;
-    int64_t blocks = (p.n_items + groups_per_block - 1) / groups_per_block;
+    const int64_t blocks = (p.n_items + groups_per_block - 1) / groups_per_block;
     if (blocks == 0) return 0;
-    static int resident[2] = {0, 0};   // resident blocks per SM for T = 256 / 128
-    int& res = resident[T == 256 ? 0 : 1];
-    if (res == 0) {
-        MMSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, spmm_csr_kernel<G, C, R>, T, 0));
-        if (res < 1) res = 1;
-    }
-    const int64_t wave = (int64_t)kNumSMs * res;
-    if (blocks > wave) blocks = wave;       // one resident wave, grid-stride over the items
+    if (blocks > 0x7fffffffll) return fail("mmssl_spmm_csr_f32", "grid too large");
     spmm_csr_kernel<G, C, R><<<(unsigned)blocks, T, 0, stream>>>(p);
     MMSSL_LAUNCH_OK();
     return 0;
