@@ -147,24 +147,16 @@ class HotStepTrainer:
         self.pin_idx = torch.empty(3, batch, dtype=torch.int64).pin_memory()
         self.pin_out = torch.empty(5, dtype=torch.float32).pin_memory()
         if world > 1:
-            import torch.distributed as dist
-            self.dist = dist
-            keys = list(self.hs.grads.keys())
-            flat = torch.zeros(sum(self.hs.grads[k].numel() for k in keys), dtype=torch.float32, device=self.hs.idx.device)
-            off = 0
-            for k in keys:       # point the persistent gradient buffers into one flat all-reduce bucket
-                n = self.hs.grads[k].numel()
-                self.hs.grads[k] = flat[off:off + n].view_as(self.hs.grads[k])
-                off += n
-            self.flat = flat
+            from mmssl_b200.parallel import GradBucket
+            self.bucket = GradBucket(self.hs.grads)      # one flat all-reduce bucket for all live parameters
+            self.hs.grads.update(self.bucket.views)
         self.hs.capture(warmup=2)
 
     def _finish_step(self):
         if self.world > 1:
             from mmssl_b200 import ops
             from mmssl_b200.engine import LIVE
-            self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM)
-            self.flat.mul_(1.0 / self.world)
+            self.bucket.all_reduce_mean()
             hs = self.hs
             ops.step_tick(hs.step_dev)
             keys = list(LIVE)
