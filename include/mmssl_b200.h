@@ -80,9 +80,18 @@ typedef struct {
     const float* sbase; int64_t ldsbase;   /* s_mode 2: S = sbase + y */
 } mmssl_spmm_rhs_t;
 /* d in {64,128,256}; nrhs in 1..3 (all right-hand sides share A and d).  s_mode: 0 none, 1 S += y, 2 S = sbase + y.
- * `partials` = scratch for split rows, >= a->segs_cap * nrhs * d floats.  impl: 0 = LDG gather, 1 = TMA-staged gather. */
+ * `partials` = zero-initialised scratch for split rows, >= a->segs_cap * nrhs * d floats (left clean by the kernel).
+ * impl: bit 1 = 8-lane groups at d = 64, bit 2 = 128-thread blocks (tuning variants of the LDG gather kernel). */
 int mmssl_spmm_csr_f32(const mmssl_csr_t* a /*host*/, int d, int nrhs, const mmssl_spmm_rhs_t* rhs /*host*/,
                        int epilogue, float alpha, int s_mode, float* partials, int64_t partials_floats, int impl, void* stream);
+
+/* TMA-staged variant for large power-law graphs: the X rows of the `n_hot` highest-degree columns
+ * (hot_ids, by decreasing degree) are staged once per CTA into shared memory with cp.async.bulk and
+ * gathers of those columns are served from shared memory.  colidx_hot = a->colidx with hot columns
+ * encoded as -(slot+1).  Same contract / epilogues as mmssl_spmm_csr_f32. */
+int mmssl_spmm_hot_f32(const mmssl_csr_t* a /*host*/, const int32_t* colidx_hot, const int32_t* hot_ids, int n_hot, int d,
+                       int nrhs, const mmssl_spmm_rhs_t* rhs /*host*/, int epilogue, float alpha, int s_mode,
+                       float* partials, int64_t partials_floats, void* stream);
 
 /* ------------------------------------------------------------------ dense fp32 GEMM (CUDA-core path)
  * C = alpha * op(A) * op(B) + beta * C, row-major.  Used for the d x d "attention" mixing

@@ -17,33 +17,9 @@
 //    reduction becomes the critical path of a small (latency-bound) graph.
 //  * fused epilogues: + alpha*C[row], row softmax over d (last GCN layer, Models.py:203-204),
 //    softmax backward y*(g - <g,y>), running layer sum S (+)= out (Models.py:213-214).
-#include "common.cuh"
-#include "../../include/mmssl_b200.h"
+#include "spmm_common.cuh"
 
 namespace mmssl {
-
-constexpr int kMaxRhs = MMSSL_SPMM_MAX_RHS;
-
-struct SpmmParams {
-    const int32_t* rowptr;
-    const int32_t* colidx;
-    const float* vals;
-    const int4* items;
-    int64_t n_items;
-    const int4* split_table;
-    int32_t* counters;
-    float* partials;
-    const float* x[kMaxRhs];  int64_t ldx[kMaxRhs];
-    float* y[kMaxRhs];        int64_t ldy[kMaxRhs];
-    const float* c[kMaxRhs];  int64_t ldc[kMaxRhs];   // optional addend (alpha * C[row])
-    const float* ys[kMaxRhs]; int64_t ldys[kMaxRhs];  // saved softmax output (softmax-backward epilogue)
-    float* s[kMaxRhs];        int64_t lds[kMaxRhs];   // optional running sum
-    const float* sb[kMaxRhs]; int64_t ldsb[kMaxRhs];  // s_mode 2: S = SB[row] + out
-    float alpha;
-    int epilogue;   // MMSSL_EPI_*
-    int s_mode;     // 0 none, 1: S += out, 2: S = SB + out
-    int has_c;
-};
 
 // G lanes per group, C float4 chunks per lane per rhs (d = 4*G*C), R right-hand sides.
 // UNR neighbour gathers are issued back to back before the first FMA consumes one, and the next
@@ -243,14 +219,8 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t stream, int T) {
     return 0;
 }
 
-}  // namespace mmssl
-
-using namespace mmssl;
-
-extern "C" int mmssl_spmm_csr_f32(const mmssl_csr_t* a, int d, int nrhs, const mmssl_spmm_rhs_t* rhs,
-                                  int epilogue, float alpha, int s_mode, float* partials, int64_t partials_floats,
-                                  int impl, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+int fill_spmm_params(SpmmParams& p, const mmssl_csr_t* a, int d, int nrhs, const mmssl_spmm_rhs_t* rhs, int epilogue,
+                     float alpha, int s_mode, float* partials, int64_t partials_floats) {
     MMSSL_REQUIRE(a != nullptr && rhs != nullptr, "null argument");
     MMSSL_REQUIRE(nrhs >= 1 && nrhs <= kMaxRhs, "nrhs must be 1..3");
     MMSSL_REQUIRE(d == 64 || d == 128 || d == 256, "embedding width must be 64, 128 or 256");
@@ -259,7 +229,6 @@ extern "C" int mmssl_spmm_csr_f32(const mmssl_csr_t* a, int d, int nrhs, const m
     MMSSL_REQUIRE(a->n_items >= 0 && a->items != nullptr, "missing work plan");
     MMSSL_REQUIRE(a->segs_cap * (int64_t)nrhs * d <= partials_floats || a->segs_cap == 0,
                   "partials buffer too small for the split rows");
-    SpmmParams p;
     memset(&p, 0, sizeof(p));
     p.rowptr = a->rowptr; p.colidx = a->colidx; p.vals = a->vals;
     p.items = (const int4*)a->items; p.n_items = a->n_items;
@@ -287,6 +256,19 @@ extern "C" int mmssl_spmm_csr_f32(const mmssl_csr_t* a, int d, int nrhs, const m
             }
         }
     }
+    return 0;
+}
+
+}  // namespace mmssl
+
+using namespace mmssl;
+
+extern "C" int mmssl_spmm_csr_f32(const mmssl_csr_t* a, int d, int nrhs, const mmssl_spmm_rhs_t* rhs, int epilogue,
+                                  float alpha, int s_mode, float* partials, int64_t partials_floats, int impl,
+                                  void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SpmmParams p;
+    if (int rc = fill_spmm_params(p, a, d, nrhs, rhs, epilogue, alpha, s_mode, partials, partials_floats)) return rc;
     // impl: bit 1 -> 8-lane groups for d = 64 (each lane owns two float4 slices; twice as many rows
     // resident per SM, so a small graph fits one wave); bit 2 -> 128-thread blocks.
     const int T = (impl & 4) ? 128 : 256;

@@ -66,6 +66,7 @@ class SparseOperand:
         # capacity (unused entries are row=-1).  Resolved lazily (first host read of `totals`).
         self._n_items_exact: Optional[int] = None
         self._work = {}
+        self._hot = None
         self.desc = CsrDesc(ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), n_rows, n_cols, nnz, ptr(self.items),
                             self.items_cap, ptr(self.split_table), ptr(self.counters), self.segs_cap)
 
@@ -79,6 +80,26 @@ class SparseOperand:
             w = (part, cnt)
             self._work[width] = w
         return w
+
+    def hot_plan(self, max_slots: int = 2048):
+        """(colidx_hot, hot_ids, n_hot) for the TMA-staged SpMM: the `max_slots` highest-degree columns
+        get shared-memory slots (ordered by decreasing degree) and are encoded as -(slot+1) in a copy of
+        the column index array.  One-time graph preparation (device-side index manipulation)."""
+        if self._hot is None:
+            col = self.colidx[:self.nnz].long()
+            deg = torch.bincount(col, minlength=self.n_cols)
+            h = int(min(max_slots, self.n_cols, int((deg > 0).sum())))
+            hot_ids = torch.topk(deg, h).indices.to(torch.int32) if h > 0 else torch.zeros(1, dtype=torch.int32, device=self.device)
+            slot = torch.full((self.n_cols,), -1, dtype=torch.int32, device=self.device)
+            if h > 0:
+                slot[hot_ids.long()] = torch.arange(h, dtype=torch.int32, device=self.device)
+            sl = slot[col]
+            hot_col = torch.where(sl >= 0, -(sl + 1), self.colidx[:self.nnz])
+            buf = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=self.device)
+            buf[:self.nnz] = hot_col
+            self._hot = (buf, hot_ids.contiguous(), h)
+            self.hot_edge_fraction = float((sl >= 0).float().mean()) if self.nnz else 0.0
+        return self._hot
 
     def tighten(self) -> None:
         """Optional: read the exact item count back (one host sync) so launches are not padded."""

@@ -13,7 +13,7 @@ from ._lib import SpmmRhs, ptr, stream
 from .graph import SparseOperand
 
 EPI_NONE, EPI_SOFTMAX, EPI_SOFTMAX_BWD = 0, 1, 2
-SPMM_IMPL_LDG, SPMM_IMPL_TMA = 0, 1
+SPMM_IMPL_LDG, SPMM_IMPL_TMA = 0, 1     # TMA = shared-memory hot rows staged by cp.async.bulk (large graphs)
 _default_spmm_impl = SPMM_IMPL_LDG
 
 _scratch = {}
@@ -79,8 +79,14 @@ def spmm(a: SparseOperand, xs: Sequence[torch.Tensor], ys: Optional[Sequence[tor
     part, counters = a.work_area(nrhs * d)
     desc = type(a.desc).from_buffer_copy(a.desc)
     desc.counters = counters.data_ptr()
-    _lib.check(lib.mmssl_spmm_csr_f32(C.byref(desc), d, nrhs, rhs, epilogue, float(alpha), s_mode, ptr(part),
-                                      part.numel(), _default_spmm_impl if impl is None else impl, stream()))
+    impl = _default_spmm_impl if impl is None else impl
+    if impl == SPMM_IMPL_TMA:
+        colidx_hot, hot_ids, n_hot = a.hot_plan()
+        _lib.check(lib.mmssl_spmm_hot_f32(C.byref(desc), ptr(colidx_hot), ptr(hot_ids), n_hot, d, nrhs, rhs, epilogue,
+                                          float(alpha), s_mode, ptr(part), part.numel(), stream()))
+    else:
+        _lib.check(lib.mmssl_spmm_csr_f32(C.byref(desc), d, nrhs, rhs, epilogue, float(alpha), s_mode, ptr(part),
+                                          part.numel(), impl, stream()))
     return list(ys)
 
 

@@ -116,6 +116,34 @@ def test_spmm_impl_variants(impl, nrhs):
         assert rel_err(y, torch.from_numpy(ref @ x.double().cpu().numpy())) < 2e-6
 
 
+@pytest.mark.parametrize("d,nrhs", [(64, 1), (64, 3), (128, 2), (256, 1)])
+def test_spmm_tma_hot_rows(d, nrhs):
+    """TMA-staged hot-row variant (impl=1): same results as the LDG kernel, incl. epilogues and split rows."""
+    from mmssl_b200 import ops
+    rng = np.random.default_rng(d + nrhs)
+    n_rows, n_cols, nnz = 3000, 5000, 90000
+    pw = 1.0 / np.arange(1, n_cols + 1); pw /= pw.sum()                     # Zipf columns -> a real hot set
+    r = rng.integers(0, n_rows, nnz); r[:20000] = rng.integers(0, 3, 20000)  # three heavy rows
+    c = rng.choice(n_cols, nnz, p=pw)
+    v = rng.standard_normal(nnz).astype(np.float32)
+    ref = sp.coo_matrix((v.astype(np.float64), (r, c)), shape=(n_rows, n_cols)).tocsr()
+    from mmssl_b200.graph import BipartiteGraph
+    g = BipartiteGraph(torch.from_numpy(r).cuda(), torch.from_numpy(c).cuda(), torch.from_numpy(v).cuda(), (n_rows, n_cols))
+    torch.manual_seed(0)
+    xs = [torch.randn(n_cols, d, device="cuda") for _ in range(nrhs)]
+    cs = [torch.randn(n_rows, d, device="cuda") for _ in range(nrhs)]
+    ys = ops.spmm(g.fwd, xs, impl=ops.SPMM_IMPL_TMA)
+    assert g.fwd.hot_edge_fraction > 0.3
+    for x, y in zip(xs, ys):
+        assert rel_err(y, torch.from_numpy(ref @ x.double().cpu().numpy())) < 2e-6
+    a = ops.spmm(g.fwd, xs, cs=cs, alpha=0.5, epilogue=ops.EPI_SOFTMAX, impl=0)
+    b = ops.spmm(g.fwd, xs, cs=cs, alpha=0.5, epilogue=ops.EPI_SOFTMAX, impl=ops.SPMM_IMPL_TMA)
+    for u, w in zip(a, b):
+        assert rel_err(w, u) < 2e-6
+    yt = ops.spmm(g.bwd, [torch.randn(n_rows, d, device="cuda")], impl=ops.SPMM_IMPL_TMA)[0]   # A^T: hot set = heavy rows of A
+    assert yt.shape == (n_cols, d) and torch.isfinite(yt).all()
+
+
 def test_spmm_empty_and_tiny():
     from mmssl_b200 import ops
     from mmssl_b200.graph import BipartiteGraph

@@ -78,9 +78,14 @@ def large(U, I, nnz, d, tag):
     res = {"config": tag, "U": U, "I": I, "nnz": nnz, "d": d, "gen_s": round(gen_s, 1),
            "ui_items": g_ui.fwd.desc.n_items, "iu_items": g_iu.fwd.desc.n_items, "iu_split_rows": g_iu.fwd.n_split_rows}
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)
+    impl = int(os.environ.get("SPMM_IMPL", "0"))
+    res["impl"] = impl
     for nm, g, x, y, M, N in (("ui", g_ui.fwd, xi, yu, U, I), ("iu", g_iu.fwd, yu, yi, I, U),
                               ("uiT", g_ui.bwd, yu, yi, I, U), ("iuT", g_iu.bwd, yi, yu, U, I)):
-        us = cold_time(lambda: ops.spmm(g, [x], [y]), flush)
+        ops.spmm(g, [x], [y], impl=impl); torch.cuda.synchronize()
+        us = cold_time(lambda: ops.spmm(g, [x], [y], impl=impl), flush)
+        if impl == 1:
+            res[nm + "_hot_frac"] = round(g.hot_edge_fraction, 3)
         alg = 8 * nnz + 4 * (M + 1) + 4 * d * N + 4 * d * M
         gat = 8 * nnz + 4 * (M + 1) + 4 * d * nnz + 4 * d * M
         res[nm] = {"us": round(us, 1), "alg_MB": round(alg / 1e6, 1), "GBs": round(alg / us / 1e3, 1),
