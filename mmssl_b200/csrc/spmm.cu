@@ -25,10 +25,11 @@ namespace mmssl {
 // UNR neighbour gathers are issued back to back before the first FMA consumes one, and the next
 // chunk of (col, val) pairs is prefetched while the current one is processed, so a row walk costs
 // about one memory round trip per UNR non-zeros instead of one per load.
-template <int G, int C, int R>
-__global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
+template <int G, int C, int R, int UMUL, int MINB>
+__global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p) {
     constexpr int RC = R * C;
-    constexpr int UNR = (8 / RC) >= 2 ? (8 / RC) : 2;
+    constexpr int UNR0 = ((8 / RC) >= 2 ? (8 / RC) : 2) * UMUL;
+    constexpr int UNR = UNR0 > G ? G : UNR0;
     const unsigned gmask = group_mask<G>();
     const int lane = threadIdx.x & (G - 1);
     const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
@@ -208,15 +209,26 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
     }
 }
 
-template <int G, int C, int R>
-static int launch_spmm(const SpmmParams& p, cudaStream_t stream, int T) {
+template <int G, int C, int R, int UMUL, int MINB>
+static int launch_spmm_v(const SpmmParams& p, cudaStream_t stream, int T) {
     const int64_t groups_per_block = T / G;
     const int64_t blocks = (p.n_items + groups_per_block - 1) / groups_per_block;
     if (blocks == 0) return 0;
     if (blocks > 0x7fffffffll) return fail("mmssl_spmm_csr_f32", "grid too large");
-    spmm_csr_kernel<G, C, R><<<(unsigned)blocks, T, 0, stream>>>(p);
+    spmm_csr_kernel<G, C, R, UMUL, MINB><<<(unsigned)blocks, T, 0, stream>>>(p);
     MMSSL_LAUNCH_OK();
     return 0;
+}
+
+// impl bit 3 (8): twice as many gathers in flight per lane; bit 4 (16): cap registers for 6 blocks/SM
+template <int G, int C, int R>
+static int launch_spmm(const SpmmParams& p, cudaStream_t stream, int T, int impl) {
+    switch ((impl >> 3) & 3) {
+        case 1: return launch_spmm_v<G, C, R, 2, 1>(p, stream, T);
+        case 2: return launch_spmm_v<G, C, R, 1, 6>(p, stream, T);
+        case 3: return launch_spmm_v<G, C, R, 2, 4>(p, stream, T);
+        default: return launch_spmm_v<G, C, R, 1, 1>(p, stream, T);
+    }
 }
 
 int fill_spmm_params(SpmmParams& p, const mmssl_csr_t* a, int d, int nrhs, const mmssl_spmm_rhs_t* rhs, int epilogue,
@@ -274,9 +286,9 @@ extern "C" int mmssl_spmm_csr_f32(const mmssl_csr_t* a, int d, int nrhs, const m
     const int T = (impl & 4) ? 128 : 256;
 #define MMSSL_SPMM_CASE(G, C)                                           \
     switch (nrhs) {                                                     \
-        case 1: return launch_spmm<G, C, 1>(p, stream, T);              \
-        case 2: return launch_spmm<G, C, 2>(p, stream, T);              \
-        default: return launch_spmm<G, C, 3>(p, stream, T);             \
+        case 1: return launch_spmm<G, C, 1>(p, stream, T, impl);        \
+        case 2: return launch_spmm<G, C, 2>(p, stream, T, impl);        \
+        default: return launch_spmm<G, C, 3>(p, stream, T, impl);       \
     }
     if (d == 64 && (impl & 2)) { MMSSL_SPMM_CASE(8, 2) }
     if (d == 64) { MMSSL_SPMM_CASE(16, 1) }

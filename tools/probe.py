@@ -57,7 +57,7 @@ def small(name):
     out["spmm_ui_in_graph_us"] = graph_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu]), inner=20)
     out["spmm_iu_in_graph_us"] = graph_time(lambda: ops.spmm(g_iu.fwd, [yu], [yi]), inner=20)
     out["spmm_ui_2rhs_in_graph_us"] = graph_time(lambda: ops.spmm(g_ui.fwd, [x2[:, :d], x2[:, d:]], [y2[:, :d], y2[:, d:]]), inner=20)
-    for impl in (0, 2, 4, 6):
+    for impl in (0, 4, 8, 12, 16, 20, 24):
         out[f"ui_impl{impl}_us"] = round(graph_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu], impl=impl), inner=20), 2)
         out[f"iu_impl{impl}_us"] = round(graph_time(lambda: ops.spmm(g_iu.fwd, [yu], [yi], impl=impl), inner=20), 2)
         out[f"ui2_impl{impl}_us"] = round(graph_time(lambda: ops.spmm(g_ui.fwd, [x2[:, :d], x2[:, d:]], [y2[:, :d], y2[:, d:]], impl=impl), inner=20), 2)
