@@ -281,6 +281,10 @@ extern "C" int mmssl_spmm_csr_f32(const mmssl_csr_t* a, int d, int nrhs, const m
     cudaStream_t stream = (cudaStream_t)stream_;
     SpmmParams p;
     if (int rc = fill_spmm_params(p, a, d, nrhs, rhs, epilogue, alpha, s_mode, partials, partials_floats)) return rc;
+    // impl 0 = automatic policy from measurements (tools/probe.py): small graphs are launch/latency
+    // bound and prefer 128-thread blocks; large graphs are bound by the number of resident row walks
+    // and prefer the register-capped variant (6 blocks/SM).
+    if (impl == 0) impl = (a->nnz >= (1ll << 21)) ? 16 : 4;
     // impl: bit 1 -> 8-lane groups for d = 64 (each lane owns two float4 slices; twice as many rows
     // resident per SM, so a small graph fits one wave); bit 2 -> 128-thread blocks.
     const int T = (impl & 4) ? 128 : 256;

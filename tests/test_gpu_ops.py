@@ -116,7 +116,7 @@ def test_spmm_impl_variants(impl, nrhs):
         assert rel_err(y, torch.from_numpy(ref @ x.double().cpu().numpy())) < 2e-6
 
 
-@pytest.mark.parametrize("d,nrhs", [(64, 1), (64, 3), (128, 2), (256, 1)])
+@pytest.mark.parametrize("d,nrhs", [(128, 1), (128, 2), (256, 1)])
 def test_spmm_tma_hot_rows(d, nrhs):
     """TMA-staged hot-row variant (impl=1): same results as the LDG kernel, incl. epilogues and split rows."""
     from mmssl_b200 import ops
