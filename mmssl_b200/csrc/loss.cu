@@ -119,8 +119,9 @@ __global__ void __launch_bounds__(256) nce_prepare_kernel(const float* __restric
 }
 
 constexpr int NT = 64;          // tile edge
-constexpr int NS = NT + 1;      // smem row stride (conflict-free column access)
-// thread (ty, tx) of a 256-thread block owns rows ty*4+ii and columns tx+16*jj of a 64x64 tile.
+constexpr int NS = NT + 4;      // smem row stride: float4-aligned rows, conflict-free 128-bit column access
+// 256 threads = 16 (ty) x 16 (tx).  Shared-memory traffic is what bounds these tiles, so every operand
+// is read with 128-bit loads along its contiguous axis (4 reduction steps per load).
 
 __device__ __forceinline__ void load_tile(float* sm, const float* __restrict__ src, int64_t row0, int64_t n, int d,
                                           int c0) {
@@ -129,54 +130,56 @@ __device__ __forceinline__ void load_tile(float* sm, const float* __restrict__ s
         const int r = e / (NT / 4), k4 = (e % (NT / 4)) * 4;
         float4 v = f4zero();
         if (row0 + r < n) v = ld4(src + (row0 + r) * (int64_t)d + c0 + k4);
-        float* o = sm + r * NS + k4;
-        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        *reinterpret_cast<float4*>(sm + r * NS + k4) = v;
     }
 }
 
-// acc[ii][jj] += sum_k X[ty*4+ii][k] * Y[tx+16*jj][k]
+// acc[ii][jj] += sum_k X[ty*4+ii][k] * Y[tx+16*jj][k]      (rows ty*4+ii, columns tx+16*jj)
 __device__ __forceinline__ void tile_nt(float (&acc)[4][4], const float* X, const float* Y, int ty, int tx) {
-#pragma unroll 8
-    for (int k = 0; k < NT; ++k) {
-        float xv[4], yv[4];
+#pragma unroll 4
+    for (int k = 0; k < NT; k += 4) {
+        float4 xv[4], yv[4];
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii) xv[ii] = X[(ty * 4 + ii) * NS + k];
+        for (int ii = 0; ii < 4; ++ii) xv[ii] = *reinterpret_cast<const float4*>(X + (ty * 4 + ii) * NS + k);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) yv[jj] = Y[(tx + 16 * jj) * NS + k];
+        for (int jj = 0; jj < 4; ++jj) yv[jj] = *reinterpret_cast<const float4*>(Y + (tx + 16 * jj) * NS + k);
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc[ii][jj] = fmaf(xv[ii], yv[jj], acc[ii][jj]);
+            for (int jj = 0; jj < 4; ++jj) acc[ii][jj] += dot4(xv[ii], yv[jj]);
     }
 }
-// acc[ii][jj] += sum_j P[ty*4+ii][j] * V[j][tx+16*jj]
+// acc[ii][jj] += sum_j P[ty*4+ii][j] * V[j][tx*4+jj]       (rows ty*4+ii, columns tx*4+jj)
 __device__ __forceinline__ void tile_nn(float (&acc)[4][4], const float* P, const float* V, int ty, int tx) {
-#pragma unroll 8
-    for (int j = 0; j < NT; ++j) {
-        float pv[4], vv[4];
+#pragma unroll 2
+    for (int j = 0; j < NT; j += 4) {
+        float4 pv[4];
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii) pv[ii] = P[(ty * 4 + ii) * NS + j];
+        for (int ii = 0; ii < 4; ++ii) pv[ii] = *reinterpret_cast<const float4*>(P + (ty * 4 + ii) * NS + j);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) vv[jj] = V[j * NS + tx + 16 * jj];
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(V + (j + q) * NS + tx * 4);
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc[ii][jj] = fmaf(pv[ii], vv[jj], acc[ii][jj]);
+            for (int ii = 0; ii < 4; ++ii) {
+                const float pq = q == 0 ? pv[ii].x : (q == 1 ? pv[ii].y : (q == 2 ? pv[ii].z : pv[ii].w));
+                acc[ii][0] = fmaf(pq, v.x, acc[ii][0]); acc[ii][1] = fmaf(pq, v.y, acc[ii][1]);
+                acc[ii][2] = fmaf(pq, v.z, acc[ii][2]); acc[ii][3] = fmaf(pq, v.w, acc[ii][3]);
+            }
+        }
     }
 }
-// acc[ii][jj] += sum_i Q[i][ty*4+ii] * V[i][tx+16*jj]
+// acc[ii][jj] += sum_i Q[i][ty*4+ii] * V[i][tx*4+jj]       (rows ty*4+ii, columns tx*4+jj)
 __device__ __forceinline__ void tile_tn(float (&acc)[4][4], const float* Q, const float* V, int ty, int tx) {
-#pragma unroll 8
+#pragma unroll 4
     for (int i = 0; i < NT; ++i) {
-        float qv[4], vv[4];
+        const float4 q = *reinterpret_cast<const float4*>(Q + i * NS + ty * 4);
+        const float4 v = *reinterpret_cast<const float4*>(V + i * NS + tx * 4);
+        const float qv[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii) qv[ii] = Q[i * NS + ty * 4 + ii];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) vv[jj] = V[i * NS + tx + 16 * jj];
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc[ii][jj] = fmaf(qv[ii], vv[jj], acc[ii][jj]);
+        for (int ii = 0; ii < 4; ++ii) {
+            acc[ii][0] = fmaf(qv[ii], v.x, acc[ii][0]); acc[ii][1] = fmaf(qv[ii], v.y, acc[ii][1]);
+            acc[ii][2] = fmaf(qv[ii], v.z, acc[ii][2]); acc[ii][3] = fmaf(qv[ii], v.w, acc[ii][3]);
+        }
     }
 }
 
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(256) nce_grad_kernel(const float* __restrict__
             const int64_t i = i0 + ty * 4 + ii, j = j0 + ty * 4 + ii;
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-                const int c = c0 + tx + 16 * jj;
+                const int c = c0 + tx * 4 + jj;
                 if (i < n) atomicAdd(ga + i * d + c, g1[ii][jj]);
                 if (j < n) atomicAdd(gb + j * d + c, g2[ii][jj]);
             }
