@@ -79,6 +79,24 @@ class Engine:
         self.two_streams = True
         self._side: Dict[Tuple, torch.cuda.Stream] = {}
 
+    def _pair(self, dev, fn_a, fn_b):
+        """Run two independent kernel groups concurrently (user side on the current stream, item side
+        on the 'pair' stream) and join.  Returns (fn_a(), fn_b())."""
+        if not self.two_streams:
+            return fn_a(), fn_b()
+        key = (dev.type, dev.index, "pair")
+        st = self._side.get(key)
+        if st is None:
+            st = torch.cuda.Stream(device=dev)
+            self._side[key] = st
+        main = torch.cuda.current_stream(dev)
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            rb = fn_b()
+        ra = fn_a()
+        main.wait_stream(st)
+        return ra, rb
+
     def _side_stream(self, dev) -> torch.cuda.Stream:
         key = (dev.type, dev.index)
         st = self._side.get(key)
@@ -175,8 +193,7 @@ class Engine:
             ya = one(ga)
             return (ya, ya) if ga is gb else (ya, one(gb))
 
-        uvid, utid = id_prop(g_vui, g_tui, e_i, U)
-        ivid, itid = id_prop(g_viu, g_tiu, e_u, I)
+        (uvid, utid), (ivid, itid) = self._pair(dev, lambda: id_prop(g_vui, g_tui, e_i, U), lambda: id_prop(g_viu, g_tiu, e_u, I))
         st = FwdState(tuple(graphs), resolved[0], X2, U2, I2, (uvid, utid, ivid, itid),
                       fused=any(g.nnz > 0 for g in (g_vui, g_viu, g_tui, g_tiu)))
         if st.fused:                                                                   # :188-197 (closed form)
@@ -198,8 +215,7 @@ class Engine:
                     out = self._new(e.shape[0], d, dev=dev)
                     return ops.id_fuse_fwd(z, e, self.id_rate, out)
 
-            u0, st.zn_u, st.nrm_u = fuse(uvid, utid, e_u)
-            i0, st.zn_i, st.nrm_i = fuse(ivid, itid, e_i)
+            (u0, st.zn_u, st.nrm_u), (i0, st.zn_i, st.nrm_i) = self._pair(dev, lambda: fuse(uvid, utid, e_u), lambda: fuse(ivid, itid, e_i))
         else:
             u0, i0 = e_u, e_i
         # GCN layers: u_{k+1} = A_ui i_k ; i_{k+1} = A_iu u_{k+1}; softmax on the last one (:201-211);
@@ -221,8 +237,9 @@ class Engine:
         inv = 1.0 / (K + 1)
         if side is not main:
             main.wait_stream(side)      # join: the combine needs Uv|Ut and Iv|It
-        u_f, st.sumsq_u = ops.combine_fwd(s_u, uv, ut, inv, self.cat_rate, self._new(U, d, dev=dev), want_sumsq)   # :213,217
-        i_f, st.sumsq_i = ops.combine_fwd(s_i, iv, it, inv, self.cat_rate, self._new(I, d, dev=dev), want_sumsq)   # :214,218
+        (u_f, st.sumsq_u), (i_f, st.sumsq_i) = self._pair(
+            dev, lambda: ops.combine_fwd(s_u, uv, ut, inv, self.cat_rate, self._new(U, d, dev=dev), want_sumsq),      # :213,217
+            lambda: ops.combine_fwd(s_i, iv, it, inv, self.cat_rate, self._new(I, d, dev=dev), want_sumsq))          # :214,218
         outs = (u_f, i_f, iv, it, uv, ut, uvid, utid, ivid, itid)
         return outs, st
 
@@ -266,8 +283,8 @@ class Engine:
         iv, it = st.I2[:, :d], st.I2[:, d:]
         # ---- combine backward (Models.py:213-218): through the two normalisations (+ feat_reg)
         gU2, gI2 = self._new(U, 2 * d, dev=dev), self._new(I, 2 * d, dev=dev)
-        ops.combine_bwd(g_uf, uv, ut, g_uv, g_ut, self.cat_rate, feat_reg_coef, gU2[:, :d], gU2[:, d:])
-        ops.combine_bwd(g_if, iv, it, g_iv, g_it, self.cat_rate, feat_reg_coef, gI2[:, :d], gI2[:, d:])
+        self._pair(dev, lambda: ops.combine_bwd(g_uf, uv, ut, g_uv, g_ut, self.cat_rate, feat_reg_coef, gU2[:, :d], gU2[:, d:]),
+                   lambda: ops.combine_bwd(g_if, iv, it, g_iv, g_it, self.cat_rate, feat_reg_coef, gI2[:, :d], gI2[:, d:]))
         main = torch.cuda.current_stream(dev)
         side = self._side_stream(dev) if self.two_streams else main
         w_slots = (slot(P_WV, P[P_WV]), slot(P_BV, P[P_BV]), slot(P_WT, P[P_WT]), slot(P_BT, P[P_BT]))
@@ -310,6 +327,7 @@ class Engine:
         # ---- id fusion backward (Models.py:188-197)
         uvid, utid, ivid, itid = st.id_out
         g_wcat = slot(P_WCAT, P[P_WCAT])
+        dwcat_args = None
         if st.fused and d in (64, 128):
             def fuse_bwd2(g0, zn, nrm, ya, yb, g_ya, g_yb):
                 same = ya is yb
@@ -317,9 +335,10 @@ class Engine:
                                                 self.id_rate, g_ya, g_yb, two_outputs=not same)
                 return oa, (oa if same else ob), part
 
-            gt_uvid, gt_utid, part_u = fuse_bwd2(g_eu, st.zn_u, st.nrm_u, uvid, utid, g_uvid, g_utid)
-            gt_ivid, gt_itid, part_i = fuse_bwd2(g_ei, st.zn_i, st.nrm_i, ivid, itid, g_ivid, g_itid)
-            ops.dwcat_reduce(part_u, part_i, d, self.H, g_wcat)
+            (gt_uvid, gt_utid, part_u), (gt_ivid, gt_itid, part_i) = self._pair(
+                dev, lambda: fuse_bwd2(g_eu, st.zn_u, st.nrm_u, uvid, utid, g_uvid, g_utid),
+                lambda: fuse_bwd2(g_ei, st.zn_i, st.nrm_i, ivid, itid, g_ivid, g_itid))
+            dwcat_args = (part_u, part_i)
         elif st.fused:
             d_wsum = torch.zeros(d, d, dtype=torch.float32, device=dev)
 
@@ -370,9 +389,14 @@ class Engine:
                 if g is not None and gr.nnz > 0:
                     ops.spmm(gr.bwd, [g], [g_e], cs=[g_e], alpha=1.0)
 
-        # Uvid = A_vui E_i, Utid = A_tui E_i -> gradient flows to E_i; Ivid/Itid -> E_u
-        id_prop_bwd(g_vui, g_tui, gt_uvid, gt_utid, g_ei, st.fused and uvid is utid)
-        id_prop_bwd(g_viu, g_tiu, gt_ivid, gt_itid, g_eu, st.fused and ivid is itid)
+        # Uvid = A_vui E_i, Utid = A_tui E_i -> gradient flows to E_i; Ivid/Itid -> E_u.  The head reduction
+        # of dWcat does not feed them, so it rides along on the pair stream.
+        def tail_b():
+            id_prop_bwd(g_viu, g_tiu, gt_ivid, gt_itid, g_eu, st.fused and ivid is itid)
+            if dwcat_args is not None:
+                ops.dwcat_reduce(dwcat_args[0], dwcat_args[1], d, self.H, g_wcat)
+
+        self._pair(dev, lambda: id_prop_bwd(g_vui, g_tui, gt_uvid, gt_utid, g_ei, st.fused and uvid is utid), tail_b)
         if side is not main:
             main.wait_stream(side)
         return res
