@@ -199,6 +199,17 @@ int mmssl_adamw(int n_tensors, float* const* p /*host array of device ptrs*/, co
                 float* const* v, const int64_t* numel /*host*/, const int32_t* step_dev, float lr, float beta1,
                 float beta2, float eps, float weight_decay, void* stream);
 
+/* ------------------------------------------------------------------ GPU triple sampler (SURVEY 8f "next" #1)
+ * Semantics of Data.sample (utility/load_data.py:153-191): `batch` (<= 1024) distinct users with >= 1
+ * training item (with replacement only if batch > n_exist), one uniform positive from the user's CSR row
+ * (indptr/indices int64, rows sorted), one uniform negative rejected against the row.  Counter-based RNG
+ * keyed by (seed, step); step is read from *step_dev when non-NULL (graph replay), else step_host.
+ * claim[n_exist] is a work table initialised once with mmssl_sampler_init and left clean by every launch. */
+int mmssl_sampler_init(int32_t* claim, int64_t n_exist, void* stream);
+int mmssl_sample_triples(const int64_t* indptr, const int64_t* indices, const int64_t* exist, int64_t n_exist,
+                         int64_t n_items, int batch, uint64_t seed, const int32_t* step_dev, int32_t step_host,
+                         int32_t* claim, int64_t* users, int64_t* pos, int64_t* neg, void* stream);
+
 /* ------------------------------------------------------------------ projection (tcgen05 + TMA), see proj_tc.cu */
 int mmssl_split_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo, int64_t ldo,
                      void* stream);

@@ -394,3 +394,37 @@ def test_dropout_mask_from_ones_matches_torch_stream():
     torch.manual_seed(123); a = F.dropout(x, 0.2, True)
     torch.manual_seed(123); m = F.dropout(torch.ones_like(x), 0.2, True)
     assert torch.equal(a, x * m)
+
+
+def test_device_triple_sampler_semantics():
+    """GPU sampler vs the semantics of Data.sample (load_data.py:153-191)."""
+    from mmssl_b200.sampler import DeviceTripleSampler
+    from mmssl_b200.synthetic import make_dataset
+    ds = make_dataset("tiktok")
+    smp = DeviceTripleSampler(ds.train, seed=7)
+    dense_row = lambda u: set(ds.train.indices[ds.train.indptr[u]:ds.train.indptr[u + 1]].tolist())
+    out = torch.empty(3, 1024, dtype=torch.int64, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    seen_users, pos_hits = [], 0
+    batches = []
+    for s in range(20):
+        step.fill_(s)
+        smp.sample_into(out, step_dev=step)
+        u, p, n = (t.cpu().numpy() for t in out)
+        batches.append((u.copy(), p.copy(), n.copy()))
+        assert len(set(u.tolist())) == 1024                                    # distinct users
+        assert (np.diff(ds.train.indptr)[u] > 0).all()                         # users with >= 1 item
+        for k in range(0, 1024, 37):
+            row = dense_row(int(u[k]))
+            assert int(p[k]) in row and int(n[k]) not in row
+        seen_users.append(u)
+    assert int((smp.claim != 0x7fffffff).sum()) == 0                           # claim table left clean
+    # deterministic in (seed, step); different steps differ
+    step.fill_(3)
+    smp.sample_into(out, step_dev=step)
+    assert np.array_equal(out[0].cpu().numpy(), batches[3][0]) and np.array_equal(out[2].cpu().numpy(), batches[3][2])
+    assert not np.array_equal(batches[3][0], batches[4][0])
+    # roughly uniform over users: every user should be hit about 20*1024/U times
+    cnt = np.bincount(np.concatenate(seen_users), minlength=ds.n_users)
+    exp = 20 * 1024 / ds.n_users
+    assert abs(cnt.mean() - exp) < 1e-9 and cnt.max() < exp * 5 + 10
