@@ -140,10 +140,10 @@ def build_problem(name: str, seed: int, device):
 class HotStepTrainer:
     """Public API of the fused path: ``train_step(users, pos, neg) -> float loss`` (host in, host out)."""
 
-    def __init__(self, P, feats, graphs, cfg, batch, world=1):
+    def __init__(self, P, feats, graphs, cfg, batch, world=1, sampler=None):
         from mmssl_b200.hotstep import HotStep
         self.world = world
-        self.hs = HotStep(P, feats, graphs, cfg, batch=batch, optimizer_step=(world == 1))
+        self.hs = HotStep(P, feats, graphs, cfg, batch=batch, optimizer_step=(world == 1), sampler=sampler)
         self.pin_idx = torch.empty(3, batch, dtype=torch.int64).pin_memory()
         self.pin_out = torch.empty(5, dtype=torch.float32).pin_memory()
         if world > 1:
@@ -168,6 +168,14 @@ class HotStepTrainer:
         self.hs.idx.copy_(idx_dev, non_blocking=True)
         self.hs.replay()
         self._finish_step()
+
+    def train_step_device_sampled(self) -> float:
+        """Batch drawn by the GPU sampler inside the graph: no host input, the loss is the only transfer."""
+        self.hs.replay()
+        self._finish_step()
+        self.pin_out.copy_(self.hs.out5, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.pin_out[0])
 
     def train_step(self, users, pos, neg) -> float:
         self.pin_idx[0].copy_(torch.as_tensor(users)); self.pin_idx[1].copy_(torch.as_tensor(pos)); self.pin_idx[2].copy_(torch.as_tensor(neg))
@@ -384,6 +392,22 @@ def main():
                         "d2h_bytes_per_step": 5 * 4, "ms_per_step": round(ms_e2e / a.steps, 4), "last_loss": round(last_loss, 6)},
                 "roofline": roof, "roofline_spmm": roofs["spmm"], "roofline_projection": roofs["projection"],
                 "launches_per_step": launches_per_step}
+        if world == 1:      # batches drawn on the device (no host sampler, no H2D)
+            from mmssl_b200.sampler import DeviceTripleSampler
+            P2 = {k: v.clone() for k, v in P.items()}
+            tr2 = HotStepTrainer(P2, feats, graphs, cfg, BATCH, world=1, sampler=DeviceTripleSampler(ds.train, device=dev, seed=a.seed))
+            for _ in range(3):
+                tr2.train_step_device_sampled()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(a.steps):
+                tr2.train_step_device_sampled()
+            g1.record()
+            torch.cuda.synchronize()
+            ms = g0.elapsed_time(g1)
+            line["device_sampler_e2e"] = {"value": round(BATCH * a.steps / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms / a.steps, 4),
+                                          "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 20}
         if not a.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(a.config, a.seed, a.cpu_steps, BATCH)
         print(json.dumps(line))

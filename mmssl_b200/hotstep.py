@@ -42,7 +42,7 @@ class HotStepConfig:
 
 class HotStep:
     def __init__(self, params: Dict[str, torch.Tensor], feats: Sequence[FeatureStore], graphs: Sequence[BipartiteGraph],
-                 cfg: HotStepConfig, batch: int, optimizer_step: bool = True):
+                 cfg: HotStepConfig, batch: int, optimizer_step: bool = True, sampler=None):
         self.cfg = cfg
         self.P = {k: params[k] for k in LIVE}
         for k, t in self.P.items():
@@ -52,6 +52,7 @@ class HotStep:
         self.U, self.I = graphs[0].shape
         self.batch = batch
         self.optimizer_step = optimizer_step
+        self.sampler = sampler          # optional sampler.DeviceTripleSampler: batches are drawn on the device
         dev = self.P[P_EU].device
         d = cfg.embed_size
         f = dict(dtype=torch.float32, device=dev)
@@ -93,8 +94,12 @@ class HotStep:
         users, pos, neg = self.idx[0], self.idx[1], self.idx[2]
         # the seed-buffer memset and the dropout masks are only needed by the modality branch / the
         # loss kernels, so they run at the head of the side stream, off the critical path
-        outs, st = self.engine.forward(self.P, self.feats, self.graphs, self._masks, want_sumsq=True,
-                                       side_pre=self.gflat.zero_)
+        def side_pre():
+            self.gflat.zero_()
+            if self.sampler is not None:      # (seed, optimiser step) -> a fresh batch on every graph replay
+                self.sampler.sample_into(self.idx, step_dev=self.step_dev)
+
+        outs, st = self.engine.forward(self.P, self.feats, self.graphs, self._masks, want_sumsq=True, side_pre=side_pre)
         u_f, i_f, _, _, _, _, u_vid, u_tid, _, _ = outs
         reg_coef = cfg.emb_decay / cfg.batch_size
         # BPR: value partials + gradient rows scattered straight into the dense table gradients
