@@ -50,7 +50,8 @@ def parse():
     ap.add_argument("--proj", default="tc", choices=["tc", "simt"])
     ap.add_argument("--spmm-impl", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--cpu-threads", type=int, default=0, help="0 = the count that measured fastest on this host class (tools/cpu_threads.py)")
     ap.add_argument("--seed", type=int, default=2022)
     return ap.parse_args()
 
@@ -247,12 +248,17 @@ def roofline_objects(ds, P, feats, graphs, hbm_peak, peak_src, dev):
     return out
 
 
-def cpu_baseline(name, seed, steps, batch):
-    """The oracle port of the reference's CPU path (stock torch CPU ops), all host threads."""
+CPU_THREADS_DEFAULT = 8      # fastest of {8,16,32,64,128} on the box's 128-thread Xeon 8562Y+: 0.37 s/step vs 40 s/step at 128
+                             # threads (profiles/r01_cpu_threads.txt) -- the baseline is reported at its best setting
+
+
+def cpu_baseline(name, seed, steps, batch, threads=0):
+    """The oracle port of the reference's CPU path (stock torch CPU ops) on the host cores.  The thread
+    count is the one that measured fastest (more threads make torch's sparse kernels slower here)."""
     from oracle import mmssl_oracle as O
     from mmssl_b200.synthetic import TripleSampler
     ds, P, feats_cpu, _, _ = build_problem(name, seed, None)
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(min(os.cpu_count(), threads if threads > 0 else CPU_THREADS_DEFAULT))
     cfg = O.HotPathConfig(embed_size=ds.embed_size, n_layers=ds.n_layers, batch_size=batch)
     ui, iu = O.to_torch_coo(ds.ui_norm), O.to_torch_coo(ds.iu_norm)
     graphs = (ui, iu, ui, iu, ui, iu)
@@ -296,8 +302,11 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        cb = cpu_baseline(a.config, a.seed, max(a.steps, 1), BATCH)
-        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        # bounded sample: a CPU hot step of this workload takes ~0.4 s at the best thread count; cap the run at ~1 minute
+        executed = max(1, min(a.steps, 100))
+        cb = cpu_baseline(a.config, a.seed, executed, BATCH, a.cpu_threads)
+        cb["sample"] += f" ({executed} of the requested {a.steps} steps executed: bounded sample)"
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": executed,
                 "warmup": 1, "ms_per_step": round(cb["s_per_step"] * 1e3, 3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -409,7 +418,7 @@ def main():
             line["device_sampler_e2e"] = {"value": round(BATCH * a.steps / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms / a.steps, 4),
                                           "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 20}
         if not a.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(a.config, a.seed, a.cpu_steps, BATCH)
+            line["cpu_baseline"] = cpu_baseline(a.config, a.seed, a.cpu_steps, BATCH, a.cpu_threads)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
