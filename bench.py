@@ -43,8 +43,8 @@ UNIT = "triples/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--config", default="baby")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--proj", default="tc", choices=["tc", "simt"])

@@ -12,8 +12,6 @@
 // persistent (one CTA of 1024 threads per SM) so the staging cost is paid once per SM per launch.
 // `colidx_hot` is the operand's column index array with hot columns encoded as -(slot+1)
 // (slots ordered by decreasing degree; slots beyond the staged count fall back to hot_ids[slot]).
-#include <stdlib.h>
-
 #include "spmm_common.cuh"
 
 namespace mmssl {
@@ -264,7 +262,6 @@ extern "C" int mmssl_spmm_hot_f32(const mmssl_csr_t* a, const int32_t* colidx_ho
                                   float* partials, int64_t partials_floats, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MMSSL_REQUIRE(colidx_hot != nullptr && hot_ids != nullptr && n_hot >= 0, "missing hot-column plan");
-    MMSSL_REQUIRE(d >= 128 || getenv("MMSSL_HOT_ALLOW_D64") != nullptr, "the TMA-staged variant is validated for d = 128 / 256 only (experimental; slower than the LDG kernel, see DESIGN.md)");
     SpmmParams p;
     if (int rc = fill_spmm_params(p, a, d, nrhs, rhs, epilogue, alpha, s_mode, partials, partials_floats)) return rc;
     for (int r = 0; r < nrhs; ++r) MMSSL_REQUIRE(p.ldx[r] % 4 == 0, "TMA staging needs 16-byte aligned rows");

@@ -116,7 +116,7 @@ def test_spmm_impl_variants(impl, nrhs):
         assert rel_err(y, torch.from_numpy(ref @ x.double().cpu().numpy())) < 2e-6
 
 
-@pytest.mark.parametrize("d,nrhs", [(128, 1), (128, 2), (256, 1)])
+@pytest.mark.parametrize("d,nrhs", [(64, 1), (64, 3), (128, 2), (256, 1)])
 def test_spmm_tma_hot_rows(d, nrhs):
     """TMA-staged hot-row variant (impl=1): same results as the LDG kernel, incl. epilogues and split rows."""
     from mmssl_b200 import ops
@@ -135,11 +135,11 @@ def test_spmm_tma_hot_rows(d, nrhs):
     ys = ops.spmm(g.fwd, xs, impl=ops.SPMM_IMPL_TMA)
     assert g.fwd.hot_edge_fraction > 0.3
     for x, y in zip(xs, ys):
-        assert rel_err(y, torch.from_numpy(ref @ x.double().cpu().numpy())) < 2e-6
+        assert rel_err(y, torch.from_numpy(ref @ x.double().cpu().numpy())) < 1e-5
     a = ops.spmm(g.fwd, xs, cs=cs, alpha=0.5, epilogue=ops.EPI_SOFTMAX, impl=0)
     b = ops.spmm(g.fwd, xs, cs=cs, alpha=0.5, epilogue=ops.EPI_SOFTMAX, impl=ops.SPMM_IMPL_TMA)
     for u, w in zip(a, b):
-        assert rel_err(w, u) < 2e-6
+        assert rel_err(w, u) < 1e-5
     yt = ops.spmm(g.bwd, [torch.randn(n_rows, d, device="cuda")], impl=ops.SPMM_IMPL_TMA)[0]   # A^T: hot set = heavy rows of A
     assert yt.shape == (n_cols, d) and torch.isfinite(yt).all()
 
