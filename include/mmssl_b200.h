@@ -78,6 +78,11 @@ typedef struct {
     const float* ysaved; int64_t ldysaved; /* MMSSL_EPI_SOFTMAX_BWD only */
     float* s; int64_t lds;                 /* optional running sum */
     const float* sbase; int64_t ldsbase;   /* s_mode 2: S = sbase + y */
+    /* fused all-gather (row-sharded tables): where the output rows go
+     *   0: y (local);  1: y is an NVSwitch MULTICAST address -> one multimem.st per 16 bytes lands in every
+     *   GPU's table;  2: additionally stored to the n_peers peer-mapped tables y_peers[] over NVLink. */
+    int32_t y_mode; int32_t n_peers;
+    float* y_peers[8];
 } mmssl_spmm_rhs_t;
 /* d in {64,128,256}; nrhs in 1..3 (all right-hand sides share A and d).  s_mode: 0 none, 1 S += y, 2 S = sbase + y.
  * `partials` = zero-initialised scratch for split rows, >= a->segs_cap * nrhs * d floats (left clean by the kernel).

@@ -28,7 +28,8 @@ class CsrDesc(C.Structure):
 class SpmmRhs(C.Structure):
     """mmssl_spmm_rhs_t"""
     _fields_ = [("x", c_vp), ("ldx", c_i64), ("y", c_vp), ("ldy", c_i64), ("c", c_vp), ("ldc", c_i64),
-                ("ysaved", c_vp), ("ldysaved", c_i64), ("s", c_vp), ("lds", c_i64), ("sbase", c_vp), ("ldsbase", c_i64)]
+                ("ysaved", c_vp), ("ldysaved", c_i64), ("s", c_vp), ("lds", c_i64), ("sbase", c_vp), ("ldsbase", c_i64),
+                ("y_mode", C.c_int32), ("n_peers", C.c_int32), ("y_peers", c_vp * 8)]
 
 
 _SIGS = {

@@ -196,7 +196,17 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
             }
         }
 #pragma unroll
-        for (int c = 0; c < C; ++c) st4(p.y[r] + (int64_t)row * p.ldy[r] + col0 + c * (4 * G), acc[r][c]);
+        for (int c = 0; c < C; ++c) {
+            const int64_t off = (int64_t)row * p.ldy[r] + col0 + c * (4 * G);
+            if (p.y_mode[r] == 1) {           // NVSwitch multicast: the store is replicated into every GPU's table
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.y[r] + off), "f"(acc[r][c].x),
+                             "f"(acc[r][c].y), "f"(acc[r][c].z), "f"(acc[r][c].w) : "memory");
+            } else {
+                st4(p.y[r] + off, acc[r][c]);
+                if (p.y_mode[r] == 2)         // peer-mapped tables over NVLink
+                    for (int q = 0; q < p.n_peers[r]; ++q) st4(p.y_peers[r][q] + off, acc[r][c]);
+            }
+        }
         if (p.s_mode != 0 && p.s[r] != nullptr) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -251,6 +261,9 @@ int fill_spmm_params(SpmmParams& p, const mmssl_csr_t* a, int d, int nrhs, const
         MMSSL_REQUIRE(q.x && q.y, "null X or Y");
         MMSSL_REQUIRE(aligned16(q.x) && aligned16(q.y) && q.ldx % 4 == 0 && q.ldy % 4 == 0, "X/Y must be 16-byte aligned with ld % 4 == 0");
         p.x[r] = q.x; p.ldx[r] = q.ldx; p.y[r] = q.y; p.ldy[r] = q.ldy;
+        MMSSL_REQUIRE(q.y_mode >= 0 && q.y_mode <= 2 && q.n_peers >= 0 && q.n_peers <= 8, "bad y_mode / n_peers");
+        p.y_mode[r] = q.y_mode; p.n_peers[r] = q.n_peers;
+        for (int k = 0; k < q.n_peers; ++k) { MMSSL_REQUIRE(aligned16(q.y_peers[k]), "peer table alignment"); p.y_peers[r][k] = q.y_peers[k]; }
         if (q.c) {
             MMSSL_REQUIRE(aligned16(q.c) && q.ldc % 4 == 0, "C alignment");
             p.c[r] = q.c; p.ldc[r] = q.ldc; p.has_c = 1;

@@ -26,6 +26,9 @@ struct SpmmParams {
     int epilogue;   // MMSSL_EPI_*
     int s_mode;     // 0 none, 1: S += out, 2: S = SB + out
     int has_c;
+    int y_mode[kMaxRhs];            // 0 local, 1 multicast (multimem.st), 2 local + peers
+    int n_peers[kMaxRhs];
+    float* y_peers[kMaxRhs][8];
 };
 
 // G lanes per group, C float4 chunks per lane per rhs (d = 4*G*C), R right-hand sides.
@@ -80,7 +83,17 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, float4 (&acc)
             }
         }
 #pragma unroll
-        for (int c = 0; c < C; ++c) st4(p.y[r] + (int64_t)row * p.ldy[r] + col0 + c * (4 * G), acc[r][c]);
+        for (int c = 0; c < C; ++c) {
+            const int64_t off = (int64_t)row * p.ldy[r] + col0 + c * (4 * G);
+            if (p.y_mode[r] == 1) {           // NVSwitch multicast: the store is replicated into every GPU's table
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.y[r] + off), "f"(acc[r][c].x),
+                             "f"(acc[r][c].y), "f"(acc[r][c].z), "f"(acc[r][c].w) : "memory");
+            } else {
+                st4(p.y[r] + off, acc[r][c]);
+                if (p.y_mode[r] == 2)         // peer-mapped tables over NVLink
+                    for (int q = 0; q < p.n_peers[r]; ++q) st4(p.y_peers[r][q] + off, acc[r][c]);
+            }
+        }
         if (p.s_mode != 0 && p.s[r] != nullptr) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {

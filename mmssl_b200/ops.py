@@ -53,8 +53,12 @@ def spmm(a: SparseOperand, xs: Sequence[torch.Tensor], ys: Optional[Sequence[tor
          epilogue: int = EPI_NONE, alpha: float = 1.0, cs: Optional[Sequence[Optional[torch.Tensor]]] = None,
          ysaved: Optional[Sequence[torch.Tensor]] = None, ss: Optional[Sequence[Optional[torch.Tensor]]] = None,
          s_mode: int = 0, sbases: Optional[Sequence[Optional[torch.Tensor]]] = None,
-         impl: Optional[int] = None) -> List[torch.Tensor]:
-    """Y_r = epi(A @ X_r + alpha * C_r), optional running sums; see mmssl_spmm_csr_f32."""
+         impl: Optional[int] = None, y_mode: int = 0, y_raw: Optional[Sequence[int]] = None,
+         y_peers: Optional[Sequence[Sequence[int]]] = None) -> List[torch.Tensor]:
+    """Y_r = epi(A @ X_r + alpha * C_r), optional running sums; see mmssl_spmm_csr_f32.
+    Fused all-gather (row-sharded tables): y_mode=1 with y_raw[r] = multicast address of the rank's row block
+    (ys[r] = the local view of the same rows, used for shape/stride only), or y_mode=2 with y_peers[r] = the
+    peer-mapped addresses of that row block on the other ranks."""
     lib = _lib_()
     nrhs = len(xs)
     d = xs[0].shape[1]
@@ -74,6 +78,14 @@ def spmm(a: SparseOperand, xs: Sequence[torch.Tensor], ys: Optional[Sequence[tor
             if t is not None:
                 _row_ok(t)
         rhs[r] = SpmmRhs(ptr(x), _ld(x), ptr(y), _ld(y), ptr(c), _ld(c), ptr(yv), _ld(yv), ptr(s), _ld(s), ptr(sb), _ld(sb))
+        if y_mode == 1:
+            rhs[r].y = int(y_raw[r])
+            rhs[r].y_mode = 1
+        elif y_mode == 2:
+            rhs[r].y_mode = 2
+            rhs[r].n_peers = len(y_peers[r])
+            for k, pp in enumerate(y_peers[r]):
+                rhs[r].y_peers[k] = int(pp)
     # split-row work area (partial sums + arrival counters), private to (operand, total width): launches
     # of different widths may run concurrently on two streams, and heavy rows need zeroed slots
     part, counters = a.work_area(nrhs * d)

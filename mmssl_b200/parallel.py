@@ -153,6 +153,100 @@ class RowShardedGCN:
         return g_su_local, t_loc
 
 
+# ------------------------------------------------------------------------------------------ fused SpMM + all-gather
+class SymmetricTable:
+    """A full [world*block, d] fp32 table that exists at the same place on every rank (CUDA symmetric
+    memory).  A rank's SpMM writes its row block straight into EVERY rank's copy from the kernel
+    epilogue -- one `multimem.st` per 16 bytes through the NVSwitch multicast address when available,
+    else one NVLink store per peer -- so the all-gather is part of the SpMM and no NCCL call is made;
+    `barrier()` (device-side signal pads) orders producers and consumers."""
+
+    def __init__(self, part: RowPartition, d: int, rank: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.part, self.d, self.rank = part, d, rank
+        self.t = symm.empty(part.world * part.block, d, dtype=torch.float32, device=device)
+        self.t.zero_()
+        g = group if group is not None else dist.group.WORLD
+        self.h = symm.rendezvous(self.t, g.group_name)
+        self.ptrs = [int(p) for p in self.h.buffer_ptrs]
+        mc = 0
+        try:
+            mc = int(self.h.multicast_ptr)
+        except Exception:
+            mc = 0
+        self.mc = mc
+        self.row_bytes = d * 4
+
+    @property
+    def multicast(self) -> bool:
+        return self.mc != 0
+
+    def local_rows(self) -> torch.Tensor:
+        lo = self.rank * self.part.block
+        return self.t[lo:lo + self.part.block]
+
+    def full(self) -> torch.Tensor:
+        return self.t[:self.part.n]
+
+    def out_spec(self):
+        """kwargs for ops.spmm so that the output rows land in every rank's table."""
+        off = self.rank * self.part.block * self.row_bytes
+        if self.multicast:
+            return dict(y_mode=1, y_raw=[self.mc + off])
+        return dict(y_mode=2, y_peers=[[p + off for r, p in enumerate(self.ptrs) if r != self.rank]])
+
+    def barrier(self):
+        self.h.barrier()
+
+
+class FusedRowShardedGCN(RowShardedGCN):
+    """RowShardedGCN whose exchanges are fused into the SpMM epilogue (no NCCL on the data path)."""
+
+    def __init__(self, operands, part_u, part_i, n_layers, rank, d, device, group=None):
+        super().__init__(operands, part_u, part_i, n_layers, cuda_spmm_fn, cuda_softmax_bwd_fn, rank, group)
+        mk = lambda part: SymmetricTable(part, d, rank, device, group)
+        self.tab = {"u": mk(part_u), "i": mk(part_i), "gu": mk(part_u), "gi": mk(part_i)}
+
+    def _spmm_into(self, op, x_full, table: SymmetricTable, **kw):
+        from . import ops
+        y_local = table.local_rows()
+        ops.spmm(op, [x_full.contiguous()], [y_local], cs=[kw["c"]] if kw.get("c") is not None else None,
+                 alpha=kw.get("alpha", 1.0), epilogue=kw.get("epilogue", EPI_NONE),
+                 ysaved=[kw["ysaved"]] if kw.get("ysaved") is not None else None, **table.out_spec())
+        table.barrier()
+        self.n_gathers += 1
+        self.gathered_bytes += y_local.numel() * 4 * (table.part.world - 1)
+        return y_local, table.full()
+
+    def forward(self, u0_local, i0_local):
+        s_u, s_i = u0_local.clone(), i0_local.clone()
+        cur_i = self._gather(i0_local, self.pi)            # i_0 is not an SpMM output: plain all-gather
+        u_last = i_last = None
+        for k in range(self.K):
+            last = k == self.K - 1
+            epi = EPI_SOFTMAX if last else EPI_NONE
+            u_loc, u_full = self._spmm_into(self.ops["ui"], cur_i, self.tab["u"], epilogue=epi)
+            s_u += u_loc
+            i_loc, cur_i = self._spmm_into(self.ops["iu"], u_full, self.tab["i"], epilogue=epi)
+            s_i += i_loc
+            if last:
+                u_last, i_last = u_loc.clone(), i_loc.clone()
+        return s_u, s_i, (u_last, i_last)
+
+    def backward(self, saved, g_su_local, g_si_local):
+        u_last, i_last = saved
+        if self.K == 0:
+            return g_su_local, g_si_local
+        t_loc = self.softmax_bwd(i_last, g_si_local, 1.0)
+        t_full = self._gather(t_loc, self.pi)               # first exchange: not an SpMM output
+        for k in range(self.K - 1, -1, -1):
+            last = k == self.K - 1
+            _, tu_full = self._spmm_into(self.ops["iuT"], t_full, self.tab["gu"], c=g_su_local, alpha=1.0,
+                                         epilogue=EPI_SOFTMAX_BWD if last else EPI_NONE, ysaved=u_last if last else None)
+            t_loc, t_full = self._spmm_into(self.ops["uiT"], tu_full, self.tab["gi"], c=g_si_local, alpha=1.0)
+        return g_su_local, t_loc.clone()
+
+
 # ------------------------------------------------------------------------------------------ CUDA binding
 def cuda_operands_from_scipy(ui_norm, iu_norm, part_u: RowPartition, part_i: RowPartition, rank: int, device):
     """Row blocks of A_ui, A_iu and of their transposes as prepared CUDA SpMM operands."""

@@ -22,7 +22,11 @@ ops_ = par.cuda_operands_from_scipy(ds.ui_norm, ds.iu_norm, pu, pi, rank, dev)
 g = torch.Generator().manual_seed(0)
 u0, i0 = torch.randn(U, d, generator=g) * 0.1, torch.randn(I, d, generator=g) * 0.1
 gu, gi = torch.randn(U, d, generator=g), torch.randn(I, d, generator=g)
-gcn = par.RowShardedGCN(ops_, pu, pi, K, par.cuda_spmm_fn, par.cuda_softmax_bwd_fn, rank)
+fused = "fused" in sys.argv and world > 1
+if fused:
+    gcn = par.FusedRowShardedGCN(ops_, pu, pi, K, rank, d, dev)
+else:
+    gcn = par.RowShardedGCN(ops_, pu, pi, K, par.cuda_spmm_fn, par.cuda_softmax_bwd_fn, rank)
 loc = lambda t, p: p.local(t, rank).to(dev)
 u0l, i0l, gul, gil = loc(u0, pu), loc(i0, pi), loc(gu, pu), loc(gi, pi)
 
@@ -48,7 +52,7 @@ torch.cuda.synchronize()
 ms = torch.tensor([a.elapsed_time(b) / steps], device=dev)
 if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-res = {"config": name, "n_gpus": world, "ms_per_chain_fwd_bwd": round(float(ms), 4), "gathers_per_chain": gcn.n_gathers // steps,
+res = {"config": name, "n_gpus": world, "exchange": ("fused-in-SpMM " + ("multicast" if gcn.tab["u"].multicast else "peer stores")) if fused else "nccl all-gather", "ms_per_chain_fwd_bwd": round(float(ms), 4), "gathers_per_chain": gcn.n_gathers // steps,
        "gathered_MB_per_rank_per_chain": round(gcn.gathered_bytes / steps / 1e6, 2), "spmm_per_chain": 4 * K}
 if check:   # parity of the sharded chain against the single-GPU engine kernels on rank 0's full graph
     s_u, s_i, (g_u0, g_i0) = out
