@@ -17,10 +17,12 @@ struct AdamPack {
     int n;
 };
 
-__global__ void step_tick_kernel(int32_t* step) { *step += 1; }
+__global__ void step_tick_kernel(int32_t* step) {
+    pdl_wait(); *step += 1; }
 
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamPack pk, const int32_t* __restrict__ step_dev, float lr,
                                                     float b1, float b2, float eps, float wd) {
+    pdl_wait();
     const int step = *step_dev;
     const float bc1 = 1.f - powf(b1, (float)step);
     const float bc2 = 1.f - powf(b2, (float)step);
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamPack pk, const int
 using namespace mmssl;
 
 extern "C" int mmssl_step_tick(int32_t* step_dev, void* stream_) {
-    step_tick_kernel<<<1, 1, 0, (cudaStream_t)stream_>>>(step_dev);
+    MMSSL_CUDA_LAUNCH((step_tick_kernel), dim3(1), dim3(1), 0, (cudaStream_t)stream_, step_dev);
     MMSSL_LAUNCH_OK();
     return 0;
 }
@@ -89,7 +91,7 @@ extern "C" int mmssl_adamw(int n_tensors, float* const* p, const float* const* g
     if (acc == 0) return 0;
     int64_t blocks = (acc + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(pk, step_dev, lr, beta1, beta2, eps, weight_decay);
+    MMSSL_CUDA_LAUNCH((adamw_kernel), dim3((unsigned)blocks), dim3(256), 0, st, pk, step_dev, lr, beta1, beta2, eps, weight_decay);
     MMSSL_LAUNCH_OK();
     return 0;
 }

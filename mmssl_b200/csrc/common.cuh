@@ -34,6 +34,29 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 constexpr int kNumSMs = 148;   // B200
 
+// ---- programmatic dependent launch (PDL) ----
+// Kernels on the critical path of the captured step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's launch and prologue overlap the
+// tail of its predecessor, and `pdl_wait()` (griddepcontrol.wait, first statement of every such kernel)
+// blocks until the predecessor has fully completed and flushed.  MMSSL_PDL=0 disables it.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    if (pdl_enabled()) { cfg.attrs = &attr; cfg.numAttrs = 1; }
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#define MMSSL_CUDA_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \
+    do {                                                                                                   \
+        cudaError_t e__ = ::mmssl::launch_k(kernel, grid, block, smem, stream, __VA_ARGS__);               \
+        if (e__ != cudaSuccess) return ::mmssl::fail_cuda(__func__, e__);                                   \
+    } while (0)
+
 // ---- device helpers ----
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }

@@ -1,4 +1,6 @@
 // Error reporting, ABI version and device check for libmmssl_b200.so.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/mmssl_b200.h"
 
@@ -8,6 +10,11 @@ char* last_error_buffer() { return g_err; }
 int fail(const char* where, const char* what) {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, what);
     return 1;
+}
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MMSSL_PDL"); v = (e == nullptr || e[0] != '0') ? 1 : 0; }
+    return v == 1;
 }
 int fail_cuda(const char* where, cudaError_t e) {
     snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s)", where, (int)e, cudaGetErrorString(e));

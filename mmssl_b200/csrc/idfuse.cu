@@ -19,6 +19,7 @@ constexpr int TR = 64;   // rows per block tile; 256 threads = 16 (ty: rows ty*4
 // wsum[k][c] = sum_h wcat[h][k][c] ; wsum_t[c][k] = the same transposed
 __global__ void wsum_kernel(const float* __restrict__ wcat, int d, int heads, float* __restrict__ wsum,
                             float* __restrict__ wsum_t) {
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d * d) return;
     float s = 0.f;
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(256) id_fuse2_fwd_kernel(const float* __restri
                                                            const float* __restrict__ wsum, const float* __restrict__ e,
                                                            int64_t lde, int64_t n, float rate, float* __restrict__ out,
                                                            int64_t ldo, float* __restrict__ zn, float* __restrict__ nrm) {
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     float* Ws = sm;              // [D][D]
     float* Ms = sm + D * D;      // [TR][D]
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(256) id_fuse2_bwd_kernel(const float* __restri
                                                            float* __restrict__ out_a, int64_t ldoa,
                                                            float* __restrict__ out_b, int64_t ldob,
                                                            float* __restrict__ dw_part) {
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     float* Wt = sm;                   // [D][D]: Wt[c][k] = Wsum[k][c]
     float* Ms = sm + D * D;           // [TR][D]  m rows
@@ -222,6 +225,7 @@ __global__ void __launch_bounds__(256) id_fuse2_bwd_kernel(const float* __restri
 __global__ void __launch_bounds__(256) dwcat_reduce_kernel(const float* __restrict__ part_u, int nu,
                                                            const float* __restrict__ part_i, int ni, int d, int heads,
                                                            float* __restrict__ dwcat) {
+    pdl_wait();
     __shared__ float red[4][64];
     const int o = threadIdx.x & 63, sl = threadIdx.x >> 6;
     const int i = blockIdx.x * 64 + o;
@@ -258,7 +262,7 @@ using namespace mmssl;
 
 extern "C" int mmssl_wsum(const float* wcat, int d, int heads, float* wsum, float* wsum_t, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
-    wsum_kernel<<<(d * d + 255) / 256, 256, 0, st>>>(wcat, d, heads, wsum, wsum_t);
+    MMSSL_CUDA_LAUNCH((wsum_kernel), dim3((d * d + 255) / 256), dim3(256), 0, st, wcat, d, heads, wsum, wsum_t);
     MMSSL_LAUNCH_OK();
     return 0;
 }
@@ -272,7 +276,7 @@ static int launch_fwd(const float* ya, int64_t lda, const float* yb, int64_t ldb
     const int smem = (D * D + TR * D) * 4;
     static bool attr = false;
     if (!attr) { MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-    id_fuse2_fwd_kernel<D><<<(unsigned)((n + TR - 1) / TR), 256, smem, st>>>(ya, lda, yb, ldb, coef, wsum, e, lde, n, rate, out, ldo, zn, nrm);
+    MMSSL_CUDA_LAUNCH((id_fuse2_fwd_kernel<D>), dim3((unsigned)((n + TR - 1) / TR)), dim3(256), smem, st, ya, lda, yb, ldb, coef, wsum, e, lde, n, rate, out, ldo, zn, nrm);
     MMSSL_LAUNCH_OK();
     return 0;
 }
@@ -297,7 +301,7 @@ static int launch_bwd(const float* g, int64_t ldg, const float* zn, const float*
     const int smem = (D * D + 2 * TR * D) * 4;
     static bool attr = false;
     if (!attr) { MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-    id_fuse2_bwd_kernel<D><<<(unsigned)((n + TR - 1) / TR), 256, smem, st>>>(g, ldg, zn, nrm, ya, lda, yb, ldb, coef, wsum_t, n, rate,
+    MMSSL_CUDA_LAUNCH((id_fuse2_bwd_kernel<D>), dim3((unsigned)((n + TR - 1) / TR)), dim3(256), smem, st, g, ldg, zn, nrm, ya, lda, yb, ldb, coef, wsum_t, n, rate,
                                                                             ext_a, ldea, ext_b, ldeb, out_a, ldoa, out_b, ldob, dw_part);
     MMSSL_LAUNCH_OK();
     return 0;
@@ -322,7 +326,7 @@ extern "C" int mmssl_id_fuse2_bwd(const float* g, int64_t ldg, const float* zn, 
 extern "C" int mmssl_dwcat_reduce(const float* part_u, int nu, const float* part_i, int ni, int d, int heads, float* dwcat,
                                   void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
-    dwcat_reduce_kernel<<<(d * d + 63) / 64, 256, 0, st>>>(part_u, nu, part_i, ni, d, heads, dwcat);
+    MMSSL_CUDA_LAUNCH((dwcat_reduce_kernel), dim3((d * d + 63) / 64), dim3(256), 0, st, part_u, nu, part_i, ni, d, heads, dwcat);
     MMSSL_LAUNCH_OK();
     return 0;
 }

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256) bpr_kernel(const float* __restrict__ uf, 
                                                   const float* __restrict__ g_emb, float* __restrict__ part,
                                                   float* __restrict__ g_u, int64_t ldgu, float* __restrict__ g_p,
                                                   int64_t ldgp, float* __restrict__ g_n, int64_t ldgn) {
+    pdl_wait();
     __shared__ float red[2][32];
     const unsigned mask = group_mask<G>();
     const int lane = threadIdx.x & (G - 1);
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(256) nce_prepare_kernel(const float* __restric
                                                           float* __restrict__ a, float* __restrict__ b,
                                                           float* __restrict__ na, float* __restrict__ nb,
                                                           float* __restrict__ ga, float* __restrict__ gb) {
+    pdl_wait();
     const unsigned mask = group_mask<G>();
     const int lane = threadIdx.x & (G - 1);
     const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
@@ -186,6 +188,7 @@ __device__ __forceinline__ void tile_tn(float (&acc)[4][4], const float* Q, cons
 // stats layout: [diagR n][diagB n][loss n][unused n][partR ntj*n][partB ntj*n]
 __global__ void __launch_bounds__(256) nce_stats_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                         int64_t n, int d, float inv_tau, float* __restrict__ stats) {
+    pdl_wait();
     extern __shared__ float sm[];
     float* Ai = sm; float* Aj = sm + NT * NS; float* Bj = sm + 2 * NT * NS;
     const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
@@ -230,6 +233,7 @@ __global__ void __launch_bounds__(256) nce_stats_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) nce_finalize_kernel(int64_t n, int64_t ntj, float* __restrict__ stats,
                                                            float* __restrict__ coef, const float* __restrict__ g_loss,
                                                            float* __restrict__ loss_part) {
+    pdl_wait();
     __shared__ float red[32];
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     float li = 0.f;
@@ -264,6 +268,7 @@ __global__ void __launch_bounds__(256) nce_finalize_kernel(int64_t n, int64_t nt
 __global__ void __launch_bounds__(256) nce_grad_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                        int64_t n, int d, float inv_tau, const float* __restrict__ coef,
                                                        float* __restrict__ ga, float* __restrict__ gb) {
+    pdl_wait();
     extern __shared__ float sm[];
     float* Ai = sm; float* Aj = sm + NT * NS; float* Bj = sm + 2 * NT * NS;
     float* P = sm + 3 * NT * NS; float* Q = sm + 4 * NT * NS;
@@ -332,6 +337,7 @@ __global__ void __launch_bounds__(256) nce_scatter_kernel(const float* __restric
                                                           const int64_t* __restrict__ idx, int64_t n,
                                                           float* __restrict__ g_z1, int64_t ldg1,
                                                           float* __restrict__ g_z2, int64_t ldg2) {
+    pdl_wait();
     const unsigned mask = group_mask<G>();
     const int lane = threadIdx.x & (G - 1);
     const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
@@ -392,6 +398,7 @@ __global__ void __launch_bounds__(1024) loss_assemble_kernel(const float* bpr_pa
                                                              const float* nce1, int64_t n_nce1, const float* nce2,
                                                              int64_t n_nce2, int64_t n_nce_rows, float cl_rate,
                                                              float* out5) {
+    pdl_wait();
     __shared__ float red[32];
     float mf = 0.f, emb = 0.f;
     {
@@ -489,9 +496,9 @@ extern "C" int mmssl_infonce_stats(const float* a, const float* b, int64_t n, in
     if (int rc = nce_smem_attr()) return rc;
     const unsigned nt = (unsigned)((n + NT - 1) / NT);
     MMSSL_REQUIRE(nt <= 65535, "batch too large for one InfoNCE call");
-    nce_stats_kernel<<<dim3(nt, nt), 256, 3 * NT * NS * 4, st>>>(a, b, n, d, inv_tau, stats);
+    MMSSL_CUDA_LAUNCH((nce_stats_kernel), dim3(dim3(nt, nt)), dim3(256), 3 * NT * NS * 4, st, a, b, n, d, inv_tau, stats);
     MMSSL_LAUNCH_OK();
-    nce_finalize_kernel<<<(unsigned)mmssl_infonce_loss_blocks(n), 256, 0, st>>>(n, nt, stats, coef, g_loss, loss_part);
+    MMSSL_CUDA_LAUNCH((nce_finalize_kernel), dim3((unsigned)mmssl_infonce_loss_blocks(n)), dim3(256), 0, st, n, nt, stats, coef, g_loss, loss_part);
     MMSSL_LAUNCH_OK();
     return 0;
 }
@@ -504,7 +511,7 @@ extern "C" int mmssl_infonce_grad(const float* a, const float* b, int64_t n, int
     if (int rc = nce_smem_attr()) return rc;
     const unsigned nt = (unsigned)((n + NT - 1) / NT);
     MMSSL_REQUIRE(nt <= 65535, "batch too large for one InfoNCE call");
-    nce_grad_kernel<<<dim3(nt, nt), 256, 5 * NT * NS * 4, st>>>(a, b, n, d, inv_tau, coef, ga, gb);
+    MMSSL_CUDA_LAUNCH((nce_grad_kernel), dim3(dim3(nt, nt)), dim3(256), 5 * NT * NS * 4, st, a, b, n, d, inv_tau, coef, ga, gb);
     MMSSL_LAUNCH_OK();
     return 0;
 }
@@ -529,7 +536,7 @@ extern "C" int mmssl_loss_assemble(const float* bpr_part, int64_t n_bpr_blocks, 
                                    int64_t n_nce_rows, float cl_rate, float* out5, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     MMSSL_REQUIRE(out5 != nullptr, "null output");
-    loss_assemble_kernel<<<1, 1024, 0, st>>>(bpr_part ? bpr_part : out5, bpr_part ? n_bpr_blocks : 0, batch, reg_coef,
+    MMSSL_CUDA_LAUNCH((loss_assemble_kernel), dim3(1), dim3(1024), 0, st, bpr_part ? bpr_part : out5, bpr_part ? n_bpr_blocks : 0, batch, reg_coef,
                                              fr_u, n_fr_u, fr_i, n_fr_i, feat_coef, nce1, n_nce1, nce2, n_nce2,
                                              n_nce_rows, cl_rate, out5);
     MMSSL_LAUNCH_OK();

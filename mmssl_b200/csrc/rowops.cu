@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) id_fuse_fwd_kernel(const float* __restric
                                                           const float* __restrict__ e, int64_t lde, int64_t n,
                                                           float rate, float* __restrict__ out, int64_t ldo,
                                                           float* __restrict__ zn, float* __restrict__ nrm_out) {
+    pdl_wait();
     RowIdx<G, C> ix;
     if (ix.row >= n) return;
     float4 zv[C], ev[C];
@@ -94,6 +95,7 @@ template <int G, int C>
 __global__ void __launch_bounds__(256) id_fuse_bwd_kernel(const float* __restrict__ g, int64_t ldg,
                                                           const float* __restrict__ zn, const float* __restrict__ nrm,
                                                           int64_t n, float rate, float* __restrict__ dz, int64_t lddz) {
+    pdl_wait();
     RowIdx<G, C> ix;
     if (ix.row >= n) return;
     float4 gv[C], nv[C], o[C];
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(256) combine_fwd_kernel(const float* __restric
                                                           const float* __restrict__ b, int64_t ldb, int64_t n,
                                                           float inv_layers, float rate, float* __restrict__ out,
                                                           int64_t ldo, float* __restrict__ sumsq_partials) {
+    pdl_wait();
     __shared__ float red[32];
     RowIdx<G, C> ix;
     float ss = 0.f;
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(256) combine_bwd_kernel(const float* __restric
                                                           const float* __restrict__ gb_ext, int64_t ldgbe, int64_t n,
                                                           float rate, float reg_coef, float* __restrict__ ga,
                                                           int64_t ldga, float* __restrict__ gb, int64_t ldgb) {
+    pdl_wait();
     RowIdx<G, C> ix;
     if (ix.row >= n) return;
     float4 gv[C], xv[C], o[C];
@@ -191,6 +195,7 @@ template <int G, int C>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ y, int64_t ldy,
                                                           const float* __restrict__ g, int64_t ldg, int64_t n,
                                                           float alpha, float* __restrict__ t, int64_t ldt) {
+    pdl_wait();
     RowIdx<G, C> ix;
     if (ix.row >= n) return;
     float4 yv[C], gv[C];
@@ -210,6 +215,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
 // ---- plain element-wise passes over strided [n, d] matrices (d % 4 == 0) ----
 __global__ void axpby_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int d4, float alpha,
                              const float* __restrict__ alpha_dev, float beta, float* __restrict__ y, int64_t ldy) {
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n * d4) return;
     const int64_t r = i / d4;
@@ -226,6 +232,7 @@ __global__ void axpby_kernel(const float* __restrict__ x, int64_t ldx, int64_t n
 
 __global__ void mul_mask_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ m, int64_t ldm,
                                 int64_t n, int d4, float* __restrict__ y, int64_t ldy) {
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n * d4) return;
     const int64_t r = i / d4;
@@ -241,6 +248,7 @@ __global__ void mul_mask_kernel(const float* __restrict__ x, int64_t ldx, const 
 constexpr int kSumsqElemsPerBlock = 256 * 4 * 8;   // 8 float4 per thread
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int d4,
                                                     float* __restrict__ partials) {
+    pdl_wait();
     __shared__ float red[32];
     const int64_t total = n * d4;
     float s = 0.f;
@@ -263,6 +271,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, int64_t ldg,
                                                      const float* __restrict__ m, int64_t ldm, int64_t rows, int n,
                                                      int rows_per_block, float* __restrict__ out) {
+    pdl_wait();
     extern __shared__ float sm[];   // [256/n_threads_per_row ...] simple: [blockDim.x]
     const int tpr = n;               // threads per row (n <= 256, blockDim.x multiple of n)
     const int rl = threadIdx.x / tpr;
@@ -375,7 +384,7 @@ extern "C" int mmssl_axpby(const float* x, int64_t ldx, int64_t n, int d, float 
     MMSSL_REQUIRE(d % 4 == 0 && ROW_ALIGN_OK(x, ldx) && ROW_ALIGN_OK(y, ldy), "alignment");
     const int64_t tot = n * (d / 4);
     if (tot == 0) return 0;
-    axpby_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, ldx, n, d / 4, alpha, alpha_dev, beta, y, ldy);
+    MMSSL_CUDA_LAUNCH((axpby_kernel), dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, x, ldx, n, d / 4, alpha, alpha_dev, beta, y, ldy);
     MMSSL_LAUNCH_OK();
     return 0;
 }
@@ -386,7 +395,7 @@ extern "C" int mmssl_mul_mask(const float* x, int64_t ldx, const float* mask, in
     MMSSL_REQUIRE(d % 4 == 0 && ROW_ALIGN_OK(x, ldx) && ROW_ALIGN_OK(y, ldy) && (mask == nullptr || ROW_ALIGN_OK(mask, ldm)), "alignment");
     const int64_t tot = n * (d / 4);
     if (tot == 0) return 0;
-    mul_mask_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, ldx, mask, ldm, n, d / 4, y, ldy);
+    MMSSL_CUDA_LAUNCH((mul_mask_kernel), dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, x, ldx, mask, ldm, n, d / 4, y, ldy);
     MMSSL_LAUNCH_OK();
     return 0;
 }
@@ -398,7 +407,7 @@ extern "C" int mmssl_sumsq(const float* x, int64_t ldx, int64_t n, int d, float*
     MMSSL_REQUIRE(d % 4 == 0 && ROW_ALIGN_OK(x, ldx), "alignment");
     const int64_t blocks = mmssl_sumsq_blocks(n, d);
     if (blocks == 0) return 0;
-    sumsq_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ldx, n, d / 4, partials);
+    MMSSL_CUDA_LAUNCH((sumsq_kernel), dim3((unsigned)blocks), dim3(256), 0, st, x, ldx, n, d / 4, partials);
     MMSSL_LAUNCH_OK();
     return 0;
 }
@@ -411,7 +420,7 @@ extern "C" int mmssl_colsum(const float* g, int64_t ldg, const float* mask, int6
     if (rows == 0) return 0;
     const int rows_per_block = 64;
     const unsigned blocks = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
-    colsum_kernel<<<blocks, 256, 256 * sizeof(float), st>>>(g, ldg, mask, ldm, rows, n, rows_per_block, out);
+    MMSSL_CUDA_LAUNCH((colsum_kernel), dim3(blocks), dim3(256), 256 * sizeof(float), st, g, ldg, mask, ldm, rows, n, rows_per_block, out);
     MMSSL_LAUNCH_OK();
     return 0;
 }

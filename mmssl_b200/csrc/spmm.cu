@@ -27,6 +27,7 @@ namespace mmssl {
 // about one memory round trip per UNR non-zeros instead of one per load.
 template <int G, int C, int R, int UMUL, int MINB>
 __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p) {
+    pdl_wait();
     constexpr int RC = R * C;
     constexpr int UNR0 = ((8 / RC) >= 2 ? (8 / RC) : 2) * UMUL;
     constexpr int UNR = UNR0 > G ? G : UNR0;
@@ -225,7 +226,7 @@ static int launch_spmm_v(const SpmmParams& p, cudaStream_t stream, int T) {
     const int64_t blocks = (p.n_items + groups_per_block - 1) / groups_per_block;
     if (blocks == 0) return 0;
     if (blocks > 0x7fffffffll) return fail("mmssl_spmm_csr_f32", "grid too large");
-    spmm_csr_kernel<G, C, R, UMUL, MINB><<<(unsigned)blocks, T, 0, stream>>>(p);
+    MMSSL_CUDA_LAUNCH((spmm_csr_kernel<G, C, R, UMUL, MINB>), dim3((unsigned)blocks), dim3(T), 0, stream, p);
     MMSSL_LAUNCH_OK();
     return 0;
 }

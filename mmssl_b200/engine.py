@@ -60,9 +60,6 @@ class FwdState:
     sumsq_i: Optional[torch.Tensor] = None
 
 
-def _same(a: torch.Tensor, b: torch.Tensor) -> bool:
-    return a.data_ptr() == b.data_ptr() and a.shape == b.shape and a.stride() == b.stride()
-
 
 class Engine:
     def __init__(self, embed_size: int, n_layers: int, head_num: int = 4, id_cat_rate: float = 0.36,
