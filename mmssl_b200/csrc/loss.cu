@@ -455,7 +455,7 @@ extern "C" int mmssl_bpr(const float* uf, int64_t ldu, const float* itf, int64_t
     if (batch == 0) return 0;
     return dispatch_d(d, [&](auto G, auto C) {
         const unsigned blocks = (unsigned)mmssl_bpr_blocks(batch, d);
-        bpr_kernel<GV(G), GV(C)><<<blocks, 256, 0, st>>>(uf, ldu, itf, ldi, itf_neg, ldin, users, pos, neg, batch, mode,
+        MMSSL_CUDA_LAUNCH((bpr_kernel<GV(G), GV(C)>), dim3(blocks), dim3(256), 0, st, uf, ldu, itf, ldi, itf_neg, ldin, users, pos, neg, batch, mode,
                                                          reg_coef, g_mf, g_emb, part, g_uf, ldgu, g_pos, ldgp, g_neg, ldgn);
         MMSSL_LAUNCH_OK();
         return 0;
@@ -470,7 +470,7 @@ extern "C" int mmssl_infonce_prepare(const float* z1, int64_t ldz1, const float*
     if (n == 0) return 0;
     return dispatch_d(d, [&](auto G, auto C) {
         const unsigned blocks = (unsigned)((n * GV(G) + 255) / 256);
-        nce_prepare_kernel<GV(G), GV(C)><<<blocks, 256, 0, st>>>(z1, ldz1, z2, ldz2, idx, n, a, b, na, nb, ga, gb);
+        MMSSL_CUDA_LAUNCH((nce_prepare_kernel<GV(G), GV(C)>), dim3(blocks), dim3(256), 0, st, z1, ldz1, z2, ldz2, idx, n, a, b, na, nb, ga, gb);
         MMSSL_LAUNCH_OK();
         return 0;
     });
@@ -524,7 +524,7 @@ extern "C" int mmssl_infonce_scatter(const float* ga, const float* gb, const flo
     if (n == 0) return 0;
     return dispatch_d(d, [&](auto G, auto C) {
         const unsigned blocks = (unsigned)((n * GV(G) + 255) / 256);
-        nce_scatter_kernel<GV(G), GV(C)><<<blocks, 256, 0, st>>>(ga, gb, a, b, na, nb, idx, n, g_z1, ldg1, g_z2, ldg2);
+        MMSSL_CUDA_LAUNCH((nce_scatter_kernel<GV(G), GV(C)>), dim3(blocks), dim3(256), 0, st, ga, gb, a, b, na, nb, idx, n, g_z1, ldg1, g_z2, ldg2);
         MMSSL_LAUNCH_OK();
         return 0;
     });

@@ -313,7 +313,7 @@ extern "C" int mmssl_id_fuse_fwd(const float* z, int64_t ldz, const float* e, in
     MMSSL_REQUIRE(ROW_ALIGN_OK(z, ldz) && ROW_ALIGN_OK(e, lde) && ROW_ALIGN_OK(out, ldo) && aligned16(zn), "alignment");
     if (n == 0) return 0;
     return dispatch_d(d, [&](auto G, auto C) {
-        id_fuse_fwd_kernel<decltype(G)::value, decltype(C)::value><<<row_blocks(n, decltype(G)::value), 256, 0, st>>>(z, ldz, e, lde, n, rate, out, ldo, zn, nrm);
+        MMSSL_CUDA_LAUNCH((id_fuse_fwd_kernel<decltype(G)::value, decltype(C)::value>), dim3(row_blocks(n, decltype(G)::value)), dim3(256), 0, st, z, ldz, e, lde, n, rate, out, ldo, zn, nrm);
         MMSSL_LAUNCH_OK();
         return 0;
     });
@@ -325,7 +325,7 @@ extern "C" int mmssl_id_fuse_bwd(const float* g, int64_t ldg, const float* zn, c
     MMSSL_REQUIRE(ROW_ALIGN_OK(g, ldg) && ROW_ALIGN_OK(dz, lddz) && aligned16(zn), "alignment");
     if (n == 0) return 0;
     return dispatch_d(d, [&](auto G, auto C) {
-        id_fuse_bwd_kernel<decltype(G)::value, decltype(C)::value><<<row_blocks(n, decltype(G)::value), 256, 0, st>>>(g, ldg, zn, nrm, n, rate, dz, lddz);
+        MMSSL_CUDA_LAUNCH((id_fuse_bwd_kernel<decltype(G)::value, decltype(C)::value>), dim3(row_blocks(n, decltype(G)::value)), dim3(256), 0, st, g, ldg, zn, nrm, n, rate, dz, lddz);
         MMSSL_LAUNCH_OK();
         return 0;
     });
@@ -341,7 +341,7 @@ extern "C" int mmssl_combine_fwd(const float* s, int64_t lds, const float* a, in
     MMSSL_REQUIRE(sumsq_partials == nullptr || n_partials >= mmssl_combine_partials(n, d), "sumsq_partials too small");
     if (n == 0) return 0;
     return dispatch_d(d, [&](auto G, auto C) {
-        combine_fwd_kernel<decltype(G)::value, decltype(C)::value><<<row_blocks(n, decltype(G)::value), 256, 0, st>>>(s, lds, a, lda, b, ldb, n, inv_layers,
+        MMSSL_CUDA_LAUNCH((combine_fwd_kernel<decltype(G)::value, decltype(C)::value>), dim3(row_blocks(n, decltype(G)::value)), dim3(256), 0, st, s, lds, a, lda, b, ldb, n, inv_layers,
                                                                                    rate, out, ldo, sumsq_partials);
         MMSSL_LAUNCH_OK();
         return 0;
@@ -358,7 +358,7 @@ extern "C" int mmssl_combine_bwd(const float* g, int64_t ldg, const float* a, in
     MMSSL_REQUIRE((ga_ext == nullptr || ROW_ALIGN_OK(ga_ext, ldgae)) && (gb_ext == nullptr || ROW_ALIGN_OK(gb_ext, ldgbe)), "alignment");
     if (n == 0) return 0;
     return dispatch_d(d, [&](auto G, auto C) {
-        combine_bwd_kernel<decltype(G)::value, decltype(C)::value><<<row_blocks(n, decltype(G)::value), 256, 0, st>>>(g, ldg, a, lda, b, ldb, ga_ext, ldgae,
+        MMSSL_CUDA_LAUNCH((combine_bwd_kernel<decltype(G)::value, decltype(C)::value>), dim3(row_blocks(n, decltype(G)::value)), dim3(256), 0, st, g, ldg, a, lda, b, ldb, ga_ext, ldgae,
                                                                                    gb_ext, ldgbe, n, rate, reg_coef, ga,
                                                                                    ldga, gb, ldgb);
         MMSSL_LAUNCH_OK();
@@ -372,7 +372,7 @@ extern "C" int mmssl_softmax_bwd(const float* y, int64_t ldy, const float* g, in
     MMSSL_REQUIRE(ROW_ALIGN_OK(y, ldy) && ROW_ALIGN_OK(g, ldg) && ROW_ALIGN_OK(t, ldt), "alignment");
     if (n == 0) return 0;
     return dispatch_d(d, [&](auto G, auto C) {
-        softmax_bwd_kernel<decltype(G)::value, decltype(C)::value><<<row_blocks(n, decltype(G)::value), 256, 0, st>>>(y, ldy, g, ldg, n, alpha, t, ldt);
+        MMSSL_CUDA_LAUNCH((softmax_bwd_kernel<decltype(G)::value, decltype(C)::value>), dim3(row_blocks(n, decltype(G)::value)), dim3(256), 0, st, y, ldy, g, ldg, n, alpha, t, ldt);
         MMSSL_LAUNCH_OK();
         return 0;
     });
