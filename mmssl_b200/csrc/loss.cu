@@ -128,7 +128,7 @@ constexpr int NS = NT + 4;      // smem row stride: float4-aligned rows, conflic
 __device__ __forceinline__ void load_tile(float* sm, const float* __restrict__ src, int64_t row0, int64_t n, int d,
                                           int c0) {
     // sm[r][k] = src[(row0+r)*d + c0 + k], r,k < 64 (zero beyond n)
-    for (int e = threadIdx.x; e < NT * (NT / 4); e += blockDim.x) {
+    for (int e = threadIdx.x; e < NT * (NT / 4); e += 256) {
         const int r = e / (NT / 4), k4 = (e % (NT / 4)) * 4;
         float4 v = f4zero();
         if (row0 + r < n) v = ld4(src + (row0 + r) * (int64_t)d + c0 + k4);
@@ -170,10 +170,10 @@ __device__ __forceinline__ void tile_nn(float (&acc)[4][4], const float* P, cons
         }
     }
 }
-// acc[ii][jj] += sum_{i in [lo,hi)} Q[i][ty*4+ii] * V[i][tx*4+jj]       (rows ty*4+ii, columns tx*4+jj)
-__device__ __forceinline__ void tile_tn_range(float (&acc)[4][4], const float* Q, const float* V, int ty, int tx, int lo, int hi) {
+// acc[ii][jj] += sum_i Q[i][ty*4+ii] * V[i][tx*4+jj]       (rows ty*4+ii, columns tx*4+jj)
+__device__ __forceinline__ void tile_tn(float (&acc)[4][4], const float* Q, const float* V, int ty, int tx) {
 #pragma unroll 4
-    for (int i = lo; i < hi; ++i) {
+    for (int i = 0; i < NT; ++i) {
         const float4 q = *reinterpret_cast<const float4*>(Q + i * NS + ty * 4);
         const float4 v = *reinterpret_cast<const float4*>(V + i * NS + tx * 4);
         const float qv[4] = {q.x, q.y, q.z, q.w};
@@ -186,44 +186,47 @@ __device__ __forceinline__ void tile_tn_range(float (&acc)[4][4], const float* Q
 }
 
 // stats layout: [diagR n][diagB n][loss n][unused n][partR ntj*n][partB ntj*n]
-// 512 threads: group 0 (threads 0..255) owns the exp(a a^T / tau) tile, group 1 the exp(a b^T / tau) tile --
-// twice the resident warps of a one-group CTA (the kernel is issue/latency bound, not LDS or FMA bound).
-__global__ void __launch_bounds__(512) nce_stats_kernel(const float* __restrict__ a, const float* __restrict__ b,
+__global__ void __launch_bounds__(256) nce_stats_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                         int64_t n, int d, float inv_tau, float* __restrict__ stats) {
     pdl_wait();
     extern __shared__ float sm[];
     float* Ai = sm; float* Aj = sm + NT * NS; float* Bj = sm + 2 * NT * NS;
-    const int grp = threadIdx.x >> 8, t = threadIdx.x & 255;
-    const int ty = t / 16, tx = t % 16;
+    const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
     const int64_t i0 = blockIdx.x * (int64_t)NT, j0 = blockIdx.y * (int64_t)NT;
-    float sv[4][4] = {};
+    float sr[4][4] = {}, sb[4][4] = {};
     for (int c0 = 0; c0 < d; c0 += NT) {
         load_tile(Ai, a, i0, n, d, c0);
         load_tile(Aj, a, j0, n, d, c0);
         load_tile(Bj, b, j0, n, d, c0);
         __syncthreads();
-        tile_nt(sv, Ai, grp == 0 ? Aj : Bj, ty, tx);
+        tile_nt(sr, Ai, Aj, ty, tx);
+        tile_nt(sb, Ai, Bj, ty, tx);
         __syncthreads();
     }
     const int64_t ntj = gridDim.y;
-    float* diag = stats + (grp == 0 ? 0 : n);
-    float* part = stats + 4 * n + (grp == 0 ? 0 : ntj * n) + blockIdx.y * n;
+    float* diag_r = stats; float* diag_b = stats + n;
+    float* part_r = stats + 4 * n + blockIdx.y * n;
+    float* part_b = stats + 4 * n + ntj * n + blockIdx.y * n;
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii) {
         const int64_t i = i0 + ty * 4 + ii;
-        float rs = 0.f;
+        float rr = 0.f, rb = 0.f;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             const int64_t j = j0 + tx + 16 * jj;
             if (i < n && j < n) {
-                const float ev = expf(sv[ii][jj] * inv_tau);
-                rs += ev;
-                if (i == j) diag[i] = ev;
+                const float er = expf(sr[ii][jj] * inv_tau), eb = expf(sb[ii][jj] * inv_tau);
+                rr += er; rb += eb;
+                if (i == j) { diag_r[i] = er; diag_b[i] = eb; }
             }
         }
+        // the 16 threads sharing `ty` are 16 consecutive lanes
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o, 16);   // the 16 tx lanes of a row
-        if (tx == 0 && i < n) part[i] = rs;
+        for (int o = 8; o > 0; o >>= 1) {
+            rr += __shfl_xor_sync(0xffffffffu, rr, o, 16);
+            rb += __shfl_xor_sync(0xffffffffu, rb, o, 16);
+        }
+        if (tx == 0 && i < n) { part_r[i] = rr; part_b[i] = rb; }
     }
 }
 
@@ -262,29 +265,26 @@ __global__ void __launch_bounds__(256) nce_finalize_kernel(int64_t n, int64_t nt
     if (threadIdx.x == 0) loss_part[blockIdx.x] = tot;
 }
 
-// 512 threads, same split: group 0 -> R tile and P coefficients, group 1 -> B tile and Q coefficients; then
-// group 0 accumulates P a_j, group 1 Q b_j (both into ga), and each group half of the i-range of Q^T a_i (into gb).
-__global__ void __launch_bounds__(512) nce_grad_kernel(const float* __restrict__ a, const float* __restrict__ b,
+__global__ void __launch_bounds__(256) nce_grad_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                        int64_t n, int d, float inv_tau, const float* __restrict__ coef,
                                                        float* __restrict__ ga, float* __restrict__ gb) {
     pdl_wait();
     extern __shared__ float sm[];
     float* Ai = sm; float* Aj = sm + NT * NS; float* Bj = sm + 2 * NT * NS;
     float* P = sm + 3 * NT * NS; float* Q = sm + 4 * NT * NS;
-    const int grp = threadIdx.x >> 8, t = threadIdx.x & 255;
-    const int ty = t / 16, tx = t % 16;
+    const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
     const int64_t i0 = blockIdx.x * (int64_t)NT, j0 = blockIdx.y * (int64_t)NT;
-    float sv[4][4] = {};
+    float sr[4][4] = {}, sb[4][4] = {};
     for (int c0 = 0; c0 < d; c0 += NT) {
         load_tile(Ai, a, i0, n, d, c0);
         load_tile(Aj, a, j0, n, d, c0);
         load_tile(Bj, b, j0, n, d, c0);
         __syncthreads();
-        tile_nt(sv, Ai, grp == 0 ? Aj : Bj, ty, tx);
+        tile_nt(sr, Ai, Aj, ty, tx);
+        tile_nt(sb, Ai, Bj, ty, tx);
         __syncthreads();
     }
     // coefficient tiles:  P_ij = -(u_i+u_j) R_ij / tau (i != j),   Q_ij = B_ij (-u_i + [i==j] v_i) / tau
-    float* coefT = grp == 0 ? P : Q;
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii) {
         const int64_t i = i0 + ty * 4 + ii;
@@ -293,13 +293,15 @@ __global__ void __launch_bounds__(512) nce_grad_kernel(const float* __restrict__
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             const int64_t j = j0 + tx + 16 * jj;
-            float cv = 0.f;
+            float pv = 0.f, qv = 0.f;
             if (i < n && j < n) {
-                const float ev = expf(sv[ii][jj] * inv_tau);
-                if (grp == 0) cv = (i == j) ? 0.f : -(ui + coef[j]) * ev * inv_tau;
-                else cv = ev * (-ui + ((i == j) ? vi : 0.f)) * inv_tau;
+                const float uj = coef[j];
+                const float er = expf(sr[ii][jj] * inv_tau), eb = expf(sb[ii][jj] * inv_tau);
+                pv = (i == j) ? 0.f : -(ui + uj) * er * inv_tau;
+                qv = eb * (-ui + ((i == j) ? vi : 0.f)) * inv_tau;
             }
-            coefT[(ty * 4 + ii) * NS + tx + 16 * jj] = cv;
+            P[(ty * 4 + ii) * NS + tx + 16 * jj] = pv;
+            Q[(ty * 4 + ii) * NS + tx + 16 * jj] = qv;
         }
     }
     __syncthreads();
@@ -311,9 +313,9 @@ __global__ void __launch_bounds__(512) nce_grad_kernel(const float* __restrict__
             __syncthreads();
         }
         float g1[4][4] = {}, g2[4][4] = {};
-        if (grp == 0) tile_nn(g1, P, Aj, ty, tx);     // dL/da_i += sum_j P_ij a_j
-        else tile_nn(g1, Q, Bj, ty, tx);              // dL/da_i += sum_j Q_ij b_j
-        tile_tn_range(g2, Q, Ai, ty, tx, grp * (NT / 2), (grp + 1) * (NT / 2));   // dL/db_j += sum_i Q_ij a_i (half of i)
+        tile_nn(g1, P, Aj, ty, tx);     // dL/da_i  += sum_j P_ij a_j
+        tile_nn(g1, Q, Bj, ty, tx);     //           + sum_j Q_ij b_j
+        tile_tn(g2, Q, Ai, ty, tx);     // dL/db_j  += sum_i Q_ij a_i
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
             const int64_t i = i0 + ty * 4 + ii, j = j0 + ty * 4 + ii;
@@ -494,7 +496,7 @@ extern "C" int mmssl_infonce_stats(const float* a, const float* b, int64_t n, in
     if (int rc = nce_smem_attr()) return rc;
     const unsigned nt = (unsigned)((n + NT - 1) / NT);
     MMSSL_REQUIRE(nt <= 65535, "batch too large for one InfoNCE call");
-    MMSSL_CUDA_LAUNCH((nce_stats_kernel), dim3(dim3(nt, nt)), dim3(512), 3 * NT * NS * 4, st, a, b, n, d, inv_tau, stats);
+    MMSSL_CUDA_LAUNCH((nce_stats_kernel), dim3(dim3(nt, nt)), dim3(256), 3 * NT * NS * 4, st, a, b, n, d, inv_tau, stats);
     MMSSL_LAUNCH_OK();
     MMSSL_CUDA_LAUNCH((nce_finalize_kernel), dim3((unsigned)mmssl_infonce_loss_blocks(n)), dim3(256), 0, st, n, nt, stats, coef, g_loss, loss_part);
     MMSSL_LAUNCH_OK();
@@ -509,7 +511,7 @@ extern "C" int mmssl_infonce_grad(const float* a, const float* b, int64_t n, int
     if (int rc = nce_smem_attr()) return rc;
     const unsigned nt = (unsigned)((n + NT - 1) / NT);
     MMSSL_REQUIRE(nt <= 65535, "batch too large for one InfoNCE call");
-    MMSSL_CUDA_LAUNCH((nce_grad_kernel), dim3(dim3(nt, nt)), dim3(512), 5 * NT * NS * 4, st, a, b, n, d, inv_tau, coef, ga, gb);
+    MMSSL_CUDA_LAUNCH((nce_grad_kernel), dim3(dim3(nt, nt)), dim3(256), 5 * NT * NS * 4, st, a, b, n, d, inv_tau, coef, ga, gb);
     MMSSL_LAUNCH_OK();
     return 0;
 }
