@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = the count that measured fastest on this host class (tools/cpu_threads.py)")
     ap.add_argument("--seed", type=int, default=2022)
+    ap.add_argument("--eager-comm", action="store_true", help="issue the DP all-reduce + AdamW eagerly after the graph replay")
     return ap.parse_args()
 
 
@@ -141,20 +142,25 @@ def build_problem(name: str, seed: int, device):
 class HotStepTrainer:
     """Public API of the fused path: ``train_step(users, pos, neg) -> float loss`` (host in, host out)."""
 
-    def __init__(self, P, feats, graphs, cfg, batch, world=1, sampler=None):
+    def __init__(self, P, feats, graphs, cfg, batch, world=1, sampler=None, graph_comm=True):
         from mmssl_b200.hotstep import HotStep
         self.world = world
-        self.hs = HotStep(P, feats, graphs, cfg, batch=batch, optimizer_step=(world == 1), sampler=sampler)
+        # graph_comm: the gradient all-reduce (NCCL) and AdamW are captured inside the CUDA graph, so a
+        # multi-GPU step is ONE graph replay; otherwise they are issued eagerly after the replay.
+        self.graph_comm = graph_comm or world == 1
+        self.hs = HotStep(P, feats, graphs, cfg, batch=batch, optimizer_step=self.graph_comm, sampler=sampler)
         self.pin_idx = torch.empty(3, batch, dtype=torch.int64).pin_memory()
         self.pin_out = torch.empty(5, dtype=torch.float32).pin_memory()
         if world > 1:
             from mmssl_b200.parallel import GradBucket
             self.bucket = GradBucket(self.hs.grads)      # one flat all-reduce bucket for all live parameters
             self.hs.grads.update(self.bucket.views)
+            if self.graph_comm:
+                self.hs.grad_sync = self.bucket.all_reduce_mean
         self.hs.capture(warmup=2)
 
     def _finish_step(self):
-        if self.world > 1:
+        if self.world > 1 and not self.graph_comm:
             from mmssl_b200 import ops
             from mmssl_b200.engine import LIVE
             self.bucket.all_reduce_mean()
@@ -218,7 +224,7 @@ def roofline_objects(ds, P, feats, graphs, hbm_peak, peak_src, dev):
     ms = time_kernel(lambda: ops.gemm_bf16x3(fs.hi, fs.lo, w_hi, w_lo, I, d, fs.dim, sk, part), flush)
     alg = 4 * I * fs.dim + 4 * d * fs.dim + 4 * I * d
     gbs = alg / (ms * 1e-3) / 1e9
-    out["projection"] = {"kernel": "gemm_bf16x3_kernel<64> (image_trans forward, tcgen05+TMA)", "bound": "hbm",
+    out["projection"] = {"kernel": f"gemm_bf16x3_kernel<{d}> (image_trans forward, tcgen05+TMA)", "bound": "hbm",
                          "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4),
                          "algorithmic_bytes": alg, "ms": round(ms, 5), "split_k": sk, "peak_source": peak_src,
                          "tflops_bf16_issued": round(3 * 2 * I * fs.dim * d / (ms * 1e-3) / 1e12, 2), "traffic": None}
@@ -229,7 +235,7 @@ def roofline_objects(ds, P, feats, graphs, hbm_peak, peak_src, dev):
     alg = 8 * nnz + 4 * (U + 1) + 4 * d * I + 4 * d * U
     gather = 8 * nnz + 4 * (U + 1) + 4 * d * nnz + 4 * d * U
     gbs = alg / (ms * 1e-3) / 1e9
-    out["spmm"] = {"kernel": "spmm_csr_kernel<16,1,1> (A_ui @ X, d=64)", "bound": "hbm", "achieved": round(gbs, 1),
+    out["spmm"] = {"kernel": f"spmm_csr_kernel (A_ui @ X, 1 right-hand side, d={d})", "bound": "hbm", "achieved": round(gbs, 1),
                    "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4), "algorithmic_bytes": alg,
                    "gather_model_gbs_effective": round(gather / (ms * 1e-3) / 1e9, 1), "ms": round(ms, 5),
                    "peak_source": peak_src, "traffic": None,
@@ -238,7 +244,7 @@ def roofline_objects(ds, P, feats, graphs, hbm_peak, peak_src, dev):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            t = json.load(open(tpath))
+            t = json.load(open(tpath)).get(ds.name, {})
             for k in out:
                 if k in t:
                     out[k]["traffic"] = t[k]
@@ -296,7 +302,7 @@ def main():
     U, I, nnz, d, K, dv, dt = CONFIGS[a.config]
     config = {"workload": f"{a.config}: synthetic bipartite {U}x{I}, {nnz} edges, d={d}, {K}-layer GCN, V{dv}/T{dt} features, "
                           f"B={BATCH} triples per GPU per step, modality graphs alias ui/iu",
-              "global_batch": BATCH * max(world, 1), "parallelism": "single GPU" if world == 1 else f"dp{world} (replicated graph, gradient all-reduce)",
+              "global_batch": BATCH * max(world, 1), "parallelism": "single GPU" if world == 1 else f"dp{world} (replicated graph, one flat gradient all-reduce per step" + (", captured in the CUDA graph)" if not a.eager_comm else ", eager)"),
               "l2_policy": "working set per step (%.0f MB of features) exceeds the 126 MB L2; isolated kernels timed after a 192 MiB L2 flush" % (4 * I * (dv + dt) / 1e6)}
 
     if a.impl == "reference":
@@ -327,7 +333,7 @@ def main():
 
     ds, P, feats, graphs, _ = build_problem(a.config, a.seed, dev)
     cfg = HotStepConfig(embed_size=d, n_layers=K, batch_size=BATCH, proj_impl=a.proj)
-    trainer = HotStepTrainer(P, feats, graphs, cfg, BATCH, world=world)
+    trainer = HotStepTrainer(P, feats, graphs, cfg, BATCH, world=world, graph_comm=not a.eager_comm)
     smp = TripleSampler(ds.train, seed=a.seed + 17 * rank)
     n_batches = a.steps + a.warmup
     host_batches = [np.stack(smp.sample(BATCH)) for _ in range(n_batches)]

@@ -86,7 +86,9 @@ typedef struct {
 } mmssl_spmm_rhs_t;
 /* d in {64,128,256}; nrhs in 1..3 (all right-hand sides share A and d).  s_mode: 0 none, 1 S += y, 2 S = sbase + y.
  * `partials` = zero-initialised scratch for split rows, >= a->segs_cap * nrhs * d floats (left clean by the kernel).
- * impl: bit 1 = 8-lane groups at d = 64, bit 2 = 128-thread blocks (tuning variants of the LDG gather kernel). */
+ * impl: 0 = automatic launch policy (128-thread blocks under 2M edges, register-capped variant above); otherwise a bit
+ * set of tuning variants of the gather kernel: 2 = 8-lane groups at d = 64, 4 = 128-thread blocks, 8 = twice the
+ * gathers in flight, 16 = registers capped for 6 resident blocks/SM (8|16 = both with 4 blocks/SM). */
 int mmssl_spmm_csr_f32(const mmssl_csr_t* a /*host*/, int d, int nrhs, const mmssl_spmm_rhs_t* rhs /*host*/,
                        int epilogue, float alpha, int s_mode, float* partials, int64_t partials_floats, int impl, void* stream);
 

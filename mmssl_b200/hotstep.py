@@ -53,6 +53,7 @@ class HotStep:
         self.batch = batch
         self.optimizer_step = optimizer_step
         self.sampler = sampler          # optional sampler.DeviceTripleSampler: batches are drawn on the device
+        self.grad_sync = None           # optional callable run between backward and AdamW (data-parallel all-reduce)
         dev = self.P[P_EU].device
         d = cfg.embed_size
         f = dict(dtype=torch.float32, device=dev)
@@ -76,7 +77,6 @@ class HotStep:
         self.masks: Optional[tuple] = None          # injected dropout masks (tests); None -> torch RNG
         self.training = True
         self._graph: Optional[torch.cuda.CUDAGraph] = None
-        self.kernel_launches = 0
 
     # ------------------------------------------------------------------ one step on the current stream
     def _masks(self):
@@ -127,6 +127,8 @@ class HotStep:
         grads = [self.g_uf, self.g_if, None, None, None, None,
                  self.g_uvid if st.fused else None, (None if self.alias_id else self.g_utid) if st.fused else None, None, None]
         self.engine.backward(st, self.P, self.feats, grads, feat_reg_coef=cfg.feat_reg_decay / self.I, out=self.grads)
+        if self.grad_sync is not None:
+            self.grad_sync()
         if self.optimizer_step:
             ops.step_tick(self.step_dev)
             keys = list(LIVE)

@@ -16,8 +16,6 @@ EPI_NONE, EPI_SOFTMAX, EPI_SOFTMAX_BWD = 0, 1, 2
 SPMM_IMPL_LDG, SPMM_IMPL_TMA = 0, 1     # TMA = shared-memory hot rows staged by cp.async.bulk (large graphs)
 _default_spmm_impl = SPMM_IMPL_LDG
 
-_scratch = {}
-
 
 def set_default_spmm_impl(impl: int) -> None:
     global _default_spmm_impl
@@ -37,16 +35,6 @@ def _row_ok(t: torch.Tensor) -> None:
 
 def _ld(t: Optional[torch.Tensor]) -> int:
     return 0 if t is None else int(t.stride(0))
-
-
-def scratch(dev: torch.device, floats: int) -> torch.Tensor:
-    """Grow-only fp32 scratch shared by stream-ordered kernels (split-row partial sums)."""
-    key = (dev.type, dev.index, torch.cuda.current_stream(dev).cuda_stream)   # concurrent streams never share scratch
-    buf = _scratch.get(key)
-    if buf is None or buf.numel() < floats:
-        buf = torch.empty(max(floats, 1024), dtype=torch.float32, device=dev)
-        _scratch[key] = buf
-    return buf
 
 
 def spmm(a: SparseOperand, xs: Sequence[torch.Tensor], ys: Optional[Sequence[torch.Tensor]] = None, *,
