@@ -53,7 +53,8 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = the count that measured fastest on this host class (tools/cpu_threads.py)")
     ap.add_argument("--seed", type=int, default=2022)
-    ap.add_argument("--eager-comm", action="store_true", help="issue the DP all-reduce + AdamW eagerly after the graph replay")
+    ap.add_argument("--graph-comm", action="store_true",
+                    help="EXPERIMENTAL (hung in round 1): capture the DP all-reduce + AdamW inside the CUDA graph")
     return ap.parse_args()
 
 
@@ -142,11 +143,12 @@ def build_problem(name: str, seed: int, device):
 class HotStepTrainer:
     """Public API of the fused path: ``train_step(users, pos, neg) -> float loss`` (host in, host out)."""
 
-    def __init__(self, P, feats, graphs, cfg, batch, world=1, sampler=None, graph_comm=True):
+    def __init__(self, P, feats, graphs, cfg, batch, world=1, sampler=None, graph_comm=False):
         from mmssl_b200.hotstep import HotStep
         self.world = world
-        # graph_comm: the gradient all-reduce (NCCL) and AdamW are captured inside the CUDA graph, so a
-        # multi-GPU step is ONE graph replay; otherwise they are issued eagerly after the replay.
+        # Default (validated at N = 2, 4, 8): the gradient all-reduce (NCCL) and AdamW are issued eagerly after
+        # the graph replay.  graph_comm=True captures them inside the graph; that variant deadlocked on the
+        # box in round 1 (NCCL capture) and is kept only as an experiment.
         self.graph_comm = graph_comm or world == 1
         self.hs = HotStep(P, feats, graphs, cfg, batch=batch, optimizer_step=self.graph_comm, sampler=sampler)
         self.pin_idx = torch.empty(3, batch, dtype=torch.int64).pin_memory()
@@ -302,7 +304,7 @@ def main():
     U, I, nnz, d, K, dv, dt = CONFIGS[a.config]
     config = {"workload": f"{a.config}: synthetic bipartite {U}x{I}, {nnz} edges, d={d}, {K}-layer GCN, V{dv}/T{dt} features, "
                           f"B={BATCH} triples per GPU per step, modality graphs alias ui/iu",
-              "global_batch": BATCH * max(world, 1), "parallelism": "single GPU" if world == 1 else f"dp{world} (replicated graph, one flat gradient all-reduce per step" + (", captured in the CUDA graph)" if not a.eager_comm else ", eager)"),
+              "global_batch": BATCH * max(world, 1), "parallelism": "single GPU" if world == 1 else f"dp{world} (replicated graph, one flat gradient all-reduce per step" + (", captured in the CUDA graph)" if a.graph_comm else ", eager after the graph replay)"),
               "l2_policy": "working set per step (%.0f MB of features) exceeds the 126 MB L2; isolated kernels timed after a 192 MiB L2 flush" % (4 * I * (dv + dt) / 1e6)}
 
     if a.impl == "reference":
@@ -333,7 +335,7 @@ def main():
 
     ds, P, feats, graphs, _ = build_problem(a.config, a.seed, dev)
     cfg = HotStepConfig(embed_size=d, n_layers=K, batch_size=BATCH, proj_impl=a.proj)
-    trainer = HotStepTrainer(P, feats, graphs, cfg, BATCH, world=world, graph_comm=not a.eager_comm)
+    trainer = HotStepTrainer(P, feats, graphs, cfg, BATCH, world=world, graph_comm=a.graph_comm)
     smp = TripleSampler(ds.train, seed=a.seed + 17 * rank)
     n_batches = a.steps + a.warmup
     host_batches = [np.stack(smp.sample(BATCH)) for _ in range(n_batches)]
