@@ -40,8 +40,8 @@ int mmssl_csr_from_coo(const int64_t* rows, const int64_t* cols, const float* va
 /* vals[e] *= (rowsum + 1e-8)^-1/2  -- csr_norm(mean_flag=True), main.py:89-103 */
 int mmssl_csr_row_normalize(const int32_t* rowptr, int64_t n_rows, float* vals, void* stream);
 
-/* nnz-balanced work plan: rows longer than 64 non-zeros are cut into segments (32..512 long,
- * growing with the row) that different lane groups process concurrently. */
+/* nnz-balanced work plan: rows longer than 64 non-zeros are cut into 32-nnz segments (64-nnz for rows over
+ * 1024, which accumulate atomically) that different lane groups process concurrently. */
 int64_t mmssl_spmm_plan_items_cap(int64_t n_rows, int64_t nnz);
 int64_t mmssl_spmm_plan_splits_cap(int64_t nnz);
 int64_t mmssl_spmm_plan_segs_cap(int64_t nnz);

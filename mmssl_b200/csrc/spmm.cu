@@ -2,19 +2,24 @@
 // path (reference: MMSSL.mm / torch.sparse.mm, Models.py:69-73, and torch.mm(sparse, dense),
 // Models.py:203-208; the transposed products autograd derives from them use the CSR of A^T).
 //
-// B200 design (HBM / L2 bound sparse gather, no tensor cores):
+// B200 design (sparse gather: latency bound on small graphs, L2-gather / resident-row-walk bound on
+// large ones -- DESIGN.md section 6; no tensor cores):
 //  * one lane *group* (16 lanes for d=64, 32 lanes for d>=128) owns one work item = one row or one
 //    fixed-length segment of a long row (plan built by mmssl_spmm_plan); every lane owns one
 //    float4 column slice per right-hand side, so a neighbour row is fetched with one coalesced
 //    128-bit load per lane (256 B .. 1 KB contiguous per neighbour).
 //  * column indices / values of the row are loaded coalesced (one per lane) and broadcast with
-//    warp shuffles; 4 neighbour gathers per right-hand side are kept in flight per lane.
+//    warp shuffles; the next chunk is prefetched and 8 neighbour gathers (float4 each) are in flight per
+//    lane before the first FMA consumes one.
 //  * up to 3 right-hand sides share one pass over the sparsity pattern (e.g. image|text features),
 //    which divides the index traffic and the launch count.
 //  * long rows (power-law item degrees) are cut into segments handled by different groups; the
-//    last group to arrive sums the partials in segment order -> deterministic, no float atomics.
-//    Segment length grows with the row (32..512) so that neither the row walk nor the final
-//    reduction becomes the critical path of a small (latency-bound) graph.
+//    last group to arrive sums the partials in segment order -> deterministic.  Rows over 1024
+//    non-zeros (the head of a power-law degree distribution) instead accumulate 64-nnz segments with
+//    128-bit float reductions into a zeroed slot: a serial reduction over hundreds of partials would be
+//    the critical path of a small (latency-bound) graph.
+//  * output rows can be stored to the NVSwitch multicast address of a symmetric table (multimem.st) or to
+//    peer-mapped tables: the all-gather of the row-sharded scheme is part of the epilogue.
 //  * fused epilogues: + alpha*C[row], row softmax over d (last GCN layer, Models.py:203-204),
 //    softmax backward y*(g - <g,y>), running layer sum S (+)= out (Models.py:213-214).
 #include "spmm_common.cuh"

@@ -7,12 +7,13 @@ drives it directly (fused with the loss kernels and AdamW, CUDA-graph captured).
 
 Launch inventory of one forward (K GCN layers, modality graphs aliasing ui/iu as at step 0,
 main.py:68-69):  2 projections x (split, GEMM, epilogue) + 2 two-RHS SpMM (image|text batched)
-+ 2 id SpMM + 4 small GEMM/row kernels + 2K SpMM (softmax / layer-sum fused) + 2 combine kernels.
++ 2 id SpMM + Wsum + 2 fused id-fusion kernels + 2K SpMM (softmax / layer-sum fused) + 2 combine kernels,
+scheduled on three streams (see ``Engine.two_streams``).
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 

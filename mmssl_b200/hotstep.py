@@ -1,7 +1,10 @@
 """Fused hot training step: forward -> BPR + 2x InfoNCE + feat_reg (value and gradient seeds in the
-same kernels) -> hand-written backward -> multi-tensor AdamW, all on one stream with static buffers
-so the whole step is captured once into a CUDA graph and replayed (no Python / launch overhead in
-the steady state, no host synchronisation besides reading the loss).
+same kernels) -> hand-written backward -> multi-tensor AdamW, with static buffers, so the whole step
+is captured once into a CUDA graph and replayed (no Python / launch overhead in the steady state, no
+host synchronisation besides reading the loss).  Inside the graph the work forms three parallel
+branches (engine.py): id/GCN chain, modality branch (projection + image|text propagation), and the
+item-side twin of every user-side kernel; memset, dropout masks, the optional GPU sampler and BPR ride
+on the side branches, off the critical path.
 
 Reference unit of work: main.py:363-371 (forward + BPR), :408-414 (feat_reg, InfoNCE),
 :420 (loss without the GAN term), :427-429 (zero_grad / backward / AdamW step).
