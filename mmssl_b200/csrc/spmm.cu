@@ -30,9 +30,7 @@ namespace mmssl {
 // UNR neighbour gathers are issued back to back before the first FMA consumes one, and the next
 // chunk of (col, val) pairs is prefetched while the current one is processed, so a row walk costs
 // about one memory round trip per UNR non-zeros instead of one per load.
-// HINT: column indices carry a 'hot column' flag in bit 31 (graph.py: flagged_colidx); hot rows are gathered
-// with L1::evict_last, cold ones with L1::no_allocate, so L1 keeps the rows most edges point to.
-template <int G, int C, int R, int UMUL, int MINB, bool HINT = false>
+template <int G, int C, int R, int UMUL, int MINB>
 __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p) {
     pdl_wait();
     constexpr int RC = R * C;
@@ -77,17 +75,9 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
                 const bool on = (j + k) < cnt;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    if (HINT) {
-                        const bool hot = cc[k] < 0;
-                        const float* xr = p.x[r] + (int64_t)(cc[k] & 0x7fffffff) * p.ldx[r] + lane * 4;
+                    const float* xr = p.x[r] + (int64_t)cc[k] * p.ldx[r] + lane * 4;
 #pragma unroll
-                        for (int c = 0; c < C; ++c)
-                            xv[k][r][c] = on ? (hot ? ldg4_keep(xr + c * (4 * G)) : ldg4_stream(xr + c * (4 * G))) : f4zero();
-                    } else {
-                        const float* xr = p.x[r] + (int64_t)cc[k] * p.ldx[r] + lane * 4;
-#pragma unroll
-                        for (int c = 0; c < C; ++c) xv[k][r][c] = on ? ldg4(xr + c * (4 * G)) : f4zero();
-                    }
+                    for (int c = 0; c < C; ++c) xv[k][r][c] = on ? ldg4(xr + c * (4 * G)) : f4zero();
                 }
             }
 #pragma unroll
@@ -235,13 +225,13 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
     }
 }
 
-template <int G, int C, int R, int UMUL, int MINB, bool HINT = false>
+template <int G, int C, int R, int UMUL, int MINB>
 static int launch_spmm_v(const SpmmParams& p, cudaStream_t stream, int T) {
     const int64_t groups_per_block = T / G;
     const int64_t blocks = (p.n_items + groups_per_block - 1) / groups_per_block;
     if (blocks == 0) return 0;
     if (blocks > 0x7fffffffll) return fail("mmssl_spmm_csr_f32", "grid too large");
-    MMSSL_CUDA_LAUNCH((spmm_csr_kernel<G, C, R, UMUL, MINB, HINT>), dim3((unsigned)blocks), dim3(T), 0, stream, p);
+    MMSSL_CUDA_LAUNCH((spmm_csr_kernel<G, C, R, UMUL, MINB>), dim3((unsigned)blocks), dim3(T), 0, stream, p);
     MMSSL_LAUNCH_OK();
     return 0;
 }
@@ -249,7 +239,6 @@ static int launch_spmm_v(const SpmmParams& p, cudaStream_t stream, int T) {
 // impl bit 3 (8): twice as many gathers in flight per lane; bit 4 (16): cap registers for 6 blocks/SM
 template <int G, int C, int R>
 static int launch_spmm(const SpmmParams& p, cudaStream_t stream, int T, int impl) {
-    if (impl & 32) return launch_spmm_v<G, C, R, 1, 6, true>(p, stream, T);   // flagged column indices + L1 hints
     switch ((impl >> 3) & 3) {
         case 1: return launch_spmm_v<G, C, R, 2, 1>(p, stream, T);
         case 2: return launch_spmm_v<G, C, R, 1, 6>(p, stream, T);

@@ -101,23 +101,6 @@ class SparseOperand:
             self.hot_edge_fraction = float((sl >= 0).float().mean()) if self.nnz else 0.0
         return self._hot
 
-    def flagged_colidx(self, row_bytes: int, l1_bytes: int = 192 * 1024):
-        """Copy of the column indices with bit 31 set on the columns whose rows should stay in L1: the
-        highest-degree columns, as many as fit (`l1_bytes / row_bytes`).  Used by the impl-bit-5 SpMM."""
-        key = ("flag", row_bytes)
-        if key not in self._work:
-            col = self.colidx[:self.nnz].long()
-            deg = torch.bincount(col, minlength=self.n_cols)
-            h = int(min(max(l1_bytes // row_bytes, 1), self.n_cols))
-            hot = torch.zeros(self.n_cols, dtype=torch.bool, device=self.device)
-            hot[torch.topk(deg, h).indices] = True
-            flagged = torch.where(hot[col], self.colidx[:self.nnz] | (-2147483648), self.colidx[:self.nnz]).to(torch.int32)
-            buf = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=self.device)
-            buf[:self.nnz] = flagged
-            self._work[key] = buf
-            self.hot_edge_fraction = float(hot[col].float().mean()) if self.nnz else 0.0
-        return self._work[key]
-
     def tighten(self) -> None:
         """Optional: read the exact item count back (one host sync) so launches are not padded."""
         if self._n_items_exact is None:

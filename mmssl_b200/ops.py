@@ -80,8 +80,6 @@ def spmm(a: SparseOperand, xs: Sequence[torch.Tensor], ys: Optional[Sequence[tor
     desc = type(a.desc).from_buffer_copy(a.desc)
     desc.counters = counters.data_ptr()
     impl = _default_spmm_impl if impl is None else impl
-    if impl != SPMM_IMPL_TMA and (impl & 32):       # L1-hinted gathers: column indices with the hot flag
-        desc.colidx = a.flagged_colidx(nrhs * d * 4).data_ptr()
     if impl == SPMM_IMPL_TMA:
         colidx_hot, hot_ids, n_hot = a.hot_plan()
         _lib.check(lib.mmssl_spmm_hot_f32(C.byref(desc), ptr(colidx_hot), ptr(hot_ids), n_hot, d, nrhs, rhs, epilogue,
