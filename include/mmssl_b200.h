@@ -206,6 +206,15 @@ int mmssl_adamw(int n_tensors, float* const* p /*host array of device ptrs*/, co
                 float* const* v, const int64_t* numel /*host*/, const int32_t* step_dev, float lr, float beta1,
                 float beta2, float eps, float weight_decay, void* stream);
 
+/* Data-parallel optimiser step fused with its collectives over NVSwitch multicast (one kernel): this rank's slice
+ * [begin, begin+count) of the flat buckets: g = multimem.ld_reduce(add) over all ranks' gradient buckets * inv_world,
+ * AdamW with slice-local m, v (indexed from 0), new parameters multimem.st'ed into every rank's parameter bucket.
+ * p_mc / g_mc are the multicast addresses of the symmetric parameter / gradient buckets, p_local this rank's copy.
+ * The caller barriers all ranks before and after.  step is 1-based (host value). */
+int mmssl_dp_fused_adamw(const float* p_local, float* p_mc, const float* g_mc, float* m, float* v, int64_t begin,
+                         int64_t count, float inv_world, int step, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, void* stream);
+
 /* ------------------------------------------------------------------ GPU triple sampler (SURVEY 8f "next" #1)
  * Semantics of Data.sample (utility/load_data.py:153-191): `batch` (<= 1024) distinct users with >= 1
  * training item (with replacement only if batch > n_exist), one uniform positive from the user's CSR row

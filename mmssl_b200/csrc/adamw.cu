@@ -60,9 +60,61 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamPack pk, const int
     }
 }
 
+// Data-parallel optimiser step in ONE kernel over NVSwitch multicast (sharded AdamW):
+//   g   = multimem.ld_reduce(add) over every rank's gradient bucket      (reduce-scatter, summed in the switch)
+//   AdamW on this rank's slice only (m, v exist only for the slice)
+//   multimem.st of the new parameters into every rank's parameter buffer  (all-gather)
+// Buckets are symmetric-memory buffers with the same layout on every rank; callers barrier before (all
+// gradients written) and after (all slices published).
+__global__ void __launch_bounds__(256) dp_fused_adamw_kernel(const float* __restrict__ p_local, float* p_mc,
+                                                             const float* g_mc, float* __restrict__ m,
+                                                             float* __restrict__ v, int64_t begin, int64_t count4,
+                                                             float inv_world, int step, float lr, float b1, float b2,
+                                                             float eps, float wd) {
+    const float bc1 = 1.f - powf(b1, (float)step);
+    const float bc2 = 1.f - powf(b2, (float)step);
+    const float step_size = lr / bc1;
+    const float inv_sqrt_bc2 = rsqrtf(bc2);
+    const float decay = 1.f - lr * wd;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = begin + i * 4;
+        float4 g;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "l"(g_mc + e) : "memory");
+        float4 pv = ld4(p_local + e), mv = ld4(m + i * 4), vv = ld4(v + i * 4);
+        float* pp = &pv.x; float* gg = &g.x; float* mm = &mv.x; float* vq = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gk = gg[k] * inv_world;
+            mm[k] = b1 * mm[k] + (1.f - b1) * gk;
+            vq[k] = b2 * vq[k] + (1.f - b2) * gk * gk;
+            pp[k] = pp[k] * decay - step_size * (mm[k] / (sqrtf(vq[k]) * inv_sqrt_bc2 + eps));
+        }
+        st4(m + i * 4, mv); st4(v + i * 4, vv);
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p_mc + e), "f"(pv.x), "f"(pv.y),
+                     "f"(pv.z), "f"(pv.w) : "memory");
+    }
+}
+
 }  // namespace mmssl
 
 using namespace mmssl;
+
+extern "C" int mmssl_dp_fused_adamw(const float* p_local, float* p_mc, const float* g_mc, float* m, float* v, int64_t begin,
+                                    int64_t count, float inv_world, int step, float lr, float beta1, float beta2, float eps,
+                                    float weight_decay, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    MMSSL_REQUIRE(begin % 4 == 0 && count % 4 == 0, "slice must be a multiple of 4 floats");
+    MMSSL_REQUIRE(aligned16(p_local) && aligned16(p_mc) && aligned16(g_mc) && aligned16(m) && aligned16(v), "alignment");
+    MMSSL_REQUIRE(step >= 1, "step is 1-based");
+    if (count == 0) return 0;
+    int64_t blocks = (count / 4 + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    dp_fused_adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p_local, p_mc, g_mc, m, v, begin, count / 4, inv_world, step, lr,
+                                                           beta1, beta2, eps, weight_decay);
+    MMSSL_LAUNCH_OK();
+    return 0;
+}
 
 extern "C" int mmssl_step_tick(int32_t* step_dev, void* stream_) {
     MMSSL_CUDA_LAUNCH((step_tick_kernel), dim3(1), dim3(1), 0, (cudaStream_t)stream_, step_dev);

@@ -52,6 +52,62 @@ class GradBucket:
         self.flat.mul_(1.0 / world)
 
 
+class FusedDPOptimizer:
+    """Data-parallel optimiser step as ONE kernel over NVSwitch multicast (mmssl_dp_fused_adamw):
+    reduce-scatter of the gradient bucket by `multimem.ld_reduce` (summed in the switch), AdamW on this
+    rank's 1/world slice (m, v are sharded), all-gather of the new parameters by `multimem.st`.
+    Parameters and gradients live in two symmetric-memory buckets with identical layout on every rank;
+    `params` / `grads` are views into them.  No NCCL on the data path; two signal-pad barriers per step."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], rank: int, world: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-8,
+                 weight_decay=1e-2, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.keys = list(params.keys())
+        self.rank, self.world = rank, world
+        self.hyper = (float(lr), float(beta1), float(beta2), float(eps), float(weight_decay))
+        offs, total = [], 0
+        for k in self.keys:
+            offs.append(total)
+            total += (params[k].numel() + 3) // 4 * 4
+        unit = 4 * world
+        total = (total + unit - 1) // unit * unit
+        dev = params[self.keys[0]].device
+        g = group if group is not None else dist.group.WORLD
+        self.pflat = symm.empty(total, dtype=torch.float32, device=dev)
+        self.gflat = symm.empty(total, dtype=torch.float32, device=dev)
+        self.pflat.zero_(); self.gflat.zero_()
+        self.hp = symm.rendezvous(self.pflat, g.group_name)
+        self.hg = symm.rendezvous(self.gflat, g.group_name)
+        self.p_mc, self.g_mc = int(self.hp.multicast_ptr), int(self.hg.multicast_ptr)
+        if self.p_mc == 0 or self.g_mc == 0:
+            raise RuntimeError("NVSwitch multicast is not available for symmetric memory on this system")
+        self.params: Dict[str, torch.Tensor] = {}
+        self.grads: Dict[str, torch.Tensor] = {}
+        for k, o in zip(self.keys, offs):
+            n = params[k].numel()
+            self.params[k] = self.pflat[o:o + n].view_as(params[k])
+            self.params[k].copy_(params[k])
+            self.grads[k] = self.gflat[o:o + n].view_as(params[k])
+        self.count = total // world
+        self.begin = rank * self.count
+        self.m = torch.zeros(self.count, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(self.count, dtype=torch.float32, device=dev)
+        self.step_no = 0
+        torch.cuda.synchronize(dev)
+        self.hp.barrier()
+
+    def step(self) -> None:
+        from . import _lib
+        from ._lib import ptr, stream
+        lib = _lib.load(require_device=True)
+        self.step_no += 1
+        lr, b1, b2, eps, wd = self.hyper
+        self.hg.barrier()          # every rank's gradients are complete
+        _lib.check(lib.mmssl_dp_fused_adamw(ptr(self.pflat), self.p_mc, self.g_mc, ptr(self.m), ptr(self.v), self.begin,
+                                            self.count, 1.0 / self.world, self.step_no, lr, b1, b2, eps, wd, stream()))
+        self.hp.barrier()          # every slice of the new parameters has been published
+
+
 # ------------------------------------------------------------------------------------------ row sharding
 @dataclass(frozen=True)
 class RowPartition:
