@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = the count that measured fastest on this host class (tools/cpu_threads.py)")
     ap.add_argument("--seed", type=int, default=2022)
+    ap.add_argument("--dp", default="fused", choices=["fused", "nccl"],
+                    help="N>1 optimiser step: 'fused' = one multimem kernel (reduce-scatter + sharded AdamW + all-gather over "
+                         "NVSwitch multicast, falls back to nccl when multicast is unavailable); 'nccl' = all-reduce + replicated AdamW")
     ap.add_argument("--graph-comm", action="store_true",
                     help="EXPERIMENTAL (hung in round 1): capture the DP all-reduce + AdamW inside the CUDA graph")
     return ap.parse_args()
@@ -143,9 +146,24 @@ def build_problem(name: str, seed: int, device):
 class HotStepTrainer:
     """Public API of the fused path: ``train_step(users, pos, neg) -> float loss`` (host in, host out)."""
 
-    def __init__(self, P, feats, graphs, cfg, batch, world=1, sampler=None, graph_comm=False):
+    def __init__(self, P, feats, graphs, cfg, batch, world=1, sampler=None, graph_comm=False, dp="fused"):
         from mmssl_b200.hotstep import HotStep
         self.world = world
+        self.dp_opt = None
+        if world > 1 and not graph_comm and dp == "fused":
+            # parameters and gradients move into symmetric-memory buckets BEFORE capture, so the graph's kernels
+            # read / write them in place and the optimiser is one multimem kernel (parallel.FusedDPOptimizer)
+            import torch.distributed as dist
+            from mmssl_b200.engine import LIVE
+            from mmssl_b200.parallel import FusedDPOptimizer
+            try:
+                self.dp_opt = FusedDPOptimizer({k: P[k] for k in LIVE}, dist.get_rank(), world, cfg.lr, cfg.beta1, cfg.beta2,
+                                               cfg.eps, cfg.weight_decay)
+                P = {**P, **self.dp_opt.params}
+            except RuntimeError as e:      # no NVSwitch multicast on this system: NCCL all-reduce path
+                if dist.get_rank() == 0:
+                    print(f"[bench] fused DP optimiser unavailable ({e}); using the NCCL path", file=sys.stderr)
+        self.dp_mode = "fused" if self.dp_opt is not None else "nccl"
         # Default (validated at N = 2, 4, 8): the gradient all-reduce (NCCL) and AdamW are issued eagerly after
         # the graph replay.  graph_comm=True captures them inside the graph; that variant deadlocked on the
         # box in round 1 (NCCL capture) and is kept only as an experiment.
@@ -153,7 +171,9 @@ class HotStepTrainer:
         self.hs = HotStep(P, feats, graphs, cfg, batch=batch, optimizer_step=self.graph_comm, sampler=sampler)
         self.pin_idx = torch.empty(3, batch, dtype=torch.int64).pin_memory()
         self.pin_out = torch.empty(5, dtype=torch.float32).pin_memory()
-        if world > 1:
+        if self.dp_opt is not None:
+            self.hs.grads.update(self.dp_opt.grads)
+        elif world > 1:
             from mmssl_b200.parallel import GradBucket
             self.bucket = GradBucket(self.hs.grads)      # one flat all-reduce bucket for all live parameters
             self.hs.grads.update(self.bucket.views)
@@ -162,7 +182,11 @@ class HotStepTrainer:
         self.hs.capture(warmup=2)
 
     def _finish_step(self):
-        if self.world > 1 and not self.graph_comm:
+        if self.dp_opt is not None:
+            from mmssl_b200 import ops
+            ops.step_tick(self.hs.step_dev)      # the device sampler's counter
+            self.dp_opt.step()
+        elif self.world > 1 and not self.graph_comm:
             from mmssl_b200 import ops
             from mmssl_b200.engine import LIVE
             self.bucket.all_reduce_mean()
@@ -335,7 +359,10 @@ def main():
 
     ds, P, feats, graphs, _ = build_problem(a.config, a.seed, dev)
     cfg = HotStepConfig(embed_size=d, n_layers=K, batch_size=BATCH, proj_impl=a.proj)
-    trainer = HotStepTrainer(P, feats, graphs, cfg, BATCH, world=world, graph_comm=a.graph_comm)
+    trainer = HotStepTrainer(P, feats, graphs, cfg, BATCH, world=world, graph_comm=a.graph_comm, dp=a.dp)
+    if world > 1 and trainer.dp_mode == "fused":
+        config["parallelism"] = (f"dp{world} (replicated graph; optimiser step = one multimem kernel after the graph replay: "
+                                 f"switch-reduced gradient slice, AdamW on 1/{world} of the parameters, multicast store of the new slice)")
     smp = TripleSampler(ds.train, seed=a.seed + 17 * rank)
     n_batches = a.steps + a.warmup
     host_batches = [np.stack(smp.sample(BATCH)) for _ in range(n_batches)]
