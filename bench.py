@@ -160,7 +160,7 @@ class HotStepTrainer:
                 self.dp_opt = FusedDPOptimizer({k: P[k] for k in LIVE}, dist.get_rank(), world, cfg.lr, cfg.beta1, cfg.beta2,
                                                cfg.eps, cfg.weight_decay)
                 P = {**P, **self.dp_opt.params}
-            except RuntimeError as e:      # no NVSwitch multicast on this system: NCCL all-reduce path
+            except (RuntimeError, ImportError, AttributeError) as e:      # no NVSwitch multicast / symmetric memory here: NCCL path
                 if dist.get_rank() == 0:
                     print(f"[bench] fused DP optimiser unavailable ({e}); using the NCCL path", file=sys.stderr)
         self.dp_mode = "fused" if self.dp_opt is not None else "nccl"

@@ -1,4 +1,5 @@
 """Pin the CPU oracle against golden vectors minted from the unmodified reference."""
+import numpy as np
 import pytest
 import torch
 
@@ -73,3 +74,20 @@ def test_adamw_matches_torch():
         opt.step()
         O.adamw_step(p, gr, m, v, step, lr=5.5e-4)
         assert rel_err(p, ref) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ evaluation path (section 8f row 3)
+@pytest.mark.parametrize("case", ["eval_random", "eval_ties", "eval_short"])
+@pytest.mark.parametrize("split", ["test", "val"])
+def test_eval_oracle_matches_reference(case, split):
+    """oracle/eval_oracle.py == the unmodified reference's test_torch / test_one_user / ranklist_by_heapq."""
+    import os
+    from oracle import eval_oracle as EO
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", case + ".npz"))
+    Ks = [int(k) for k in g["Ks"]]
+    out = EO.evaluate(g["ua"], g["ia"], g[f"{split}_users"], g["train_indptr"], g["train_indices"], g[f"{split}_indptr"],
+                      g[f"{split}_indices"], Ks)
+    assert np.array_equal(out["ranked"], g[f"{split}_ranked"])          # incl. the tie order
+    assert np.array_equal(out["hits"], g[f"{split}_hits"])
+    np.testing.assert_allclose(out["per_user"], g[f"{split}_per_user"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(out["result"], g[f"{split}_result"], rtol=0, atol=1e-14)
