@@ -226,6 +226,24 @@ int mmssl_sample_triples(const int64_t* indptr, const int64_t* indices, const in
                          int64_t n_items, int batch, uint64_t seed, const int32_t* step_dev, int32_t step_host,
                          int32_t* claim, int64_t* users, int64_t* pos, int64_t* neg, void* stream);
 
+/* ------------------------------------------------------------------ evaluation (SURVEY 8f "next" #3)
+ * Trainer.test -> test_torch / test_one_user (main.py:301-306, utility/batch_test.py:21-36, :83-169) and
+ * utility/metrics.py:9-19, :43-90, fused: scores of users[n_eval] against all items are ranked on the fly (no
+ * [users x items] matrix in HBM), training items (CSR rows, int64, SORTED) are skipped, the max(Ks) best remain,
+ * equal scores keep the lower item id first (heapq.nlargest over ascending ids).  Outputs:
+ *   ranked[n_eval, kmax] item ids best first (-1 past the end of a short list); ranked_scores (may be NULL);
+ *   hits[n_eval, kmax] 1/0 membership in the held-out row (CSR, SORTED), -1 past the end (may be NULL);
+ *   per_user[n_eval, 4, n_ks] fp64 = precision, recall, ndcg, hit_ratio at every K (reference quirks kept:
+ *   ideal DCG from the retrieved hit list, precision divisor shrinks with short lists, recall / len(held-out));
+ *   scores_out[n_eval, n_items] (may be NULL; debugging / tests).  ks_host is a HOST array of n_ks <= 8 cut-offs <= 64.
+ * mmssl_eval_reduce: result[m] = mean over users of per_user[:, m] (batch_test.py:159-163), fixed order. */
+int mmssl_eval_rank(const float* user_emb, int64_t ldu, const float* item_emb, int64_t ldi, int64_t n_items, int d,
+                    const int64_t* users, int64_t n_eval, const int64_t* train_indptr, const int64_t* train_indices,
+                    const int64_t* held_indptr, const int64_t* held_indices, const int32_t* ks_host, int n_ks,
+                    int32_t* ranked, float* ranked_scores, int32_t* hits, double* per_user, float* scores_out,
+                    void* stream);
+int mmssl_eval_reduce(const double* per_user, int64_t n_eval, int n_metrics, double* result, void* stream);
+
 /* ------------------------------------------------------------------ projection (tcgen05 + TMA), see proj_tc.cu */
 int mmssl_split_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo, int64_t ldo,
                      void* stream);

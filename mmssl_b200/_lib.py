@@ -85,6 +85,9 @@ _SIGS = {
     "mmssl_dp_fused_adamw": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_i32, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp]),
     "mmssl_sampler_init": (C.c_int, [c_vp, c_i64, c_vp]),
     "mmssl_sample_triples": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, C.c_uint64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mmssl_eval_rank": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, C.POINTER(c_i32), c_i32,
+                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mmssl_eval_reduce": (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     "mmssl_split_bf16": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "mmssl_split_bf16_t": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "mmssl_gemm_bf16x3_workspace_floats": (c_i64, [c_i64, c_i64, c_i64, C.POINTER(c_i32)]),
@@ -105,6 +108,7 @@ KERNELS_PER_CALL = {
     "mmssl_infonce_stats": 2, "mmssl_infonce_grad": 1, "mmssl_infonce_scatter": 1, "mmssl_loss_assemble": 1,
     "mmssl_step_tick": 1, "mmssl_dp_fused_adamw": 1, "mmssl_sampler_init": 1, "mmssl_sample_triples": 1, "mmssl_adamw": 1, "mmssl_split_bf16": 1, "mmssl_split_bf16_t": 1, "mmssl_gemm_bf16x3": 1,
     "mmssl_proj_epilogue": 1, "mmssl_wgrad_epilogue": 1, "mmssl_colsum": 1,
+    "mmssl_eval_rank": 1, "mmssl_eval_reduce": 1,
 }
 launch_count = 0
 call_log = None   # set to a list to record (name) of every kernel-launching call

@@ -91,3 +91,42 @@ def test_eval_oracle_matches_reference(case, split):
     assert np.array_equal(out["hits"], g[f"{split}_hits"])
     np.testing.assert_allclose(out["per_user"], g[f"{split}_per_user"], rtol=0, atol=1e-15)
     np.testing.assert_allclose(out["result"], g[f"{split}_result"], rtol=0, atol=1e-14)
+
+
+def _model_vs_oracle(ua, ia, users, tr_ptr, tr_idx, he_ptr, he_idx, Ks, seed=0):
+    from oracle import eval_oracle as EO
+    from tests.eval_kernel_model import rank_one_user
+    ref = EO.evaluate(ua, ia, users, tr_ptr, tr_idx, he_ptr, he_idx, Ks)
+    rating = EO.scores(ua, ia, users)
+    rng = np.random.default_rng(seed)
+    for n, u in enumerate(users):
+        tr = np.sort(tr_idx[tr_ptr[u]:tr_ptr[u + 1]])
+        he = np.sort(he_idx[he_ptr[u]:he_ptr[u + 1]])
+        ranked, met = rank_one_user(rating[n], tr, he, Ks, rng)
+        want = ref["ranked"][n]
+        assert np.array_equal(ranked, want[want >= 0]), (n, u)
+        np.testing.assert_allclose(met, ref["per_user"][n], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("case", ["eval_random", "eval_ties", "eval_short"])
+def test_eval_kernel_algorithm_model_on_golden(case):
+    """The selection algorithm of csrc/eval.cu (executable model) == oracle == reference, incl. ties and short lists."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", case + ".npz"))
+    _model_vs_oracle(g["ua"], g["ia"], g["test_users"], g["train_indptr"], g["train_indices"], g["test_indptr"],
+                     g["test_indices"], [int(k) for k in g["Ks"]])
+
+
+def test_eval_kernel_algorithm_model_many_items_and_ties():
+    """Several compactions per user (I = 3000 > buffer), heavy ties, negative / zero / signed-zero scores."""
+    rng = np.random.default_rng(3)
+    U, I, d = 12, 3000, 8
+    ua = (np.round(rng.standard_normal((U, d)) * 2) / 2).astype(np.float32)
+    ia = (np.round(rng.standard_normal((I, d)) * 2) / 2).astype(np.float32)
+    ia[::7] = 0.0                                      # exact zeros; with negative user entries -> -0.0 products
+    ua[3] = -np.abs(ua[3])
+    tr_ptr = np.arange(0, (U + 1) * 40, 40, dtype=np.int64)
+    tr_idx = np.concatenate([rng.choice(I, 40, replace=False) for _ in range(U)]).astype(np.int64)
+    he_ptr = np.arange(0, (U + 1) * 25, 25, dtype=np.int64)
+    he_idx = np.concatenate([rng.choice(I, 25, replace=False) for _ in range(U)]).astype(np.int64)
+    _model_vs_oracle(ua, ia, np.arange(U), tr_ptr, tr_idx, he_ptr, he_idx, [1, 10, 20, 50, 64], seed=1)
