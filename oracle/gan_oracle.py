@@ -87,7 +87,8 @@ def discriminator(x: torch.Tensor, S: Dict[str, torch.Tensor], mask1: Optional[t
         return F.batch_norm(h, S[f"net.{k}.running_mean"], S[f"net.{k}.running_var"], S[f"net.{k}.weight"], S[f"net.{k}.bias"],
                             training, 0.1, 1e-5)
 
-    h = F.linear(x.float(), S["net.0.weight"], S["net.0.bias"])
+    w1 = S["net.0.weight"]
+    h = F.linear(x.float() if w1.dtype == torch.float32 else x.to(w1.dtype), w1, S["net.0.bias"])     # fp64 only in closed-form tests
     h = F.leaky_relu(h, negative_slope=1.0)               # nn.LeakyReLU(True): negative_slope = True
     h = bn(h, 2)
     h = h * mask1 if training else h
@@ -245,3 +246,132 @@ class FullStep:
         self.graphs = new_graphs
         self.idx += 1
         return tr
+
+
+# ==========================================================================================
+# Closed forms (no autograd) -- the arithmetic a CUDA implementation of the D step executes.
+# Verified against the autograd versions above in tests/test_gan_oracle.py.
+#
+# One D call on n rows (training mode), h1 = I/4, h2 = I/8:
+#   a1 = x W1^T + b1 ; BN: mu, r = (var_biased + eps)^-1/2, ah = (a - mu) r, y = gamma ah + beta ; h = y * M
+#   a2 = h1 W2^T + b2 ; BN ; h2 ; z = h2 w3^T + b3 ; s = sigmoid(z) ; out = 100 s
+# GEMM census per call (big = n x I x h1): forward 1 big; parameter gradients 1 big (dW1); input gradient 1 big (dx);
+# gradient penalty = forward + input gradient + 3 big in the second-order sweep (gbar W1^T, da1^T gbar, abar1^T x).
+# ==========================================================================================
+_EPS = 1e-5
+
+
+def d_forward_cache(x: torch.Tensor, S: Dict[str, torch.Tensor], m1: torch.Tensor, m2: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Forward of one training-mode D call keeping what the backward sweeps need (BatchNorm buffers are NOT touched)."""
+    c: Dict[str, torch.Tensor] = {"x": x, "m1": m1, "m2": m2}
+    h = x
+    for li, (lin, bn, mask) in enumerate((("net.0", "net.2", m1), ("net.4", "net.6", m2)), start=1):
+        a = h @ S[lin + ".weight"].T + S[lin + ".bias"]
+        mu = a.mean(0)
+        var = ((a - mu) ** 2).mean(0)
+        r = (var + _EPS).rsqrt()
+        ah = (a - mu) * r
+        y = ah * S[bn + ".weight"] + S[bn + ".bias"]
+        c[f"hin{li}"], c[f"r{li}"], c[f"ah{li}"] = h, r, ah
+        h = y * mask
+    c["h2"] = h
+    z = h @ S["net.8.weight"].T + S["net.8.bias"]
+    c["s"] = torch.sigmoid(z).view(-1)
+    c["out"] = 100 * c["s"]
+    return c
+
+
+def _bn_bwd(dah: torch.Tensor, ah: torch.Tensor, r: torch.Tensor) -> torch.Tensor:
+    return r * (dah - dah.mean(0) - ah * (dah * ah).mean(0))
+
+
+def d_backward(c: Dict[str, torch.Tensor], S: Dict[str, torch.Tensor], dout: torch.Tensor, need_dx: bool = False):
+    """First-order sweep: gradients of sum(dout * out) w.r.t. the D parameters (and x).  Also returns the per-layer
+    pre-BatchNorm gradients the second-order sweep reuses."""
+    g: Dict[str, torch.Tensor] = {}
+    dz = (100 * c["s"] * (1 - c["s"]) * dout).unsqueeze(1)                       # [n, 1]
+    g["net.8.weight"] = dz.T @ c["h2"]
+    g["net.8.bias"] = dz.sum(0)
+    dh = dz @ S["net.8.weight"]
+    keep = {"dz": dz}
+    for li, (lin, bn, mask) in ((2, ("net.4", "net.6", c["m2"])), (1, ("net.0", "net.2", c["m1"]))):
+        dy = dh * mask
+        g[bn + ".weight"] = (dy * c[f"ah{li}"]).sum(0)
+        g[bn + ".bias"] = dy.sum(0)
+        dah = dy * S[bn + ".weight"]
+        da = _bn_bwd(dah, c[f"ah{li}"], c[f"r{li}"])
+        g[lin + ".weight"] = da.T @ c[f"hin{li}"]
+        g[lin + ".bias"] = da.sum(0)                                              # exactly 0 in exact arithmetic
+        keep[f"dy{li}"], keep[f"dah{li}"], keep[f"da{li}"] = dy, dah, da
+        if li == 2 or need_dx:
+            dh = da @ S[lin + ".weight"]
+    return g, (dh if need_dx else None), keep
+
+
+def gradient_penalty_closed(x: torch.Tensor, S: Dict[str, torch.Tensor], m1, m2, lam: float = 0.3):
+    """gp = lam * mean_i (||g_i|| - 1)^2 with g = d(sum out)/dx, and its gradient w.r.t. every D parameter,
+    by an explicit reverse sweep over [forward ; first-order backward]."""
+    n = x.shape[0]
+    c = d_forward_cache(x, S, m1, m2)
+    _, gx, k = d_backward(c, S, torch.ones(n), need_dx=True)
+    norm = gx.norm(2, dim=1, keepdim=True)
+    gp = lam * ((norm - 1) ** 2).mean()
+    gbar = (2 * lam / n) * (norm - 1) * gx / norm                                # d gp / d g     [n, I]
+    G = {kk: torch.zeros_like(S[kk]) for kk in D_PARAMS}
+
+    # ---- reverse of the first-order backward sweep (bottom-up: layer 1 first) ----
+    def rev_bn_bwd(q, dah, ah, r):
+        """da = r * u, u = dah - mean(dah) - ah * mean(dah * ah).  q = adjoint of da.
+        Returns adjoints of (dah, ah, r)."""
+        u = dah - dah.mean(0) - ah * (dah * ah).mean(0)
+        r_bar = (q * u).sum(0)
+        ub = q * r
+        c_bar = -(ub * ah).sum(0) / n
+        dah_bar = ub - ub.mean(0) + c_bar * ah
+        ah_bar = c_bar * dah - ub * (dah * ah).mean(0)
+        return dah_bar, ah_bar, r_bar
+
+    q1 = gbar @ S["net.0.weight"].T                                              # adjoint of da1   (big GEMM)
+    G["net.0.weight"] += k["da1"].T @ gbar                                       #                  (big GEMM)
+    dah1_bar, ah1_bar, r1_bar = rev_bn_bwd(q1, k["dah1"], c["ah1"], c["r1"])
+    G["net.2.weight"] += (dah1_bar * k["dy1"]).sum(0)
+    dh1_bar = dah1_bar * S["net.2.weight"] * c["m1"]                             # adjoint of dh1 = da2 W2
+    q2 = dh1_bar @ S["net.4.weight"].T
+    G["net.4.weight"] += k["da2"].T @ dh1_bar
+    dah2_bar, ah2_bar, r2_bar = rev_bn_bwd(q2, k["dah2"], c["ah2"], c["r2"])
+    G["net.6.weight"] += (dah2_bar * k["dy2"]).sum(0)
+    dh2_bar = dah2_bar * S["net.6.weight"] * c["m2"]                             # adjoint of dh2 = dz w3
+    dz_bar = dh2_bar @ S["net.8.weight"].T                                       # [n, 1]
+    G["net.8.weight"] += (k["dz"] * dh2_bar).sum(0, keepdim=True)
+    s = c["s"].unsqueeze(1)
+    s_bar = dz_bar * 100 * (1 - 2 * s)
+
+    # ---- reverse of the forward sweep, seeded with the adjoints collected above ----
+    z_bar = s_bar * s * (1 - s)
+    G["net.8.weight"] += z_bar.T @ c["h2"]
+    G["net.8.bias"] += z_bar.sum(0)
+    h_bar = z_bar @ S["net.8.weight"]
+    for li, (lin, bn, mask, ah_bar, r_bar) in ((2, ("net.4", "net.6", c["m2"], ah2_bar, r2_bar)),
+                                               (1, ("net.0", "net.2", c["m1"], ah1_bar, r1_bar))):
+        y_bar = h_bar * mask
+        G[bn + ".weight"] += (y_bar * c[f"ah{li}"]).sum(0)
+        G[bn + ".bias"] += y_bar.sum(0)
+        ah_tot = ah_bar + y_bar * S[bn + ".weight"]
+        a_bar = _bn_bwd(ah_tot, c[f"ah{li}"], c[f"r{li}"]) - (r_bar * c[f"r{li}"] ** 2) * c[f"ah{li}"] / n
+        G[lin + ".weight"] += a_bar.T @ c[f"hin{li}"]                            # layer 1: big GEMM
+        G[lin + ".bias"] += a_bar.sum(0)
+        if li == 2:
+            h_bar = a_bar @ S[lin + ".weight"]
+    return gp, G
+
+
+def u_sim_backward(users, user_final, item_final, train_csr: sp.csr_matrix, g_out: torch.Tensor):
+    """Closed-form backward of u_sim: g_out [B, I] -> (rows of d user_final at `users` [B, d], d item_final [I, d])."""
+    users = [int(u) for u in users]
+    keep = 1 - torch.from_numpy(np.asarray(train_csr[users].todense()))
+    ub = user_final[users]
+    raw = (ub @ item_final.T) * keep
+    nrm = raw.norm(2, dim=1, keepdim=True).clamp_min(1e-12)
+    y = raw / nrm
+    d_raw = (g_out - y * (g_out * y).sum(1, keepdim=True)) / nrm * keep
+    return d_raw @ item_final, d_raw.T @ ub

@@ -96,3 +96,81 @@ def test_modality_graph_rebuilds(replay):
             assert np.array_equal(gc.indices().numpy(), z[f"graph_idx/{n}"])
             np.testing.assert_allclose(gc.values().numpy(), z[f"graph_val/{n}"], rtol=1e-6)
     assert traces[1]["graphs"][0]._nnz() > 0 and traces[2]["graphs"][0]._nnz() == 0
+
+
+# ------------------------------------------------------------------------------------------ closed forms vs autograd
+def _random_d(n_items=96, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    h1, h2 = n_items // 4, n_items // 8
+    S = {"net.0.weight": torch.randn(h1, n_items, generator=g) * (2 / n_items) ** 0.5, "net.0.bias": torch.randn(h1, generator=g) * 0.1,
+         "net.2.weight": 1 + 0.2 * torch.randn(h1, generator=g), "net.2.bias": 0.1 * torch.randn(h1, generator=g),
+         "net.4.weight": torch.randn(h2, h1, generator=g) * (2 / h1) ** 0.5, "net.4.bias": torch.randn(h2, generator=g) * 0.1,
+         "net.6.weight": 1 + 0.2 * torch.randn(h2, generator=g), "net.6.bias": 0.1 * torch.randn(h2, generator=g),
+         "net.8.weight": torch.randn(1, h2, generator=g) * (2 / h2) ** 0.5, "net.8.bias": torch.zeros(1)}
+    for k, n in (("net.2", h1), ("net.6", h2)):
+        S[k + ".running_mean"], S[k + ".running_var"] = torch.zeros(n), torch.ones(n)
+        S[k + ".num_batches_tracked"] = torch.tensor(0)
+    return {k: v.double() if v.is_floating_point() else v for k, v in S.items()}, g
+
+
+def test_closed_form_first_order_backward_matches_autograd():
+    S, g = _random_d()
+    n, I = 48, 96
+    x = torch.randn(n, I, generator=g).double()
+    m1 = ((torch.rand(n, I // 4, generator=g) >= 0.31) / 0.69).double()
+    m2 = ((torch.rand(n, I // 8, generator=g) >= 0.5) / 0.5).double()
+    dout = torch.randn(n, generator=g).double()
+    Sa = {k: (v.clone().requires_grad_(True) if k in GO.D_PARAMS else v.clone()) for k, v in S.items()}
+    xa = x.clone().requires_grad_(True)
+    out = GO.discriminator(xa, Sa, m1, m2)
+    want = torch.autograd.grad((out * dout).sum(), [Sa[k] for k in GO.D_PARAMS] + [xa])
+    c = GO.d_forward_cache(x, S, m1, m2)
+    assert rel_err(c["out"], out) < 1e-12
+    got, dx, _ = GO.d_backward(c, S, dout, need_dx=True)
+    for k, w in zip(GO.D_PARAMS, want):
+        if k in DEAD_BIAS:
+            assert float(got[k].abs().max()) < 1e-9 and float(w.abs().max()) < 1e-9
+        else:
+            assert rel_err(got[k].view_as(w), w) < 1e-10, k
+    assert rel_err(dx, want[-1]) < 1e-10
+
+
+def test_closed_form_gradient_penalty_matches_double_backward():
+    """Explicit reverse sweep over [forward ; backward] (BatchNorm statistics included) == autograd's double backward."""
+    S, g = _random_d(seed=4)
+    n, I = 64, 96
+    xr = torch.nn.functional.normalize(torch.rand(n, I, generator=g).double(), dim=1)
+    xf = torch.nn.functional.normalize(torch.randn(n, I, generator=g).double(), dim=1)
+    alpha = torch.rand(n, 1, generator=g).double()
+    m1 = ((torch.rand(n, I // 4, generator=g) >= 0.31) / 0.69).double()
+    m2 = ((torch.rand(n, I // 8, generator=g) >= 0.5) / 0.5).double()
+    Sa = {k: (v.clone().requires_grad_(True) if k in GO.D_PARAMS else v.clone()) for k, v in S.items()}
+    gp_a = GO.gradient_penalty(Sa, xr, xf, alpha, m1, m2, GO.GanConfig())
+    want = torch.autograd.grad(gp_a, [Sa[k] for k in GO.D_PARAMS], allow_unused=True)
+    inter = alpha * xr + (1 - alpha) * xf
+    gp_c, G = GO.gradient_penalty_closed(inter, S, m1, m2, lam=0.3)
+    assert abs(float(gp_c) - float(gp_a)) < 1e-12 * max(1.0, abs(float(gp_a)))
+    scale = max(float(w.abs().max()) for w in want if w is not None)
+    for k, w in zip(GO.D_PARAMS, want):
+        if w is None:                                  # the last bias does not reach d out / d x
+            assert float(G[k].abs().max()) == 0.0, k
+        elif k in DEAD_BIAS:
+            assert float(G[k].abs().max()) < 1e-9 * scale
+        else:
+            assert rel_err(G[k].view_as(w), w) < 1e-9, k
+
+
+def test_closed_form_u_sim_backward_matches_autograd():
+    g = torch.Generator().manual_seed(2)
+    U, I, d, B = 40, 50, 16, 12
+    R = sp.random(U, I, density=0.1, format="csr", random_state=1, dtype=np.float32)
+    R.data[:] = 1.0
+    uf = torch.randn(U, d, generator=g, dtype=torch.float64, requires_grad=True)
+    itf = torch.randn(I, d, generator=g, dtype=torch.float64, requires_grad=True)
+    users = torch.randperm(U, generator=g)[:B].tolist()
+    go = torch.randn(B, I, generator=g, dtype=torch.float64)
+    R64 = R.astype(np.float64)
+    out = GO.u_sim(users, uf, itf, R64, batch_size=16)
+    wu, wi = torch.autograd.grad((out * go).sum(), [uf, itf])
+    du_rows, di = GO.u_sim_backward(users, uf.detach(), itf.detach(), R64, go)
+    assert rel_err(du_rows, wu[users]) < 1e-10 and rel_err(di, wi) < 1e-10
