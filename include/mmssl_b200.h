@@ -244,6 +244,59 @@ int mmssl_eval_rank(const float* user_emb, int64_t ldu, const float* item_emb, i
                     void* stream);
 int mmssl_eval_reduce(const double* per_user, int64_t n_eval, int n_metrics, double* result, void* stream);
 
+/* ------------------------------------------------------------------ GAN side (SURVEY 8f "next" #2), see csrc/gan.cu
+ * Device ops sequenced by mmssl_b200/gan.py; the Discriminator of Models.py:224-245 on n rows (LeakyReLU(True) is the
+ * identity and does not appear), gradient_penalty main.py:140-160, u_sim_calculation main.py:283-298, the real rows of
+ * main.py:348-351.  All matrices fp32 row-major and CONTIGUOUS ([n][h]); h need not be a multiple of 4.
+ * Specification of every op: the function of the same name in tests/gan_ops_cpu.py.
+ *   bn_fwd      training-mode BatchNorm1d of (a + bias) then the dropout mask: h_out, ah (normalised), rstd; running stats
+ *               updated in place (momentum 0.1, unbiased variance)
+ *   bn_bwd      dy = dh*mask, dgamma, dbeta, da (gradient w.r.t. the Linear output in front)
+ *   gp_rev_bn   adjoint of bn_bwd seeded with q = adjoint(da): adjoint(dh), adjoint(ah), adjoint(rstd), gamma gradient
+ *   bn_fwd_rev  adjoint of bn_fwd given adjoint(h) and the extra adjoints of ah / rstd: adjoint(a), gamma / beta gradients
+ *   head_fwd    s = sigmoid(h2 . w3 + b3), s_sum = sum(s)            (D output = 100 s)
+ *   head_bwd    backward of sum(coef * 100 s): dh2, dz, dw3, db3
+ *   gp_rows     gp = lam * mean_i (||gx_i|| - 1)^2 and gbar = d gp / d gx      (sq_scratch: n floats)
+ *   gp_head_rev adjoint of head_bwd + head_fwd: adjoint(h2) of the forward, w3 / b3 gradients (z_bar_scratch: n floats)
+ *   usim_finish y = rows of `scores` with the user's training items (CSR, int64) zeroed, L2-normalised; nrm = the norms
+ *   usim_bwd_pre d_raw = (g - y <g,y>) / nrm, zero at the training items
+ *   real_rows   normalize(softmax(R_row - log_log_scale * log(-log(u + 1e-8) + 1e-8) / tau) + pre_scale * ui_sim) */
+int mmssl_gan_bn_fwd(const float* a, const float* bias, const float* gamma, const float* beta, const float* mask,
+                     float* running_mean, float* running_var, int64_t n, int64_t h, float* h_out, float* ah, float* rstd,
+                     void* stream);
+int mmssl_gan_bn_bwd(const float* dh, const float* mask, const float* gamma, const float* ah, const float* rstd, int64_t n,
+                     int64_t h, float* da, float* dy, float* dgamma, float* dbeta, void* stream);
+int mmssl_gan_gp_rev_bn(const float* q, const float* dy, const float* ah, const float* rstd, const float* gamma,
+                        const float* mask, int64_t n, int64_t h, float* dh_bar, float* ah_bar, float* r_bar, float* g_gamma,
+                        void* stream);
+int mmssl_gan_bn_fwd_rev(const float* h_bar, const float* mask, const float* gamma, const float* ah, const float* rstd,
+                         const float* ah_bar, const float* r_bar, int64_t n, int64_t h, float* a_bar, float* g_gamma,
+                         float* g_beta, void* stream);
+int mmssl_gan_colsum(const float* x, int64_t n, int64_t h, float* out, void* stream);
+int mmssl_gan_head_fwd(const float* h2, const float* w3, const float* b3, int64_t n, int64_t h, float* s, float* s_sum,
+                       void* stream);
+int mmssl_gan_head_bwd(const float* s, float coef, const float* w3, const float* h2, int64_t n, int64_t h, float* dh2,
+                       float* dz, float* dw3, float* db3, void* stream);
+int mmssl_gan_gp_rows(const float* gx, int64_t n, int64_t w, float lam, float* gbar, float* sq_scratch, float* gp,
+                      void* stream);
+int mmssl_gan_gp_head_rev(const float* dh2_bar, const float* dz, const float* s, const float* w3, const float* h2,
+                          int64_t n, int64_t h, float* z_bar_scratch, float* h_bar, float* g_w3, float* g_b3, void* stream);
+int mmssl_gan_usim_finish(const float* scores, const int64_t* users, const int64_t* indptr, const int64_t* indices,
+                          int64_t rows, int64_t w, float* y, float* nrm, void* stream);
+int mmssl_gan_usim_bwd_pre(const float* g, const float* y, const float* nrm, const int64_t* users, const int64_t* indptr,
+                           const int64_t* indices, int64_t rows, int64_t w, float* d_raw, void* stream);
+int mmssl_gan_real_rows(const int64_t* users, const int64_t* indptr, const int64_t* indices, const float* uniform,
+                        const float* ui_sim, int64_t rows, int64_t w, float log_log_scale, float tau, float pre_scale,
+                        float* out, void* stream);
+/* out = alpha[row] * xr + (1 - alpha[row]) * xf ;  acc += alpha * x (flat) ;  row gather / atomic row scatter-add */
+int mmssl_gan_interpolate(const float* alpha, const float* xr, const float* xf, int64_t rows, int64_t w, float* out,
+                          void* stream);
+int mmssl_gan_add_scaled(float* acc, const float* x, float alpha, int64_t total, void* stream);
+int mmssl_gan_gather_rows(const float* table, int64_t ld, const int64_t* rows, int64_t n_rows, int d, float* out,
+                          void* stream);
+int mmssl_gan_scatter_add_rows(float* table, int64_t ld, const int64_t* rows, int64_t n_rows, int d, const float* src,
+                               void* stream);
+
 /* ------------------------------------------------------------------ projection (tcgen05 + TMA), see proj_tc.cu */
 int mmssl_split_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo, int64_t ldo,
                      void* stream);

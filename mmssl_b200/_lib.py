@@ -88,6 +88,22 @@ _SIGS = {
     "mmssl_eval_rank": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, C.POINTER(c_i32), c_i32,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mmssl_eval_reduce": (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),
+    "mmssl_gan_bn_fwd": (C.c_int, [c_vp] * 7 + [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "mmssl_gan_bn_bwd": (C.c_int, [c_vp] * 5 + [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mmssl_gan_gp_rev_bn": (C.c_int, [c_vp] * 6 + [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mmssl_gan_bn_fwd_rev": (C.c_int, [c_vp] * 7 + [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "mmssl_gan_colsum": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "mmssl_gan_head_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "mmssl_gan_head_bwd": (C.c_int, [c_vp, c_f32, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mmssl_gan_gp_rows": (C.c_int, [c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "mmssl_gan_gp_head_rev": (C.c_int, [c_vp] * 5 + [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mmssl_gan_usim_finish": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "mmssl_gan_usim_bwd_pre": (C.c_int, [c_vp] * 6 + [c_i64, c_i64, c_vp, c_vp]),
+    "mmssl_gan_real_rows": (C.c_int, [c_vp] * 5 + [c_i64, c_i64, c_f32, c_f32, c_f32, c_vp, c_vp]),
+    "mmssl_gan_interpolate": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "mmssl_gan_add_scaled": (C.c_int, [c_vp, c_vp, c_f32, c_i64, c_vp]),
+    "mmssl_gan_gather_rows": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp]),
+    "mmssl_gan_scatter_add_rows": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "mmssl_split_bf16": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "mmssl_split_bf16_t": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "mmssl_gemm_bf16x3_workspace_floats": (c_i64, [c_i64, c_i64, c_i64, C.POINTER(c_i32)]),
@@ -109,6 +125,10 @@ KERNELS_PER_CALL = {
     "mmssl_step_tick": 1, "mmssl_dp_fused_adamw": 1, "mmssl_sampler_init": 1, "mmssl_sample_triples": 1, "mmssl_adamw": 1, "mmssl_split_bf16": 1, "mmssl_split_bf16_t": 1, "mmssl_gemm_bf16x3": 1,
     "mmssl_proj_epilogue": 1, "mmssl_wgrad_epilogue": 1, "mmssl_colsum": 1,
     "mmssl_eval_rank": 1, "mmssl_eval_reduce": 1,
+    "mmssl_gan_bn_fwd": 1, "mmssl_gan_bn_bwd": 1, "mmssl_gan_gp_rev_bn": 1, "mmssl_gan_bn_fwd_rev": 1, "mmssl_gan_colsum": 1,
+    "mmssl_gan_head_fwd": 2, "mmssl_gan_head_bwd": 1, "mmssl_gan_gp_rows": 2, "mmssl_gan_gp_head_rev": 2, "mmssl_gan_usim_finish": 1,
+    "mmssl_gan_usim_bwd_pre": 1, "mmssl_gan_real_rows": 1, "mmssl_gan_interpolate": 1, "mmssl_gan_add_scaled": 1,
+    "mmssl_gan_gather_rows": 1, "mmssl_gan_scatter_add_rows": 1,
 }
 launch_count = 0
 call_log = None   # set to a list to record (name) of every kernel-launching call
