@@ -1,0 +1,61 @@
+"""Run the product's Python binding (mmssl_b200/_lib.py and the modules above it) against the host-emulated library
+(tests/cuemu/_build/libmmssl_emu.so) -- TEST INFRASTRUCTURE ONLY.
+
+``emulated_device(monkeypatch)`` makes, for the duration of one test:
+  * ``_lib.load()`` return the emulated library (same C ABI, same ctypes signatures, host pointers as "device" pointers);
+  * ``tensor.cuda()`` / ``.to("cuda")`` the identity, ``tensor.is_cuda`` true, ``torch.cuda.synchronize`` a no-op,
+    the stream argument NULL.
+The bodies of the ``-m gpu`` tests can then be executed unchanged on the CPU: same wrappers, same argument marshalling,
+same kernels (compiled from the same .cu sources), CUDA's block / warp semantics provided by the fiber emulator.
+The patches are undone by ``monkeypatch``; nothing under mmssl_b200/ knows about this."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+from . import build as _build
+
+_EMU = None
+
+
+def emu_lib():
+    global _EMU
+    if _EMU is None:
+        from mmssl_b200 import _lib
+        lib = C.CDLL(_build.build())
+        have = []
+        for name, (res, args) in _lib._SIGS.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                continue                      # entry points of files the emulator cannot compile (CUB, TMA, tcgen05)
+            fn.restype, fn.argtypes = res, args
+            have.append(name)
+        lib._emulated = tuple(have)
+        _EMU = lib
+    return _EMU
+
+
+def set_order(order: str) -> None:
+    """fwd | rev | shuffle:<seed> -- the order in which the fibers of a block get the CPU."""
+    os.environ["CUEMU_ORDER"] = order
+
+
+def emulated_device(monkeypatch):
+    from mmssl_b200 import _lib
+    lib = emu_lib()
+    # a failed launch leaves a sticky error in the emulator, like CUDA: clear it between tests
+    clear = getattr(lib, "cuemu_clear_error", None)
+    if clear is not None:
+        clear()
+    monkeypatch.setattr(_lib, "load", lambda require_device=False: lib)
+    monkeypatch.setattr(_lib, "_lib", lib)
+    null_stream = lambda: C.c_void_p(0)
+    for name, mod in list(sys.modules.items()):
+        if name.startswith("mmssl_b200") and mod is not None and hasattr(mod, "stream"):
+            monkeypatch.setattr(mod, "stream", null_stream)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    return lib

@@ -1,0 +1,37 @@
+"""The GAN-side kernels (csrc/gan.cu) executed on the CPU by the cuemu fiber emulator (tests/cuemu), through the
+product's own Python binding, against their specification -- the bodies of tests/test_gpu_zz_gan.py, unchanged.
+This is what stands in for a GPU run while the container has none: barriers, shuffles, indexing, reduction order and
+the ctypes marshalling are the real ones; see tests/cuemu/include/cuemu.h for what the emulator does not cover."""
+import pytest
+
+from tests import test_gpu_zz_gan as G
+from tests.cuemu import harness
+
+
+@pytest.fixture(params=["fwd", "rev"])
+def emu(request, monkeypatch):
+    harness.set_order(request.param)
+    return harness.emulated_device(monkeypatch)
+
+
+@pytest.mark.parametrize("n,h", [(64, 24), (50, 33), (130, 70)])
+def test_bn_ops(emu, n, h):
+    G.test_bn_ops(n, h)
+
+
+@pytest.mark.parametrize("n,h", [(64, 12), (37, 5), (300, 40)])
+def test_head_ops(emu, n, h):
+    G.test_head_ops(n, h)
+
+
+@pytest.mark.parametrize("n,w", [(64, 96), (9, 700)])
+def test_gp_rows_interpolate_and_axpy(emu, n, w):
+    G.test_gp_rows_interpolate_and_axpy(n, w)
+
+
+def test_usim_and_real_rows(emu):
+    G.test_usim_and_real_rows(120, 96, 32, 64)
+
+
+def test_d_step_matches_reference_trace(emu):
+    G.test_d_step_on_gpu_matches_reference_trace()
