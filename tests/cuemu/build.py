@@ -5,7 +5,8 @@ The sources are mmssl_b200/csrc/*.cu, untouched except for three pieces of synta
   kernel<<<grid, block, smem, stream>>>(args)   ->  cuemu::launch(kernel, cuemu::cfg(grid, block, smem, stream), "kernel")(args)
   extern __shared__ [__align__(n)] T name[];    ->  T* name = (T*)cuemu::dyn_smem();
   asm volatile("ptx" : ... );                   ->  cuemu::ptx("ptx");     (fails the launch, except griddepcontrol.wait)
-Files that need CUB, TMA or tcgen05 are left out (graph.cu, proj_*.cu, spmm_hot.cu).
+CUB's SortPairs / ExclusiveSum are host shims (include/cub/cub.cuh).  Files that need TMA or tcgen05 are left out
+(proj_*.cu, spmm_hot.cu).
 
     python -m tests.cuemu.build [--force]
 """
@@ -21,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "mmssl_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libmmssl_emu.so")
-SOURCES = ["core.cu", "gan.cu", "eval.cu", "sgemm.cu", "adamw.cu", "rowops.cu", "loss.cu", "idfuse.cu", "sampler.cu", "spmm.cu"]
+SOURCES = ["core.cu", "gan.cu", "eval.cu", "sgemm.cu", "adamw.cu", "rowops.cu", "loss.cu", "idfuse.cu", "sampler.cu", "spmm.cu", "graph.cu"]
 HEADERS = ["common.cuh", "spmm_common.cuh"]
 CXX = os.environ.get("CXX", "g++")
 FLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-fno-strict-aliasing", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",

@@ -56,7 +56,12 @@ struct Bar {
 struct Warp {
     uint64_t slot[32];
     unsigned exist = 0, exited = 0;
-    Bar bar[32];                 // keyed by the lowest lane of the mask
+    // One barrier per distinct membermask, like the hardware: lanes 0-15 may run shuffles under mask 0x0000ffff while
+    // lanes 16-31 already wait in a full-mask shuffle further down the program.
+    static constexpr int kMaxMasks = 96;
+    int n_bars = 0;
+    unsigned bar_mask[kMaxMasks];
+    Bar bar[kMaxMasks];
 };
 
 std::string g_err_text;
@@ -176,12 +181,13 @@ static Bar& warp_bar(unsigned mask, Warp** wout) {
     Fiber* f = cur;
     Warp& w = g_warps[f->warp];
     if (!((mask >> f->lane) & 1u)) fail("warp primitive called by a lane that is not in its own mask");
-    const int leader = __builtin_ctz(mask);
-    Bar& b = w.bar[leader];
-    if (b.arrived == 0) b.mask = mask;
-    else if (b.mask != mask) fail("lanes meet in one warp primitive with different masks");
     *wout = &w;
-    return b;
+    for (int i = 0; i < w.n_bars; ++i)
+        if (w.bar_mask[i] == mask) return w.bar[i];
+    if (w.n_bars == Warp::kMaxMasks) fail("too many distinct warp masks in one block");
+    w.bar_mask[w.n_bars] = mask;
+    w.bar[w.n_bars] = Bar();
+    return w.bar[w.n_bars++];
 }
 
 static void warp_arrive_wait(unsigned mask) {

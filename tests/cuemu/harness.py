@@ -3,7 +3,7 @@
 
 ``emulated_device(monkeypatch)`` makes, for the duration of one test:
   * ``_lib.load()`` return the emulated library (same C ABI, same ctypes signatures, host pointers as "device" pointers);
-  * ``tensor.cuda()`` / ``.to("cuda")`` the identity, ``tensor.is_cuda`` true, ``torch.cuda.synchronize`` a no-op,
+  * ``tensor.cuda()`` a plain copy, ``tensor.is_cuda`` true, ``torch.cuda.synchronize`` a no-op,
     the stream argument NULL.
 The bodies of the ``-m gpu`` tests can then be executed unchanged on the CPU: same wrappers, same argument marshalling,
 same kernels (compiled from the same .cu sources), CUDA's block / warp semantics provided by the fiber emulator.
@@ -42,6 +42,16 @@ def set_order(order: str) -> None:
     os.environ["CUEMU_ORDER"] = order
 
 
+def _on_cpu(fn):
+    """torch factory with ``device="cuda"`` rewritten to the CPU (the tests' inputs are created on the 'device')."""
+    def wrapped(*a, **k):
+        if "device" in k and k["device"] is not None and str(k["device"]).startswith("cuda"):
+            k["device"] = "cpu"
+        return fn(*a, **k)
+    wrapped.__name__ = getattr(fn, "__name__", "factory")
+    return wrapped
+
+
 def emulated_device(monkeypatch):
     from mmssl_b200 import _lib
     lib = emu_lib()
@@ -55,7 +65,18 @@ def emulated_device(monkeypatch):
     for name, mod in list(sys.modules.items()):
         if name.startswith("mmssl_b200") and mod is not None and hasattr(mod, "stream"):
             monkeypatch.setattr(mod, "stream", null_stream)
-    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self.clone())   # a copy, like a real host->device transfer
+    real_to = torch.Tensor.to
+
+    def to(self, *a, **k):
+        is_cuda = lambda d: isinstance(d, (str, torch.device)) and str(d).startswith("cuda")
+        a = tuple("cpu" if is_cuda(x) else x for x in a)
+        if is_cuda(k.get("device")):
+            k["device"] = "cpu"
+        return real_to(self, *a, **k)
+    monkeypatch.setattr(torch.Tensor, "to", to)
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    for fname in ("randn", "rand", "randint", "zeros", "ones", "empty", "full", "tensor", "arange", "as_tensor", "randperm"):
+        monkeypatch.setattr(torch, fname, _on_cpu(getattr(torch, fname)))
     return lib

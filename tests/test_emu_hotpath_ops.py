@@ -1,0 +1,67 @@
+"""Kernels of the hot path that are already parity-green on a real B200 (tests/test_gpu_ops.py), executed on the CPU by
+the cuemu fiber emulator through the same bodies.  Two purposes: (1) cross-check the emulator itself against kernels
+whose GPU behaviour is known -- warp-group shuffles, block reductions, 128-bit vector atomics, last-arriver counters;
+(2) keep these kernels under test in the `-m "not gpu"` suite, which runs where there is no GPU."""
+import pytest
+
+from tests import test_gpu_ops as T
+from tests.cuemu import harness
+
+
+@pytest.fixture(params=["fwd", "rev"])
+def emu(request, monkeypatch):
+    harness.set_order(request.param)
+    return harness.emulated_device(monkeypatch)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, True)])
+def test_sgemm(emu, ta, tb):
+    T.test_sgemm(ta, tb)
+
+
+@pytest.mark.parametrize("d", [64, 128, 256])
+def test_rowops(emu, d):
+    T.test_rowops_vs_autograd(d)
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_bpr(emu, d):
+    T.test_bpr_fused_and_autograd(d)
+
+
+@pytest.mark.parametrize("n,d", [(64, 64), (257, 64), (130, 128), (96, 256)])
+def test_infonce(emu, n, d):
+    T.test_infonce_forward_backward(n, d)
+
+
+def test_feat_reg_and_adamw(emu):
+    T.test_feat_reg_autograd()
+    T.test_adamw_matches_torch()
+
+
+def test_sampler(emu):
+    T.test_device_triple_sampler_semantics()
+
+
+@pytest.mark.parametrize("shape_nnz", [((50, 70), 400), ((1, 1), 1), ((300, 200), 0), ((2000, 900), 60000)])
+def test_csr_from_coo(emu, shape_nnz):
+    T.test_csr_from_coo(shape_nnz)
+
+
+def test_row_normalize(emu):
+    T.test_row_normalize_matches_reference_formula()
+
+
+@pytest.mark.parametrize("d,nrhs", [(64, 1), (64, 3), (128, 2), (256, 1)])
+def test_spmm_plain(emu, d, nrhs):
+    T.test_spmm_plain(d, nrhs)
+
+
+@pytest.mark.parametrize("impl,nrhs", [(2, 1), (4, 3), (6, 1)])
+def test_spmm_impl_variants(emu, impl, nrhs):
+    T.test_spmm_impl_variants(impl, nrhs)
+
+
+def test_spmm_empty_and_epilogues(emu):
+    T.test_spmm_empty_and_tiny()
+    T.test_spmm_epilogues(64)
