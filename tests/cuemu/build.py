@@ -6,7 +6,8 @@ The sources are mmssl_b200/csrc/*.cu, untouched except for three pieces of synta
   extern __shared__ [__align__(n)] T name[];    ->  T* name = (T*)cuemu::dyn_smem();
   asm volatile("ptx" : ... );                   ->  cuemu::ptx("ptx");     (fails the launch, except griddepcontrol.wait)
 CUB's SortPairs / ExclusiveSum are host shims (include/cub/cub.cuh).  Files that need TMA or tcgen05 are left out
-(proj_*.cu, spmm_hot.cu).
+(proj_tc.cu, spmm_hot.cu); the
+tcgen05 GEMM entry points are provided by a host statement of their contract (gemm_bf16x3_host.cpp).
 
     python -m tests.cuemu.build [--force]
 """
@@ -22,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "mmssl_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libmmssl_emu.so")
-SOURCES = ["core.cu", "gan.cu", "eval.cu", "sgemm.cu", "adamw.cu", "rowops.cu", "loss.cu", "idfuse.cu", "sampler.cu", "spmm.cu", "graph.cu"]
+SOURCES = ["core.cu", "gan.cu", "eval.cu", "sgemm.cu", "adamw.cu", "rowops.cu", "loss.cu", "idfuse.cu", "sampler.cu", "spmm.cu", "graph.cu", "proj_common.cu"]
 HEADERS = ["common.cuh", "spmm_common.cuh"]
 CXX = os.environ.get("CXX", "g++")
 FLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-fno-strict-aliasing", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",
@@ -76,7 +77,7 @@ def transform(src: str) -> str:
 
 def _digest() -> str:
     h = hashlib.sha1()
-    files = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, "cuemu.cpp"), os.path.join(HERE, "selftest.cu"), os.path.join(HERE, "include", "cuemu.h"),
+    files = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, "cuemu.cpp"), os.path.join(HERE, "selftest.cu"), os.path.join(HERE, "gemm_bf16x3_host.cpp"), os.path.join(HERE, "include", "cuemu.h"),
                                                                    os.path.join(ROOT, "include", "mmssl_b200.h"), __file__]
     for p in files:
         with open(p, "rb") as f:
@@ -113,6 +114,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with open(os.path.join(HERE, "selftest.cu")) as f, open(dst, "w") as g:
         g.write(transform(f.read()))
     jobs.append((dst, dst[:-4] + ".o"))
+    jobs.append((os.path.join(HERE, "gemm_bf16x3_host.cpp"), os.path.join(OUT, "gemm_bf16x3_host.o")))
     jobs.append((os.path.join(HERE, "cuemu.cpp"), os.path.join(OUT, "cuemu.o")))
     with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
         warns = list(ex.map(lambda j: _compile(*j), jobs))

@@ -8,6 +8,7 @@
 The bodies of the ``-m gpu`` tests can then be executed unchanged on the CPU: same wrappers, same argument marshalling,
 same kernels (compiled from the same .cu sources), CUDA's block / warp semantics provided by the fiber emulator.
 The patches are undone by ``monkeypatch``; nothing under mmssl_b200/ knows about this."""
+import contextlib
 import ctypes as C
 import os
 import sys
@@ -40,6 +41,20 @@ def emu_lib():
 def set_order(order: str) -> None:
     """fwd | rev | shuffle:<seed> -- the order in which the fibers of a block get the CPU."""
     os.environ["CUEMU_ORDER"] = order
+
+
+class _NullStream:
+    """torch.cuda.Stream stand-in: the emulator executes every launch synchronously, in program order."""
+    cuda_stream = 0
+
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+    def synchronize(self):
+        pass
 
 
 def _on_cpu(fn):
@@ -77,6 +92,9 @@ def emulated_device(monkeypatch):
     monkeypatch.setattr(torch.Tensor, "to", to)
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "Stream", _NullStream)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _NullStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     for fname in ("randn", "rand", "randint", "zeros", "ones", "empty", "full", "tensor", "arange", "as_tensor", "randperm"):
         monkeypatch.setattr(torch, fname, _on_cpu(getattr(torch, fname)))
     return lib

@@ -1,18 +1,16 @@
 """Parity of the device evaluation path (mmssl_eval_rank / mmssl_eval_reduce) with the oracle and
 the golden vectors minted from the reference's batch_test.py.
 
-NOT YET RUN ON A GPU: the kernel was written after round 1's GPU budget was spent; its algorithm is checked on the
-CPU through an executable model (tests/eval_kernel_model.py, tests/test_oracle_golden.py).  Until the first GPU run
-these tests only execute with MMSSL_RUN_UNVALIDATED=1 (first task of round 2); remove the gate once green."""
+The kernel was written after round 1's GPU budget was spent.  Before its first GPU run these same test bodies were
+executed on the CPU against the same kernel source under the cuemu fiber emulator (tests/test_emu_eval.py, incl. the
+Baby-size case below once); the selection algorithm also has an executable model (tests/eval_kernel_model.py)."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MMSSL_RUN_UNVALIDATED") != "1",
-                                 reason="eval kernel not yet validated on a GPU (set MMSSL_RUN_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
