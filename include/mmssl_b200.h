@@ -297,6 +297,18 @@ int mmssl_gan_gather_rows(const float* table, int64_t ld, const int64_t* rows, i
 int mmssl_gan_scatter_add_rows(float* table, int64_t ld, const int64_t* rows, int64_t n_rows, int d, const float* src,
                                void* stream);
 
+/* ------------------------------------------------------------------ modality-graph bookkeeping of the full step (regraph.cu)
+ * mmssl_topk_rows: ids[rows, k] (int64) = columns of the k largest entries of every row of x[rows, w], best first, equal
+ *   values keep the lower column first -- torch.topk(G_*_u_sim_detach, int(n_items * m_topk_rate)) at main.py:397,400.
+ * mmssl_pair_append: x[j] = users[j % batch], y[j] = ids.flat[j] for j < batch * k -- the python lists of main.py:398-402
+ *   (the x list tiles the user vector k times, the y list is row-major: the reference's pairing, kept).
+ * mmssl_degree_values: vals[j] = (deg(idx[j]) + 1e-8)^-1/2 with deg = number of entries carrying the same index --
+ *   csr_norm(mean_flag=True) (main.py:89-103) applied to the 0/1 (duplicates summed) matrix of main.py:379-391, per COO
+ *   entry; deg_scratch holds n_rows int32. */
+int mmssl_topk_rows(const float* x, int64_t ldx, int64_t rows, int64_t w, int k, int64_t* ids, void* stream);
+int mmssl_pair_append(const int64_t* users, int64_t batch, const int64_t* ids, int k, int64_t* x, int64_t* y, void* stream);
+int mmssl_degree_values(const int64_t* idx, int64_t n, int64_t n_rows, int32_t* deg_scratch, float* vals, void* stream);
+
 /* ------------------------------------------------------------------ projection (tcgen05 + TMA), see proj_tc.cu */
 int mmssl_split_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo, int64_t ldo,
                      void* stream);

@@ -45,7 +45,7 @@ class HotStepConfig:
 
 class HotStep:
     def __init__(self, params: Dict[str, torch.Tensor], feats: Sequence[FeatureStore], graphs: Sequence[BipartiteGraph],
-                 cfg: HotStepConfig, batch: int, optimizer_step: bool = True, sampler=None):
+                 cfg: HotStepConfig, batch: int, optimizer_step: bool = True, sampler=None, allow_alias: bool = True):
         self.cfg = cfg
         self.P = {k: params[k] for k in LIVE}
         for k, t in self.P.items():
@@ -57,11 +57,16 @@ class HotStep:
         self.optimizer_step = optimizer_step
         self.sampler = sampler          # optional sampler.DeviceTripleSampler: batches are drawn on the device
         self.grad_sync = None           # optional callable run between backward and AdamW (data-parallel all-reduce)
+        # optional callable(outs, st) -> (g_Iv, g_It, g_Uv, g_Ut): extra output gradients of the forward, e.g. the
+        # G_rate * G_lossf term of the full step (main.py:414-420); runs after the loss kernels, before the backward
+        self.post_forward = None
         dev = self.P[P_EU].device
         d = cfg.embed_size
         f = dict(dtype=torch.float32, device=dev)
         self.idx = torch.zeros(3, batch, dtype=torch.int64, device=dev)     # users / pos / neg (static input)
-        self.alias_id = graphs[2] is graphs[4]
+        # image and text graphs are the same object at step 0 (main.py:68-69): one InfoNCE instead of two.  The full
+        # step (fullstep.py) replaces them by distinct top-k graphs later, so it asks for the general layout up front.
+        self.alias_id = allow_alias and graphs[2] is graphs[4]
         # gradient seeds of the loss kernels: one contiguous buffer -> one memset per step
         n_u = 2 if self.alias_id else 3
         self.gflat = torch.zeros((n_u * self.U + self.I) * d, **f)
@@ -127,7 +132,8 @@ class HotStep:
         nce2 = parts[0] if self.alias_id else parts[1]
         ops.loss_assemble(bpr_part, n_bpr, self.batch, reg_coef, st.sumsq_u, st.sumsq_i, 0.5 * cfg.feat_reg_decay / self.I,
                           nce1, nce2, self.batch, cfg.cl_rate, self.out5)
-        grads = [self.g_uf, self.g_if, None, None, None, None,
+        extra = self.post_forward(outs, st) if self.post_forward is not None else (None, None, None, None)
+        grads = [self.g_uf, self.g_if, extra[0], extra[1], extra[2], extra[3],
                  self.g_uvid if st.fused else None, (None if self.alias_id else self.g_utid) if st.fused else None, None, None]
         self.engine.backward(st, self.P, self.feats, grads, feat_reg_coef=cfg.feat_reg_decay / self.I, out=self.grads)
         if self.grad_sync is not None:

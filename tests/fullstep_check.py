@@ -1,0 +1,83 @@
+"""Shared body of the full-step parity tests (GPU: tests/test_gpu_zz_fullstep.py, CPU emulation: tests/test_emu_fullstep.py):
+``mmssl_b200.fullstep.FullStep`` replayed against the 3-iteration trace recorded from the UNMODIFIED reference trainer
+(tests/golden/gan_trace.npz, minted by tests/golden/make_gan_trace.py) with every random draw injected."""
+import json
+import os
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from tests.golden_util import rel_err
+
+TOL = 1e-4                                            # north_star: 1e-4 relative fp32
+DEAD_BIAS = {"net.0.bias": "net.0.weight", "net.4.bias": "net.4.weight"}     # exactly-zero gradients (bias before BatchNorm)
+
+
+def load_trace():
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "gan_trace.npz"))
+    return z, json.loads(str(z["cfg"]))
+
+
+def build(z, c, dev, proj_impl="tc"):
+    from mmssl_b200 import gan
+    from mmssl_b200.engine import FeatureStore
+    from mmssl_b200.fullstep import FullStep, FullStepConfig
+    from mmssl_b200.graph import BipartiteGraph
+    from mmssl_b200.hotstep import HotStepConfig
+    from mmssl_b200.synthetic import csr_norm
+    t = lambda a: torch.from_numpy(np.asarray(a)).clone().to(dev)
+    R = sp.csr_matrix((np.ones(len(z["train_rows"]), np.float32), (z["train_rows"], z["train_cols"])), shape=(c["U"], c["I"]))
+    R.sort_indices()
+    hot = HotStepConfig(embed_size=c["d"], n_layers=c["n_layers"], head_num=c["head_num"], id_cat_rate=c["id_cat_rate"],
+                        model_cat_rate=c["model_cat_rate"], drop_rate=c["drop_rate"], tau=c["tau"], cl_rate=c["cl_rate"],
+                        emb_decay=c["emb_decay"], feat_reg_decay=c["feat_reg_decay"], batch_size=c["B"], lr=c["lr"], proj_impl=proj_impl)
+    hp = gan.GanHyper(gp_rate=c["gp_rate"], G_rate=c["G_rate"], D_lr=c["D_lr"], log_log_scale=c["log_log_scale"],
+                      real_data_tau=c["real_data_tau"], ui_pre_scale=c["ui_pre_scale"])
+    cfg = FullStepConfig(hot=hot, gan=hp, m_topk_rate=c["m_topk_rate"], T=c["T"], G_drop1=c["G_drop1"], G_drop2=c["G_drop2"])
+    P = {k[3:]: t(z[k]).contiguous() for k in z.files if k.startswith("G0/")}
+    S = {k[3:]: t(z[k]) for k in z.files if k.startswith("D0/")}
+    feats = (FeatureStore(t(z["image_feats"])), FeatureStore(t(z["text_feats"])))
+    ui = BipartiteGraph.from_scipy(csr_norm(R), device=dev)
+    iu = BipartiteGraph.from_scipy(csr_norm(R.T.tocsr()), device=dev)
+    fs = FullStep(P, S, feats, t(R.indptr.astype(np.int64)), t(R.indices.astype(np.int64)), ui, iu, cfg, batch=c["B"])
+    return fs, P, t
+
+
+def run_and_check(dev="cuda", proj_impl="tc", steps=None):
+    from mmssl_b200 import gan
+    from mmssl_b200.engine import LIVE
+    z, c = load_trace()
+    fs, P, t = build(z, c, dev, proj_impl)
+    n_steps = c["steps"] if steps is None else steps
+    for s in range(n_steps):
+        users, pos, neg = (t(z["sample"][s][j]) for j in range(3))
+        out = fs.step(users, pos, neg,
+                      model_masks=[t(z["mask_model"][4 * s + j]) for j in range(4)],
+                      d_masks1=[t(z["mask_d1"][4 * s + j]) for j in range(4)],
+                      d_masks2=[t(z["mask_d2"][4 * s + j]) for j in range(4)],
+                      gumbel_u=t(z["gumbel_u"][s]), alpha=t(z["alpha"][s]).view(-1))
+        # the five u_sim calls of the iteration, in the reference's order
+        sims = list(fs.last["D_u_sim"]) + list(fs.last["G_u_sim"])
+        for j, got in enumerate(sims):
+            assert rel_err(got, torch.from_numpy(z["u_sim"][5 * s + j])) < TOL, (s, "u_sim", j)
+        # Discriminator: penalty, gradients, state after Adam
+        assert abs(float(out["gp"]) - float(z["gp"][s])) <= 2e-4 * abs(float(z["gp"][s])), (s, "gp")
+        for k in gan.PARAMS:
+            want = torch.from_numpy(z["Dgrad/" + k][s])
+            got = out["D_grads"][k].cpu().view_as(want)
+            if k in DEAD_BIAS:
+                assert float(got.abs().max()) < 1e-5 * float(np.abs(z["Dgrad/" + DEAD_BIAS[k]][s]).max()), (s, k)
+            else:
+                assert rel_err(got, want) < 5e-4, (s, k, rel_err(got, want))
+        for k in gan.PARAMS:
+            if k not in DEAD_BIAS:
+                assert rel_err(fs.D.t[k], torch.from_numpy(z["Dstate/" + k][s])) < 5e-4, (s, "Dstate", k)
+        # generator: gradients of batch_loss (main.py:420) and parameters after AdamW
+        for k in LIVE:
+            e = rel_err(fs.hs.grads[k], torch.from_numpy(z["Ggrad/" + k][s]))
+            assert e < TOL, (s, "Ggrad", k, e)
+        for k in LIVE:
+            e = rel_err(P[k], torch.from_numpy(z["Gparam/" + k][s]))
+            assert e < TOL, (s, "Gparam", k, e)
+    return fs

@@ -1,0 +1,39 @@
+"""The whole training iteration of the reference (D step, G step with the G_rate * G_lossf term, both optimisers, top-k
+graph rebuilds) executed by the product's FullStep on the CPU under the cuemu emulator, against the trace recorded from
+the unmodified reference trainer.  Same body as the GPU test (tests/fullstep_check.py)."""
+import pytest
+
+from tests import fullstep_check
+from tests.cuemu import harness
+
+
+@pytest.mark.parametrize("proj_impl", ["tc", "simt"])
+def test_full_step_matches_reference_trace(monkeypatch, proj_impl):
+    harness.set_order("fwd")
+    harness.emulated_device(monkeypatch)
+    fs = fullstep_check.run_and_check(dev="cpu", proj_impl=proj_impl)
+    # T = 1: iteration 0 collected pairs, iteration 1 built graphs from them, iteration 2 rebuilt from empty lists
+    assert fs.idx == 3 and fs.hs.graphs[2].nnz == 0 and fs.hs.graphs[4].nnz == 0
+
+
+@pytest.fixture(params=["fwd", "rev"])
+def emu(request, monkeypatch):
+    harness.set_order(request.param)
+    return harness.emulated_device(monkeypatch)
+
+
+@pytest.mark.parametrize("rows,w,k", [(32, 96, 4), (5, 7050, 1), (64, 1000, 17), (3, 40, 40), (7, 300, 0)])
+def test_topk_rows_and_pairs(emu, rows, w, k):
+    from tests import test_gpu_zz_fullstep as G
+    G.test_topk_rows_and_pairs(rows, w, k)
+
+
+@pytest.mark.parametrize("n_pairs", [0, 128, 5000])
+def test_graphs_from_pairs(emu, n_pairs):
+    from tests import test_gpu_zz_fullstep as G
+    G.test_graphs_from_pairs_match_csr_norm(n_pairs)
+
+
+def test_own_random_draws(emu):
+    from tests import test_gpu_zz_fullstep as G
+    G.test_full_step_own_random_draws_runs_and_learns()
