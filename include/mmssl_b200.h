@@ -321,6 +321,12 @@ int64_t mmssl_gemm_bf16x3_workspace_floats(int64_t m, int64_t n, int64_t k, int*
 int mmssl_gemm_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi,
                       const uint16_t* b_lo, int64_t ldb, int64_t m, int64_t n, int64_t k, int split_k, float* partial,
                       void* stream);
+/* General-width variant for the GAN side (gemm_wide.cu): c[m][ldc] = alpha * (Ahi+Alo)[m,k] * (Bhi+Blo)[n,k]^T (+ c when
+ * accumulate != 0), any n >= 1, no split-K, alpha / accumulate applied in the epilogue; replaces the Discriminator's
+ * nn.Linear products and their closed-form backward / gradient-penalty variants (Models.py:224-245, main.py:140-160). */
+int mmssl_gemm_bf16x3_wide(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi,
+                           const uint16_t* b_lo, int64_t ldb, int64_t m, int64_t n, int64_t k, float alpha, int accumulate,
+                           float* c, int64_t ldc, void* stream);
 /* y[m][ldy + col_off] = (sum_s partial[s][m][n] + bias[n]) * mask[m][n]     (bias / mask may be NULL) */
 int mmssl_proj_epilogue(const float* partial, int split_k, int64_t m, int64_t n, const float* bias, const float* mask,
                         int64_t ldm, float* y, int64_t ldy, float* y_pre, int64_t ldyp, void* stream);

@@ -1,11 +1,17 @@
 """CUDA backend of the GAN-side ops (csrc/gan.cu) -- the namespace ``mmssl_b200.gan`` is given as ``K`` in the product.
 One function per op of tests/gan_ops_cpu.py (its specification), same names and argument meaning; outputs are allocated
 here, every call goes through the C ABI and raises when the extension or a CUDA device is missing (no CPU fallback).
-GEMMs: ``mmssl_sgemm`` (fp32 CUDA-core path) for now; the n x I x I/4 products move to the tcgen05 bf16x3 kernel once
-this path is validated on the GPU."""
+GEMMs: ``GEMM_IMPL = "tc"`` routes every product through the general-width tcgen05 kernel (csrc/gemm_wide.cu; operands
+split into bf16 hi/lo pairs, K-major, by the same split kernels as the projection); ``"simt"`` is the fp32 CUDA-core GEMM.
+The default stays "simt" until gemm_wide.cu has passed its GPU test (it was written without GPU access); set
+``MMSSL_GAN_GEMM=tc`` or assign ``gan_ops.GEMM_IMPL``."""
 from __future__ import annotations
 
+import os
+
 import torch
+
+GEMM_IMPL = os.environ.get("MMSSL_GAN_GEMM", "simt")
 
 from . import _lib, ops
 from ._lib import ptr, stream
@@ -28,6 +34,13 @@ def mm(a, b, ta=False, tb=False, alpha=1.0):
     a, b = _c(a), _c(b)
     m = a.shape[1] if ta else a.shape[0]
     n = b.shape[0] if tb else b.shape[1]
+    if GEMM_IMPL == "tc":
+        k = a.shape[0] if ta else a.shape[1]
+        a_hi, a_lo = ops.split_bf16_t(a) if ta else ops.split_bf16(a)          # [m][ceil8(k)], K-major
+        b_hi, b_lo = ops.split_bf16(b) if tb else ops.split_bf16_t(b)          # [n][ceil8(k)], K-major
+        return ops.gemm_bf16x3_wide(a_hi, a_lo, b_hi, b_lo, m, n, k, _new(m, n, like=a), alpha=alpha)
+    if GEMM_IMPL != "simt":
+        raise ValueError("gan_ops.GEMM_IMPL must be 'tc' or 'simt'")
     return ops.sgemm(a, b, _new(m, n, like=a), trans_a=ta, trans_b=tb, alpha=alpha)
 
 

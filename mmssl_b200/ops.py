@@ -331,6 +331,15 @@ def split_bf16_t(x, mask=None, ldo=None, out=None):
     return hi, lo
 
 
+def gemm_bf16x3_wide(a_hi, a_lo, b_hi, b_lo, m, n, k, out, alpha: float = 1.0, accumulate: bool = False):
+    """out[m, n] (+)= alpha * (a_hi + a_lo)[m,k] @ (b_hi + b_lo)[n,k]^T on tcgen05 tensor cores, any n (csrc/gemm_wide.cu)."""
+    lib = _lib_()
+    assert out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (m, n)
+    _lib.check(lib.mmssl_gemm_bf16x3_wide(ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(b_hi), ptr(b_lo), b_hi.stride(0), m, n, k,
+                                          float(alpha), int(accumulate), ptr(out), out.stride(0), stream()))
+    return out
+
+
 def gemm_bf16x3_plan(m, n, k):
     lib = _lib_()
     sk = C.c_int(0)

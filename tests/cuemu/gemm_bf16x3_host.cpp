@@ -66,3 +66,32 @@ extern "C" int mmssl_gemm_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int
     }
     return 0;
 }
+
+// Contract of csrc/gemm_wide.cu:mmssl_gemm_bf16x3_wide (general n, no split-K, alpha / accumulate epilogue).
+extern "C" int mmssl_gemm_bf16x3_wide(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi, const uint16_t* b_lo,
+                                      int64_t ldb, int64_t m, int64_t n, int64_t k, float alpha, int accumulate, float* c, int64_t ldc,
+                                      void*) {
+    MMSSL_REQUIRE(m >= 1 && n >= 1 && k >= 1, "bad m / n / k");
+    MMSSL_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= k && ldb >= k, "lda/ldb must be >= k and multiples of 8 (16-byte TMA strides)");
+    MMSSL_REQUIRE(mmssl::aligned16(a_hi) && mmssl::aligned16(a_lo) && mmssl::aligned16(b_hi) && mmssl::aligned16(b_lo), "operand alignment");
+    MMSSL_REQUIRE(c != nullptr && ldc >= n, "bad output");
+    // the tensor maps cover [rows][ld]: the padding columns k..ld are READ by the kernel, so they must be zero
+    for (int64_t i = 0; i < m; ++i)
+        for (int64_t kk = k; kk < lda; ++kk) MMSSL_REQUIRE(a_hi[i * lda + kk] == 0 && a_lo[i * lda + kk] == 0, "A padding is not zero");
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t kk = k; kk < ldb; ++kk) MMSSL_REQUIRE(b_hi[j * ldb + kk] == 0 && b_lo[j * ldb + kk] == 0, "B padding is not zero");
+    for (int64_t i = 0; i < m; ++i)
+        for (int64_t j = 0; j < n; ++j) {
+            float acc = 0.f;
+            for (int64_t kk = 0; kk < k; ++kk) {
+                const float ah = bf(a_hi[i * lda + kk]), al = bf(a_lo[i * lda + kk]);
+                const float bh = bf(b_hi[j * ldb + kk]), bl = bf(b_lo[j * ldb + kk]);
+                acc += ah * bh;
+                acc += ah * bl;
+                acc += al * bh;
+            }
+            const float r = alpha * acc;
+            c[i * ldc + j] = accumulate ? c[i * ldc + j] + r : r;
+        }
+    return 0;
+}

@@ -37,3 +37,11 @@ def test_graphs_from_pairs(emu, n_pairs):
 def test_own_random_draws(emu):
     from tests import test_gpu_zz_fullstep as G
     G.test_full_step_own_random_draws_runs_and_learns()
+
+
+def test_full_step_with_tensor_core_gan_gemms(monkeypatch):
+    from mmssl_b200 import gan_ops
+    harness.set_order("fwd")
+    harness.emulated_device(monkeypatch)
+    monkeypatch.setattr(gan_ops, "GEMM_IMPL", "tc")
+    fullstep_check.run_and_check(dev="cpu", proj_impl="tc")

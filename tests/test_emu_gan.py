@@ -35,3 +35,31 @@ def test_usim_and_real_rows(emu):
 
 def test_d_step_matches_reference_trace(emu):
     G.test_d_step_on_gpu_matches_reference_trace()
+
+
+@pytest.fixture
+def tc_gemm(monkeypatch):
+    from mmssl_b200 import gan_ops
+    monkeypatch.setattr(gan_ops, "GEMM_IMPL", "tc")
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+def test_tensor_core_gemm_route_operand_layouts(emu, tc_gemm, ta, tb):
+    """gan_ops.mm through the bf16 hi/lo splits and the wide-GEMM entry point (contract stand-in on the CPU): the four
+    transpose combinations, ragged sizes (k, n not multiples of 8 / of the tiles), the alpha epilogue."""
+    import torch
+    from mmssl_b200 import gan_ops as K
+    from tests.golden_util import rel_err
+    g = torch.Generator().manual_seed(3)
+    m, n, k = 37, 45, 77
+    a = torch.randn((k, m) if ta else (m, k), generator=g)
+    b = torch.randn((n, k) if tb else (k, n), generator=g)
+    got = K.mm(a, b, ta=ta, tb=tb, alpha=-0.25)
+    A = a.double().t() if ta else a.double()
+    B = b.double().t() if tb else b.double()
+    assert rel_err(got, -0.25 * A @ B) < 2e-5
+
+
+def test_d_step_trace_with_tensor_core_gemms(emu, tc_gemm):
+    G.test_d_step_on_gpu_matches_reference_trace()
+    G.test_usim_and_real_rows(120, 96, 32, 64)

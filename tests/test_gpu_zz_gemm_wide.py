@@ -1,0 +1,47 @@
+"""General-width tcgen05 GEMM (csrc/gemm_wide.cu) against fp64, and the GAN side running on it.
+
+NOT YET RUN ON A GPU: the kernel was written when round 1 had no GPU time left.  Unlike the plain-CUDA kernels it cannot
+be executed by the CPU emulator (TMA / TMEM / tcgen05 PTX); only the host contract around it is checked there
+(tests/test_emu_gan.py).  Gated by MMSSL_RUN_UNVALIDATED=1 until its first green GPU run; gan_ops.GEMM_IMPL stays "simt"
+by default until then."""
+import os
+
+import pytest
+import torch
+
+from tests.golden_util import rel_err
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("MMSSL_RUN_UNVALIDATED") != "1",
+                                 reason="gemm_wide.cu not yet validated on a GPU (set MMSSL_RUN_UNVALIDATED=1)")]
+
+
+@pytest.mark.parametrize("m,n,k", [(64, 24, 96), (300, 200, 96), (2048, 1762, 7050), (1762, 7050, 2048), (2048, 7050, 1762),
+                                   (2048, 881, 1762), (130, 257, 70), (5, 1, 8)])
+def test_gemm_wide_vs_fp64(m, n, k):
+    from mmssl_b200 import ops
+    g = torch.Generator().manual_seed(m + n + k)
+    a, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g)
+    a_hi, a_lo = ops.split_bf16(a.cuda())
+    b_hi, b_lo = ops.split_bf16(b.cuda())
+    want = a.double() @ b.double().t()
+    out = torch.full((m, n), float("nan"), device="cuda")
+    ops.gemm_bf16x3_wide(a_hi, a_lo, b_hi, b_lo, m, n, k, out, alpha=0.5)
+    assert rel_err(out, 0.5 * want) < 2e-5
+    base = torch.randn(m, n, generator=g)
+    out2 = base.clone().cuda()
+    ops.gemm_bf16x3_wide(a_hi, a_lo, b_hi, b_lo, m, n, k, out2, alpha=-1.0, accumulate=True)
+    assert rel_err(out2, base.double() - want) < 2e-5
+    # a strided output (leading dimension > n, rows not 16-byte aligned): the scalar-store epilogue
+    wide = torch.zeros(m, n + 3, device="cuda")
+    ops.gemm_bf16x3_wide(a_hi, a_lo, b_hi, b_lo, m, n, k, wide[:, 1:n + 1], alpha=1.0)
+    assert rel_err(wide[:, 1:n + 1], want) < 2e-5 and float(wide[:, 0].abs().max()) == 0 and float(wide[:, n + 1:].abs().max()) == 0
+
+
+def test_gan_side_on_tensor_cores(monkeypatch):
+    from mmssl_b200 import gan_ops
+    from tests import fullstep_check, test_gpu_zz_gan as G
+    monkeypatch.setattr(gan_ops, "GEMM_IMPL", "tc")
+    G.test_d_step_on_gpu_matches_reference_trace()
+    G.test_usim_and_real_rows(19445, 7050, 1024, 64)
+    fullstep_check.run_and_check(dev="cuda", proj_impl="tc")
