@@ -12,6 +12,7 @@ import contextlib
 import ctypes as C
 import os
 import sys
+import weakref
 
 import torch
 
@@ -67,8 +68,65 @@ def _on_cpu(fn):
     return wrapped
 
 
-def emulated_device(monkeypatch):
+class _Guard:
+    """Red zones around every tensor the patched factories hand out; ``check`` runs after every library call.
+    The "device" is the host heap here, so an out-of-bounds kernel write would otherwise corrupt it silently."""
+    PAD = 512
+
+    def __init__(self, real_empty):
+        self.real_empty, self.live = real_empty, []
+
+    def alloc(self, shape, dtype, fill):
+        n = 1
+        for v in shape:
+            n *= int(v)
+        es = self.real_empty(0, dtype=dtype).element_size()
+        buf = self.real_empty(n * es + 2 * self.PAD, dtype=torch.uint8)
+        buf[:self.PAD] = 0xA5
+        buf[self.PAD + n * es:] = 0xA5
+        view = buf[self.PAD:self.PAD + n * es].view(dtype).view(*shape) if n else self.real_empty(*shape, dtype=dtype)
+        if fill is not None and n:
+            view.fill_(fill)
+        if n:
+            self.live.append((weakref.ref(view), buf, tuple(shape), dtype))
+        return view
+
+    def check(self, where):
+        keep = []
+        for ref, buf, shape, dtype in self.live:
+            if ref() is None:
+                continue
+            keep.append((ref, buf, shape, dtype))
+            lo, hi = buf[:self.PAD], buf[buf.numel() - self.PAD:]
+            if bool((lo != 0xA5).any()) or bool((hi != 0xA5).any()):
+                side = "before" if bool((lo != 0xA5).any()) else "after"
+                raise AssertionError(f"cuemu guard: {where} wrote {side} a {dtype} tensor of shape {shape}")
+        self.live = keep
+
+
+class _Checked:
+    """Library proxy: every call is followed by a red-zone check."""
+
+    def __init__(self, lib, guard):
+        object.__setattr__(self, "_lib", lib)
+        object.__setattr__(self, "_guard", guard)
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not callable(fn):
+            return fn
+        guard = self._guard
+
+        def call(*a):
+            r = fn(*a)
+            guard.check(name)
+            return r
+        return call
+
+
+def emulated_device(monkeypatch, guard: bool = False):
     from mmssl_b200 import _lib
+    guard = guard or os.environ.get("CUEMU_GUARD") == "1"       # CUEMU_GUARD=1 pytest ... : the whole emulated suite with red zones
     lib = emu_lib()
     # a failed launch leaves a sticky error in the emulator, like CUDA: clear it between tests
     clear = getattr(lib, "cuemu_clear_error", None)
@@ -95,6 +153,23 @@ def emulated_device(monkeypatch):
     monkeypatch.setattr(torch.cuda, "Stream", _NullStream)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _NullStream())
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    if guard:
+        g = _Guard(torch.empty)
+        lib = _Checked(lib, g)
+        monkeypatch.setattr(_lib, "load", lambda require_device=False: lib)
+        monkeypatch.setattr(_lib, "_lib", lib)
+
+        def factory(fill):
+            def make(*shape, dtype=torch.float32, device=None, **kw):
+                if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)):
+                    shape = tuple(shape[0])
+                return g.alloc(shape, dtype or torch.float32, fill)
+            return make
+        monkeypatch.setattr(torch, "empty", factory(None))
+        monkeypatch.setattr(torch, "zeros", factory(0))
+        monkeypatch.setattr(torch, "ones", factory(1))
+        monkeypatch.setattr(torch, "empty_like", lambda t, **kw: g.alloc(tuple(t.shape), kw.get("dtype") or t.dtype, None))
+        monkeypatch.setattr(torch, "zeros_like", lambda t, **kw: g.alloc(tuple(t.shape), kw.get("dtype") or t.dtype, 0))
     for fname in ("randn", "rand", "randint", "zeros", "ones", "empty", "full", "tensor", "arange", "as_tensor", "randperm"):
         monkeypatch.setattr(torch, fname, _on_cpu(getattr(torch, fname)))
     return lib
