@@ -7,8 +7,9 @@
 backward are the sm_100a kernels of libmmssl_b200 (functional.MMSSLForwardFn) -- CSR SpMM with fused
 softmax / layer-sum epilogues, tcgen05 projection, fused row-wise glue.  There is no eager fallback.
 
-Only the hot path is re-implemented.  ``Discriminator`` (GAN side, out of scope -- SURVEY.md section 2)
-stays a stock-torch module with the reference's architecture so checkpoints and the trainer keep working.
+``Discriminator`` stays a stock-torch module with the reference's architecture so that the reference's own trainer and its
+checkpoints keep working; the device implementation of the GAN side (no autograd) is mmssl_b200/gan.py + fullstep.py, which
+reads and updates this module's state_dict in place (mmssl_b200/trainer.py).
 """
 from __future__ import annotations
 
@@ -117,7 +118,7 @@ class MMSSL(nn.Module):
 
 
 class Discriminator(nn.Module):
-    """GAN discriminator of the reference (Models.py:224-245), stock torch (out of the hot path).
+    """GAN discriminator of the reference (Models.py:224-245), stock torch (parameter container for fullstep.FullStep).
     ``nn.LeakyReLU(True)`` means negative_slope == 1.0, i.e. identity -- kept as is."""
 
     def __init__(self, dim):
