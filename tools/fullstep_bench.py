@@ -1,0 +1,106 @@
+"""Full training iteration (mmssl_b200/fullstep.py = main.py:333-434: D step + G step + both optimisers + graph rebuilds) on one
+GPU, timed with CUDA events, next to the hot step alone and to the oracle's CPU restatement of the same iteration.
+SURVEY 8d: "also report full step for C1-C3".  Prints one JSON line.
+
+    python tools/fullstep_bench.py [config=baby] [--steps K] [--warmup W] [--gemm tc|simt] [--cpu-steps N]
+
+Not part of bench.py's contract (the headline metric is the hot step); written when round 1 had no GPU time left -- first run
+is a round-2 task."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("config", nargs="?", default="baby")
+ap.add_argument("--steps", type=int, default=50)
+ap.add_argument("--warmup", type=int, default=5)
+ap.add_argument("--gemm", default=os.environ.get("MMSSL_GAN_GEMM", "simt"), choices=["tc", "simt"])
+ap.add_argument("--cpu-steps", type=int, default=2)
+ap.add_argument("--seed", type=int, default=2022)
+a = ap.parse_args()
+
+import bench  # noqa: E402  (problem builder shared with the headline benchmark)
+from mmssl_b200 import gan, gan_ops  # noqa: E402
+from mmssl_b200.fullstep import FullStep, FullStepConfig  # noqa: E402
+from mmssl_b200.hotstep import HotStepConfig  # noqa: E402
+from mmssl_b200.synthetic import TripleSampler  # noqa: E402
+
+gan_ops.GEMM_IMPL = a.gemm
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(dev)
+B = bench.BATCH
+ds, P, feats, graphs, feats_cpu = bench.build_problem(a.config, a.seed, dev)
+U, I, d = ds.n_users, ds.n_items, ds.embed_size
+h1, h2 = int(I / 4), int(I / 8)
+g = torch.Generator().manual_seed(a.seed + 1)
+
+
+def d_state(device):
+    """Discriminator(n_items) after weights_init (main.py:73, :133-136): kaiming-normal Linear weights, zero biases."""
+    kn = lambda o, i: torch.randn(o, i, generator=g) * (2.0 / i) ** 0.5
+    s = {"net.0.weight": kn(h1, I), "net.0.bias": torch.zeros(h1), "net.2.weight": torch.ones(h1), "net.2.bias": torch.zeros(h1),
+         "net.2.running_mean": torch.zeros(h1), "net.2.running_var": torch.ones(h1), "net.2.num_batches_tracked": torch.zeros((), dtype=torch.int64),
+         "net.4.weight": kn(h2, h1), "net.4.bias": torch.zeros(h2), "net.6.weight": torch.ones(h2), "net.6.bias": torch.zeros(h2),
+         "net.6.running_mean": torch.zeros(h2), "net.6.running_var": torch.ones(h2), "net.6.num_batches_tracked": torch.zeros((), dtype=torch.int64),
+         "net.8.weight": kn(1, h2), "net.8.bias": torch.zeros(1)}
+    return {k: v.to(device) for k, v in s.items()}
+
+
+S_cpu = d_state("cpu")
+R = ds.train.tocsr()
+R.sort_indices()
+t64 = lambda x: torch.from_numpy(np.asarray(x, dtype=np.int64)).to(dev)
+cfg = FullStepConfig(hot=HotStepConfig(embed_size=d, n_layers=ds.n_layers, batch_size=B), gan=gan.GanHyper())
+fs = FullStep(P, {k: v.clone().to(dev) for k, v in S_cpu.items()}, feats, t64(R.indptr), t64(R.indices), graphs[0], graphs[1], cfg, batch=B)
+smp = TripleSampler(ds.train, seed=a.seed)
+batches = [tuple(torch.from_numpy(x).to(dev) for x in smp.sample(B)) for _ in range(8)]
+
+
+def run(n):
+    for s in range(n):
+        out = fs.step(*batches[s % len(batches)])
+    return out
+
+
+run(a.warmup)
+torch.cuda.synchronize()
+from mmssl_b200 import _lib  # noqa: E402
+_lib.launch_count = 0
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+out = run(a.steps)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.steps
+launches = _lib.launch_count / a.steps
+res = {"metric": "bpr_triples_per_sec_full_step", "unit": "triples/s", "value": B / ms * 1e3, "ms_per_step": ms, "n_gpus": 1,
+       "steps": a.steps, "warmup": a.warmup, "config": {"workload": a.config, "U": U, "I": I, "nnz": int(ds.nnz), "d": d, "batch": B,
+                                                          "gan_gemm": a.gemm, "graph_capture": False, "modality_graphs": "empty after iteration 1 (T=1, reference quirk)"},
+       "gpu_launches_per_step": launches, "batch_loss": float(out["batch_loss"]), "loss_D": float(out["loss_D"]),
+       "big_gemm_gflop_per_step": 11 * 2 * 2 * B * I * h1 / 1e9}
+
+if a.cpu_steps > 0:          # the oracle's restatement of the same iteration on the host (all threads), a bounded sample
+    import scipy.sparse as sp  # noqa: F401
+    from oracle import gan_oracle as GO, mmssl_oracle as O
+    ocfg = O.HotPathConfig(embed_size=d, n_layers=ds.n_layers, batch_size=B)
+    _, Pc, fc, _, _ = bench.build_problem(a.config, a.seed, None)
+    cpu = GO.FullStep({k: v.clone() for k, v in Pc.items()}, {k: v.clone() for k, v in S_cpu.items()}, fc[0], fc[1], R, ocfg, GO.GanConfig())
+    gen = torch.Generator().manual_seed(3)
+    p = 0.2
+    mk = lambda n, w, q: ((torch.rand(n, w, generator=gen) >= q) / (1 - q)).float()
+    t0 = time.time()
+    for s in range(a.cpu_steps):
+        u, po, ne = (x.cpu() for x in batches[s % len(batches)])
+        cpu.step(u.tolist(), po.tolist(), ne.tolist(), [mk(I, d, p) for _ in range(4)], [mk(2 * B, h1, 0.31) for _ in range(4)],
+                 [mk(2 * B, h2, 0.5) for _ in range(4)], torch.rand(B, I, generator=gen), torch.rand(2 * B, 1, generator=gen))
+    dt = (time.time() - t0) / a.cpu_steps
+    res["cpu_baseline"] = {"value": B / dt, "unit": "triples/s", "cores": torch.get_num_threads(), "kind": "port",
+                           "sample": f"{a.cpu_steps} full iterations of oracle/gan_oracle.py:FullStep"}
+print(json.dumps(res))
