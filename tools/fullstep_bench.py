@@ -24,6 +24,7 @@ ap.add_argument("--warmup", type=int, default=5)
 ap.add_argument("--gemm", default=os.environ.get("MMSSL_GAN_GEMM", "simt"), choices=["tc", "simt"])
 ap.add_argument("--cpu-steps", type=int, default=2)
 ap.add_argument("--seed", type=int, default=2022)
+ap.add_argument("--batch", type=int, default=0, help="0 = bench.BATCH (1024, the reference default)")
 a = ap.parse_args()
 
 import bench  # noqa: E402  (problem builder shared with the headline benchmark)
@@ -35,7 +36,7 @@ from mmssl_b200.synthetic import TripleSampler  # noqa: E402
 gan_ops.GEMM_IMPL = a.gemm
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
-B = bench.BATCH
+B = a.batch or bench.BATCH
 ds, P, feats, graphs, feats_cpu = bench.build_problem(a.config, a.seed, dev)
 U, I, d = ds.n_users, ds.n_items, ds.embed_size
 h1, h2 = int(I / 4), int(I / 8)
