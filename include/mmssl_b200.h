@@ -297,6 +297,16 @@ int mmssl_gan_gather_rows(const float* table, int64_t ld, const int64_t* rows, i
 int mmssl_gan_scatter_add_rows(float* table, int64_t ld, const int64_t* rows, int64_t n_rows, int d, const float* src,
                                void* stream);
 
+/* ------------------------------------------------------------------ row-sharded hot step (shard.cu)
+ * A rank holds the rows [lo, hi) of a table; the batch indexes the FULL table (main.py:368-370, :411-412).
+ * mmssl_gather_owned: out[j] = table_local[idx[j] - lo] when the rank owns row idx[j], zeros otherwise (summing the
+ *   ranks' outputs gives the batch rows everywhere).  mmssl_scatter_add_owned: table_local[idx[j] - lo] += src[j] for the
+ *   owned rows only (atomic; duplicate ids accumulate). */
+int mmssl_gather_owned(const float* table, int64_t ld, const int64_t* idx, int64_t lo, int64_t hi, int64_t n, int d, float* out,
+                       int64_t ldo, void* stream);
+int mmssl_scatter_add_owned(float* table, int64_t ld, const int64_t* idx, int64_t lo, int64_t hi, int64_t n, int d,
+                            const float* src, int64_t lds, void* stream);
+
 /* ------------------------------------------------------------------ modality-graph bookkeeping of the full step (regraph.cu)
  * mmssl_topk_rows: ids[rows, k] (int64) = columns of the k largest entries of every row of x[rows, w], best first, equal
  *   values keep the lower column first -- torch.topk(G_*_u_sim_detach, int(n_items * m_topk_rate)) at main.py:397,400.

@@ -76,6 +76,13 @@ class Engine:
         # streams; inside a CUDA graph they become parallel branches.  Set to False to serialise.
         self.two_streams = True
         self._side: Dict[Tuple, torch.cuda.Stream] = {}
+        # Row-sharded scheme (rowshard_step.py): every table is a row block, the graphs are row blocks with
+        # global column ids, and each SpMM needs its dense operand from all ranks.  ``exchange(list_of_local, space)``
+        # ('u' = user rows, 'i' = item rows) returns the gathered operands; None = single GPU, operands pass through.
+        self.exchange = None
+
+    def _full(self, xs, space: str):
+        return xs if self.exchange is None else self.exchange(xs, space)
 
     def _pair(self, dev, fn_a, fn_b):
         """Run two independent kernel groups concurrently (user side on the current stream, item side
@@ -173,8 +180,8 @@ class Engine:
             resolved[0] = m
             self._project(P[P_WV], P[P_BV], feats[0], m[0] if m else None, xv)             # Models.py:173
             self._project(P[P_WT], P[P_BT], feats[1], m[1] if m else None, xt)             # Models.py:174
-            ops.spmm(g_ui.fwd, [xv, xt], [uv, ut])                                         # :177,182
-            ops.spmm(g_iu.fwd, [uv, ut], [iv, it])                                         # :178,183
+            ops.spmm(g_ui.fwd, self._full([xv, xt], "i"), [uv, ut])                        # :177,182
+            ops.spmm(g_iu.fwd, self._full([uv, ut], "u"), [iv, it])                        # :178,183
 
         if side is not main:
             side.wait_stream(main)
@@ -183,7 +190,10 @@ class Engine:
         else:
             modal_branch()
 
-        def id_prop(ga, gb, e, rows):                                                  # :179-180,185-186
+        def id_prop(ga, gb, e, rows, space):                                           # :179-180,185-186
+            if ga.nnz > 0 or gb.nnz > 0:
+                e = self._full([e], space)[0]
+
             def one(g):
                 if g.nnz == 0:
                     return torch.zeros(rows, d, dtype=torch.float32, device=dev)
@@ -191,7 +201,7 @@ class Engine:
             ya = one(ga)
             return (ya, ya) if ga is gb else (ya, one(gb))
 
-        (uvid, utid), (ivid, itid) = self._pair(dev, lambda: id_prop(g_vui, g_tui, e_i, U), lambda: id_prop(g_viu, g_tiu, e_u, I))
+        (uvid, utid), (ivid, itid) = self._pair(dev, lambda: id_prop(g_vui, g_tui, e_i, U, "i"), lambda: id_prop(g_viu, g_tiu, e_u, I, "u"))
         st = FwdState(tuple(graphs), resolved[0], X2, U2, I2, (uvid, utid, ivid, itid),
                       fused=any(g.nnz > 0 for g in (g_vui, g_viu, g_tui, g_tiu)))
         if st.fused:                                                                   # :188-197 (closed form)
@@ -227,8 +237,8 @@ class Engine:
             last = k == K - 1
             epi = ops.EPI_SOFTMAX if last else ops.EPI_NONE
             mode = 2 if k == 0 else 1
-            u_n = ops.spmm(g_ui.fwd, [cur_i], epilogue=epi, ss=[s_u], s_mode=mode, sbases=[u0] if k == 0 else None)[0]
-            i_n = ops.spmm(g_iu.fwd, [u_n], epilogue=epi, ss=[s_i], s_mode=mode, sbases=[i0] if k == 0 else None)[0]
+            u_n = ops.spmm(g_ui.fwd, self._full([cur_i], "i"), epilogue=epi, ss=[s_u], s_mode=mode, sbases=[u0] if k == 0 else None)[0]
+            i_n = ops.spmm(g_iu.fwd, self._full([u_n], "u"), epilogue=epi, ss=[s_i], s_mode=mode, sbases=[i0] if k == 0 else None)[0]
             if last:
                 st.u_last, st.i_last = u_n, i_n
             cur_i = i_n
@@ -290,9 +300,9 @@ class Engine:
         def modal_backward():
             # modality propagation backward (Models.py:177-178,182-183), image|text batched, then the
             # projection backward (dropout mask folded into the operand split)
-            ops.spmm(g_iu.bwd, [gI2[:, :d], gI2[:, d:]], [gU2[:, :d], gU2[:, d:]], cs=[gU2[:, :d], gU2[:, d:]], alpha=1.0)
+            ops.spmm(g_iu.bwd, self._full([gI2[:, :d], gI2[:, d:]], "i"), [gU2[:, :d], gU2[:, d:]], cs=[gU2[:, :d], gU2[:, d:]], alpha=1.0)
             gX2 = self._new(I, 2 * d, dev=dev)
-            ops.spmm(g_ui.bwd, [gU2[:, :d], gU2[:, d:]], [gX2[:, :d], gX2[:, d:]])
+            ops.spmm(g_ui.bwd, self._full([gU2[:, :d], gU2[:, d:]], "u"), [gX2[:, :d], gX2[:, d:]])
             m = st.masks
             self._project_bwd(gX2[:, :d], m[0] if m else None, feats[0], w_slots[0], w_slots[1])
             self._project_bwd(gX2[:, d:], m[1] if m else None, feats[1], w_slots[2], w_slots[3])
@@ -309,10 +319,10 @@ class Engine:
             t = ops.softmax_bwd(st.i_last, g_if, inv, self._new(I, d, dev=dev))
             for k in range(K - 1, -1, -1):
                 last = k == K - 1
-                tu = ops.spmm(g_iu.bwd, [t], cs=[g_uf], alpha=inv,
+                tu = ops.spmm(g_iu.bwd, self._full([t], "i"), cs=[g_uf], alpha=inv,
                               epilogue=ops.EPI_SOFTMAX_BWD if last else ops.EPI_NONE,
                               ysaved=[st.u_last] if last else None)[0]
-                t = ops.spmm(g_ui.bwd, [tu], cs=[g_if], alpha=inv)[0]
+                t = ops.spmm(g_ui.bwd, self._full([tu], "u"), cs=[g_if], alpha=inv)[0]
             g_i0 = t                                            # d loss / d i_0
         else:
             g_i0 = ops.axpby(g_if, inv, 0.0, self._new(I, d, dev=dev))
@@ -371,30 +381,30 @@ class Engine:
             g_wcat.zero_()
             gt_uvid, gt_utid, gt_ivid, gt_itid = g_uvid, g_utid, g_ivid, g_itid
 
-        def id_prop_bwd(ga, gb, gya, gyb, g_e, same_out):
+        def id_prop_bwd(ga, gb, gya, gyb, g_e, same_out, space):
             # E-gradient += A^T g  for each modality graph (same_out: both modalities share graph and output)
             if ga is gb:
                 if ga.nnz == 0:
                     return
                 if same_out and gya is not None:
-                    ops.spmm(ga.bwd, [gya], [g_e], cs=[g_e], alpha=1.0)
+                    ops.spmm(ga.bwd, self._full([gya], space), [g_e], cs=[g_e], alpha=1.0)
                     return
                 for g in (gya, gyb):
                     if g is not None:
-                        ops.spmm(ga.bwd, [g], [g_e], cs=[g_e], alpha=1.0)
+                        ops.spmm(ga.bwd, self._full([g], space), [g_e], cs=[g_e], alpha=1.0)
                 return
             for gr, g in ((ga, gya), (gb, gyb)):
                 if g is not None and gr.nnz > 0:
-                    ops.spmm(gr.bwd, [g], [g_e], cs=[g_e], alpha=1.0)
+                    ops.spmm(gr.bwd, self._full([g], space), [g_e], cs=[g_e], alpha=1.0)
 
         # Uvid = A_vui E_i, Utid = A_tui E_i -> gradient flows to E_i; Ivid/Itid -> E_u.  The head reduction
         # of dWcat does not feed them, so it rides along on the pair stream.
         def tail_b():
-            id_prop_bwd(g_viu, g_tiu, gt_ivid, gt_itid, g_eu, st.fused and ivid is itid)
+            id_prop_bwd(g_viu, g_tiu, gt_ivid, gt_itid, g_eu, st.fused and ivid is itid, "i")
             if dwcat_args is not None:
                 ops.dwcat_reduce(dwcat_args[0], dwcat_args[1], d, self.H, g_wcat)
 
-        self._pair(dev, lambda: id_prop_bwd(g_vui, g_tui, gt_uvid, gt_utid, g_ei, st.fused and uvid is utid), tail_b)
+        self._pair(dev, lambda: id_prop_bwd(g_vui, g_tui, gt_uvid, gt_utid, g_ei, st.fused and uvid is utid, "u"), tail_b)
         if side is not main:
             main.wait_stream(side)
         return res

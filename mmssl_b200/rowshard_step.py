@@ -1,0 +1,214 @@
+"""The whole hot step under the row-sharded scheme of north_star / SURVEY 8e: embedding tables, features and every
+[U, d] / [I, d] intermediate are block-partitioned by rows over the ranks of one box, each rank holds the row blocks of the
+normalised graphs (and of their transposes for the backward), and every SpMM is preceded by one all-gather of its dense
+operand -- 2 per GCN layer forward, 2 backward, plus the modality / id propagations (parallel.RowShardedGCN is the same
+schedule for the bare K-layer chain).  Everything else of the step is local to the rows a rank owns:
+
+  projection + dropout   rows I_r of the features (no communication forward; dW, db all-reduced, they are [d, Dv+Dt])
+  id fusion, layer mean, modality residual, softmax   row-wise
+  losses                 the batch names rows of the FULL tables (main.py:368-370, :411-412).  Each rank contributes the
+                         rows it owns (mmssl_gather_owned), ONE all-reduce of [5, B, d] gives every rank the batch rows
+                         of u_f[users], i_f[pos], i_f[neg], Uvid[users], Utid[users]; the loss kernels then run replicated
+                         (B = 1024: 0.27 GFLOP), and each rank keeps the gradient rows it owns (mmssl_scatter_add_owned) --
+                         no second exchange, no cross-rank float atomics, bit-identical losses on every rank
+  AdamW                  on the local row blocks of the two tables (optimiser state sharded with them); the five small
+                         replicated parameters get identical all-reduced gradients and identical updates
+
+The exchange is injected into ``Engine`` (``engine.exchange``): NCCL all-gather on the box, gloo in the CPU tests where the
+kernels run under the emulator (tests/test_dist_emu.py).  Fusing the all-gather into the producing SpMM over NVSwitch
+multicast (parallel.FusedRowShardedGCN) applies to the same call sites and is the next step for this class.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from ._lib import ptr, stream
+from .engine import LIVE, P_EI, P_EU, Engine, FeatureStore
+from .graph import SparseOperand
+from .hotstep import HotStepConfig
+from .parallel import RowPartition, all_gather_rows, shard_rows_scipy
+
+REPLICATED = tuple(k for k in LIVE if k not in (P_EU, P_EI))
+
+
+class RowBlockGraph:
+    """What ``Engine`` needs of a graph, for one rank: ``fwd`` = A[rows_r, :] and ``bwd`` = (A^T)[cols_r, :] as prepared
+    SpMM operands (global column ids), ``shape`` = the LOCAL (padded) row counts of the two row spaces, ``nnz`` = the
+    global edge count (only compared with 0)."""
+
+    def __init__(self, fwd: SparseOperand, bwd: SparseOperand, shape: Tuple[int, int], nnz: int):
+        self.fwd, self.bwd, self.shape, self.nnz = fwd, bwd, shape, int(nnz)
+
+    @classmethod
+    def from_scipy(cls, mat, part_rows: RowPartition, part_cols: RowPartition, rank: int, device) -> "RowBlockGraph":
+        def op(m, part):
+            blk = shard_rows_scipy(m, part, rank).tocoo()
+            t = lambda a, dt: torch.from_numpy(np.asarray(a).astype(dt)).to(device)
+            o = SparseOperand(t(blk.row, "int64"), t(blk.col, "int64"), t(blk.data, "float32"), blk.shape[0], blk.shape[1])
+            o.tighten()
+            return o
+        mat = mat.tocsr()
+        return cls(op(mat, part_rows), op(mat.T.tocsr(), part_cols), (part_rows.block, part_cols.block), mat.nnz)
+
+
+def gather_owned(table: torch.Tensor, idx: torch.Tensor, lo: int, hi: int, out: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load(require_device=True)
+    _lib.check(lib.mmssl_gather_owned(ptr(table), table.stride(0), ptr(idx), lo, hi, idx.numel(), table.shape[1], ptr(out),
+                                      out.stride(0), stream()))
+    return out
+
+
+def scatter_add_owned(table: torch.Tensor, idx: torch.Tensor, lo: int, hi: int, src: torch.Tensor) -> None:
+    lib = _lib.load(require_device=True)
+    _lib.check(lib.mmssl_scatter_add_owned(ptr(table), table.stride(0), ptr(idx), lo, hi, idx.numel(), table.shape[1], ptr(src),
+                                           src.stride(0), stream()))
+
+
+class RowShardedHotStep:
+    """One rank of the row-sharded hot step.  ``params``: the rank's padded row blocks of the two embedding tables
+    (``RowPartition.local``) and full copies of the five small parameters; ``feats``: FeatureStores of the rank's item rows;
+    ``graphs``: six RowBlockGraphs (ui, iu, image ui/iu, text ui/iu; pass the same objects to alias them, main.py:68-69)."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], feats: Sequence[FeatureStore], graphs: Sequence[RowBlockGraph],
+                 cfg: HotStepConfig, batch: int, part_u: RowPartition, part_i: RowPartition, rank: int, group=None,
+                 optimizer_step: bool = True):
+        self.cfg, self.batch, self.pu, self.pi, self.rank, self.group = cfg, batch, part_u, part_i, rank, group
+        self.P = {k: params[k] for k in LIVE}
+        self.feats, self.graphs = tuple(feats), tuple(graphs)
+        self.engine = Engine(cfg.embed_size, cfg.n_layers, cfg.head_num, cfg.id_cat_rate, cfg.model_cat_rate, cfg.proj_impl)
+        self.engine.two_streams = False                     # the collectives order the work on one stream
+        self.engine.exchange = self._exchange
+        self.optimizer_step = optimizer_step
+        self.n_gathers, self.gathered_bytes = 0, 0
+        dev = self.P[P_EU].device
+        d, B = cfg.embed_size, batch
+        f = dict(dtype=torch.float32, device=dev)
+        self.idx = torch.zeros(3, B, dtype=torch.int64, device=dev)
+        self.rows = torch.zeros(5, B, d, **f)               # u_f[users], i_f[pos], i_f[neg], Uvid[users], Utid[users]
+        self.g_rows = torch.zeros(5, B, d, **f)
+        self.g_uf = torch.zeros(part_u.block, d, **f)
+        self.g_if = torch.zeros(part_i.block, d, **f)
+        self.g_uvid = torch.zeros(part_u.block, d, **f)
+        self.g_utid = torch.zeros(part_u.block, d, **f)
+        # image and text graphs are the same object at step 0 (main.py:68-69): Uvid is Utid, one InfoNCE counted twice
+        self.alias = graphs[2] is graphs[4] and graphs[3] is graphs[5]
+        self.nce = [ops.InfoNCEWork(B, d, dev) for _ in range(1 if self.alias else 2)]
+        self.cl_seed = torch.full((1,), cfg.cl_rate * (2.0 if self.alias else 1.0), **f)
+        self.out5 = torch.zeros(5, **f)
+        self.grads = {k: torch.zeros_like(t) for k, t in self.P.items()}
+        self.m = {k: torch.zeros_like(t) for k, t in self.P.items()}
+        self.v = {k: torch.zeros_like(t) for k, t in self.P.items()}
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.masks: Optional[tuple] = None                  # injected [I_block, d] keep-masks of the rank's item rows
+        self.training = True
+        # the small replicated gradients travel in one flat buffer
+        n = sum((self.grads[k].numel() + 3) // 4 * 4 for k in REPLICATED)
+        self._flat = torch.zeros(n, **f)
+        o = 0
+        for k in REPLICATED:
+            g = self.grads[k]
+            self.grads[k] = self._flat[o:o + g.numel()].view_as(g)
+            o += (g.numel() + 3) // 4 * 4
+
+    # -------------------------------------------------------------- exchange
+    def _exchange(self, xs: List[torch.Tensor], space: str) -> List[torch.Tensor]:
+        part = self.pu if space == "u" else self.pi
+        out = []
+        for x in xs:
+            self.n_gathers += 1
+            self.gathered_bytes += x.numel() * x.element_size() * (part.world - 1)
+            out.append(all_gather_rows(x, part, self.group))
+        return out
+
+    def _masks(self):
+        if not self.training or self.cfg.drop_rate <= 0:
+            return None
+        if self.masks is not None:
+            return self.masks
+        import torch.nn.functional as F
+        ones = torch.ones(self.pi.block, self.cfg.embed_size, dtype=torch.float32, device=self.idx.device)
+        return (F.dropout(ones, self.cfg.drop_rate, True), F.dropout(ones, self.cfg.drop_rate, True))
+
+    def set_indices(self, users, pos, neg) -> None:
+        for j, t in enumerate((users, pos, neg)):
+            self.idx[j].copy_(torch.as_tensor(t, dtype=torch.int64), non_blocking=True)
+
+    # -------------------------------------------------------------- one step
+    def run(self) -> torch.Tensor:
+        """One hot step on the batch in ``self.idx`` (GLOBAL user / item ids, identical on every rank).  Returns the device
+        tensor [total, mf, emb, feat_reg, cl] -- global values, identical on every rank."""
+        cfg, B = self.cfg, self.batch
+        users, pos, neg = self.idx[0], self.idx[1], self.idx[2]
+        ulo, uhi = self.pu.bounds(self.rank)
+        ilo, ihi = self.pi.bounds(self.rank)
+        for t in (self.g_uf, self.g_if, self.g_uvid, self.g_utid, self.g_rows):
+            t.zero_()
+        outs, st = self.engine.forward(self.P, self.feats, self.graphs, self._masks(), want_sumsq=True)
+        u_f, i_f, _, _, _, _, u_vid, u_tid, _, _ = outs
+        alias = self.alias
+        # ---- the batch rows of the full tables: owned rows + one all-reduce
+        gather_owned(u_f, users, ulo, uhi, self.rows[0])
+        gather_owned(i_f, pos, ilo, ihi, self.rows[1])
+        gather_owned(i_f, neg, ilo, ihi, self.rows[2])
+        gather_owned(u_vid, users, ulo, uhi, self.rows[3])
+        if not alias:
+            gather_owned(u_tid, users, ulo, uhi, self.rows[4])
+        if self.pu.world > 1:
+            dist.all_reduce(self.rows, op=dist.ReduceOp.SUM, group=self.group)
+        ub, pb, nb, zv, zt = self.rows
+        g_ub, g_pb, g_nb, g_zv, g_zt = self.g_rows
+        # ---- losses on the compact batch tables (identity indices), replicated on every rank
+        reg_coef = cfg.emb_decay / cfg.batch_size
+        bpr_part, n_bpr = ops.bpr(ub, pb, nb, None, None, None, mode=3, reg_coef=reg_coef, g_u=g_ub, g_p=g_pb, g_n=g_nb)
+        inv_tau = 1.0 / cfg.tau
+        parts = []
+        for w, z1, gz1 in zip(self.nce, (zv, zt), (g_zv, g_zt)):
+            parts.append(ops.infonce_forward(z1, ub, None, inv_tau, w, g_loss=self.cl_seed))
+            if st.fused:
+                ops.infonce_backward(None, inv_tau, w, gz1, g_ub)
+        nce1, nce2 = parts[0], parts[-1]
+        ops.loss_assemble(bpr_part, n_bpr, B, reg_coef, st.sumsq_u, st.sumsq_i, 0.5 * cfg.feat_reg_decay / self.pi.n, nce1, nce2, B,
+                          cfg.cl_rate, self.out5)
+        if self.pu.world > 1:                               # feat_reg was summed over the local rows only
+            feat = self.out5[3].clone()
+            dist.all_reduce(feat, op=dist.ReduceOp.SUM, group=self.group)
+            self.out5[0] += feat - self.out5[3]
+            self.out5[3] = feat
+        # ---- gradient rows go back to their owners
+        scatter_add_owned(self.g_uf, users, ulo, uhi, g_ub)
+        scatter_add_owned(self.g_if, pos, ilo, ihi, g_pb)
+        scatter_add_owned(self.g_if, neg, ilo, ihi, g_nb)
+        if st.fused:
+            scatter_add_owned(self.g_uvid, users, ulo, uhi, g_zv)
+            if not alias:
+                scatter_add_owned(self.g_utid, users, ulo, uhi, g_zt)
+        grads = [self.g_uf, self.g_if, None, None, None, None, self.g_uvid if st.fused else None,
+                 (None if alias else self.g_utid) if st.fused else None, None, None]
+        self.engine.backward(st, self.P, self.feats, grads, feat_reg_coef=cfg.feat_reg_decay / self.pi.n, out=self.grads)
+        if self.pu.world > 1:                               # dW, db, dWcat: sums over the ranks' rows
+            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
+        if self.optimizer_step:
+            ops.step_tick(self.step_dev)
+            keys = list(LIVE)
+            ops.adamw([self.P[k] for k in keys], [self.grads[k] for k in keys], [self.m[k] for k in keys], [self.v[k] for k in keys],
+                      self.step_dev, cfg.lr, cfg.beta1, cfg.beta2, cfg.eps, cfg.weight_decay)
+        return self.out5
+
+
+def shard_problem(P_full: Dict[str, torch.Tensor], feats_full: Sequence[torch.Tensor], ui_norm, iu_norm, rank: int, world: int, device):
+    """Rank-local pieces of a full problem: (params, FeatureStores, six RowBlockGraphs with the modality graphs aliased,
+    part_u, part_i).  The full problem only has to exist on the host."""
+    U, I = ui_norm.shape
+    pu, pi = RowPartition(U, world), RowPartition(I, world)
+    P = {k: P_full[k].to(device).contiguous() for k in REPLICATED}
+    P[P_EU] = pu.local(P_full[P_EU], rank).to(device).contiguous()
+    P[P_EI] = pi.local(P_full[P_EI], rank).to(device).contiguous()
+    feats = tuple(FeatureStore(pi.local(f, rank).to(device).contiguous(), keep_fp32=True) for f in feats_full)
+    g_ui = RowBlockGraph.from_scipy(ui_norm, pu, pi, rank, device)
+    g_iu = RowBlockGraph.from_scipy(iu_norm, pi, pu, rank, device)
+    return P, feats, (g_ui, g_iu, g_ui, g_iu, g_ui, g_iu), pu, pi

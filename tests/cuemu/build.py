@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "mmssl_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libmmssl_emu.so")
-SOURCES = ["core.cu", "gan.cu", "eval.cu", "sgemm.cu", "adamw.cu", "rowops.cu", "loss.cu", "idfuse.cu", "sampler.cu", "spmm.cu", "graph.cu", "proj_common.cu", "regraph.cu"]
+SOURCES = ["core.cu", "gan.cu", "eval.cu", "sgemm.cu", "adamw.cu", "rowops.cu", "loss.cu", "idfuse.cu", "sampler.cu", "spmm.cu", "graph.cu", "proj_common.cu", "regraph.cu", "shard.cu"]
 HEADERS = ["common.cuh", "spmm_common.cuh"]
 CXX = os.environ.get("CXX", "g++")
 FLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-fno-strict-aliasing", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",
