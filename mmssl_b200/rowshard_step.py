@@ -118,6 +118,12 @@ class RowShardedHotStep:
     # -------------------------------------------------------------- exchange
     def _exchange(self, xs: List[torch.Tensor], space: str) -> List[torch.Tensor]:
         part = self.pu if space == "u" else self.pi
+        if len(xs) == 2 and xs[0].stride() == xs[1].stride() and xs[0].shape == xs[1].shape and xs[0].stride(1) == 1 and \
+                xs[0].stride(0) == 2 * xs[0].shape[1] and xs[1].data_ptr() == xs[0].data_ptr() + 4 * xs[0].shape[1]:
+            # image | text halves of one [rows, 2d] buffer (engine.X2 / U2 / I2 and their gradients): one collective
+            w = xs[0].shape[1]
+            both = self._exchange([torch.as_strided(xs[0], (xs[0].shape[0], 2 * w), (2 * w, 1))], space)[0]
+            return [both[:, :w], both[:, w:]]
         out = []
         for x in xs:
             self.n_gathers += 1

@@ -1,7 +1,7 @@
 """Row-sharded WHOLE hot step (mmssl_b200/rowshard_step.py) on N GPUs of one box: parity against the single-GPU
 fused HotStep on the same problem (`check`) and time per step (CUDA events, max over ranks).  One JSON line from rank 0.
 
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/rowshard_step_bench.py [config] [check] [--steps K]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/rowshard_step_bench.py [config] [check] [--steps K] [--batch B]
 
 Written when round 1 had no GPU time left; the same class runs in tests/test_dist_emu.py with 2 gloo ranks on the CPU emulator."""
 import json
@@ -28,7 +28,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-B = bench.BATCH
+B = int(sys.argv[sys.argv.index("--batch") + 1]) if "--batch" in sys.argv else bench.BATCH
 ds, P_cpu, feats_cpu, _, _ = bench.build_problem(name, 2022, None)           # the same seeded problem on every rank (host)
 cfg = HotStepConfig(embed_size=ds.embed_size, n_layers=ds.n_layers, batch_size=B)
 Pl, fl, gl, pu, pi = shard_problem(P_cpu, feats_cpu, ds.ui_norm, ds.iu_norm, rank, world, dev)
