@@ -168,6 +168,8 @@ class FullStep:
     def _bookkeeping(self, users, img_sim, txt_sim) -> None:
         self._new_graphs = None
         if self.idx % self.cfg.T == 0 and self.idx != 0:
+            if not self.pairs["image"] and not self.pairs["text"] and all(g.nnz == 0 for g in self.hs.graphs[2:]):
+                return                                   # empty lists onto already empty graphs: nothing changes (steady state at T = 1)
             new = list(self.hs.graphs)
             for j, key in ((2, "image"), (4, "text")):
                 xs = [p[0] for p in self.pairs[key]]
@@ -183,16 +185,9 @@ class FullStep:
                 self.pairs[key].append(pair_append(users, topk_rows(sim, self.k)))
 
     # -------------------------------------------------------------- one iteration
-    def step(self, users, pos, neg, model_masks: Optional[Sequence[torch.Tensor]] = None,
-             d_masks1: Optional[Sequence[torch.Tensor]] = None, d_masks2: Optional[Sequence[torch.Tensor]] = None,
-             gumbel_u: Optional[torch.Tensor] = None, alpha: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-        """users/pos/neg: the batch of ``data_generator.sample()`` (lists or int64 tensors).  Returns device tensors:
-        ``loss5`` = [hot total, mf, emb, feat_reg, cl] (HotStep), ``G_lossf``, ``batch_loss`` (main.py:420), ``gp``,
-        ``loss_D`` (main.py:357) -- nothing is copied to the host."""
+    def _body(self, mm, m1, m2, gu, al) -> Dict[str, torch.Tensor]:
         K, hp, hs = self.K, self.cfg.gan, self.hs
-        hs.set_indices(users, pos, neg)
         u_dev = hs.idx[0]
-        mm, m1, m2, gu, al = self._draws(model_masks, d_masks1, d_masks2, gumbel_u, alpha)
         self._draw = {"m1": m1, "m2": m2}
         # ---- D step (main.py:339-361)
         outs, _ = hs.engine.forward(hs.P, hs.feats, hs.graphs, (mm[0], mm[1]), want_sumsq=False)
@@ -204,11 +199,67 @@ class FullStep:
         # ---- G step (main.py:363-429): HotStep.run calls _generator_side between the loss kernels and the backward
         hs.masks = (mm[2], mm[3])
         loss5 = hs.run()
-        if self._new_graphs is not None:
-            hs.graphs = self._new_graphs
-        self.idx += 1
         n = 2 * self.batch
         g_lossf = self.last["G_s_sum"] * (-100.0 / n)
         loss_d = (dres["lossf_sum"] - dres["lossr_sum"]) * (100.0 / n) + hp.gp_rate * dres["gp"]
         return dict(loss5=loss5, G_lossf=g_lossf, batch_loss=loss5[0] + hp.G_rate * g_lossf, gp=dres["gp"], loss_D=loss_d,
                     D_grads=dres["grads"])
+
+    def step(self, users, pos, neg, model_masks: Optional[Sequence[torch.Tensor]] = None,
+             d_masks1: Optional[Sequence[torch.Tensor]] = None, d_masks2: Optional[Sequence[torch.Tensor]] = None,
+             gumbel_u: Optional[torch.Tensor] = None, alpha: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """users/pos/neg: the batch of ``data_generator.sample()`` (lists or int64 tensors).  Returns device tensors:
+        ``loss5`` = [hot total, mf, emb, feat_reg, cl] (HotStep), ``G_lossf``, ``batch_loss`` (main.py:420), ``gp``,
+        ``loss_D`` (main.py:357) -- nothing is copied to the host."""
+        self.hs.set_indices(users, pos, neg)
+        draws = self._draws(model_masks, d_masks1, d_masks2, gumbel_u, alpha)
+        if self._graph is not None and self.steady():
+            for dst, src in zip(self._flat(self._static), self._flat(draws)):
+                dst.copy_(src)
+            self._graph.replay()
+            self.D.step += 1
+            self.idx += 1
+            return self._static_out
+        out = self._body(*draws)
+        if self._new_graphs is not None:
+            self.hs.graphs = self._new_graphs
+        self.idx += 1
+        return out
+
+    # -------------------------------------------------------------- CUDA graph of the steady state
+    _graph = None
+
+    @staticmethod
+    def _flat(draws):
+        mm, m1, m2, gu, al = draws
+        return [*mm, *m1, *m2, gu, al]
+
+    def steady(self) -> bool:
+        """True when an iteration leaves the graphs as they are and collects nothing: the modality graphs are empty, the pair
+        lists are empty and this iteration is on the rebuild branch (with the default T = 1: every iteration from the 4th of
+        an epoch on; with m_topk_rate * n_items < 1, as at Baby, from the 3rd of the FIRST epoch on, for the whole run)."""
+        rebuild = self.idx % self.cfg.T == 0 and self.idx != 0
+        empty = not self.pairs["image"] and not self.pairs["text"] and all(g.nnz == 0 for g in self.hs.graphs[2:])
+        return empty and (rebuild or self.k == 0)
+
+    def capture(self) -> None:
+        """Capture one steady-state iteration (D step + G step + both optimisers, ~150 launches) into a CUDA graph; ``step``
+        replays it whenever ``steady()`` holds and runs eagerly otherwise (first iterations of an epoch).  The random draws
+        are static input buffers refilled before every replay (by torch's generator, or by the caller's injected draws).
+        EXPERIMENTAL: written without GPU access, first run is a round-2 task."""
+        if not self.steady():
+            raise RuntimeError("capture() needs the steady state: run the first iterations of the epoch eagerly")
+        self._static = self._draws(None, None, None, None, None)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):                           # warm-up: every lazily created buffer exists before the capture
+            self._body(*self._static)
+            self.idx += 1
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        step_before = self.D.step
+        with torch.cuda.graph(g):
+            self._static_out = self._body(*self._static)
+        self.D.step = step_before                            # the capture pass does not execute
+        self._graph = g

@@ -49,6 +49,7 @@ class DiscriminatorState:
         self.m = {k: torch.zeros_like(self.t[k]) for k in PARAMS}
         self.v = {k: torch.zeros_like(self.t[k]) for k in PARAMS}
         self.step = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.t[PARAMS[0]].device)     # the same count, on the device
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return dict(self.t)
@@ -159,7 +160,7 @@ def d_step(K, D: DiscriminatorState, hp: GanHyper, image_sim, text_sim, ui_sim, 
     gp = gradient_penalty(K, D, inter, masks1[2], masks2[2], hp.gp_lambda, grads, hp.gp_rate)
     D.step += 1
     K.adam([D.t[k] for k in PARAMS], [grads[k] for k in PARAMS], [D.m[k] for k in PARAMS], [D.v[k] for k in PARAMS], D.step,
-           hp.D_lr, hp.beta1, hp.beta2)
+           hp.D_lr, hp.beta1, hp.beta2, step_dev=D.step_dev)
     return dict(gp=gp, lossf_sum=cf["s_sum"], lossr_sum=cr["s_sum"], grads=grads, n=n)
 
 

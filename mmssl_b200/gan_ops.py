@@ -170,7 +170,12 @@ def interpolate(alpha, xr, xf):
     return out
 
 
-def adam(params, grads, ms, vs, step, lr, b1, b2, eps=1e-8):
-    """torch.optim.Adam without weight decay == the library's AdamW kernel with weight_decay = 0."""
-    step_dev = torch.tensor([int(step)], dtype=torch.int32, device=params[0].device)
+def adam(params, grads, ms, vs, step, lr, b1, b2, eps=1e-8, step_dev=None):
+    """torch.optim.Adam without weight decay == the library's AdamW kernel with weight_decay = 0.  ``step_dev`` (int32 device
+    scalar holding step - 1) is advanced by a kernel, so the call is CUDA-graph capturable; without it the counter is uploaded
+    from the host value (one small H2D copy per call)."""
+    if step_dev is None:
+        step_dev = torch.tensor([int(step)], dtype=torch.int32, device=params[0].device)
+    else:
+        ops.step_tick(step_dev)
     ops.adamw(list(params), [_c(g) for g in grads], list(ms), list(vs), step_dev, lr, b1, b2, eps, 0.0)

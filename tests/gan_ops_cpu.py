@@ -130,7 +130,7 @@ def interpolate(alpha, xr, xf):
     return a * xr + (1 - a) * xf
 
 
-def adam(params, grads, ms, vs, step, lr, b1, b2, eps=1e-8):
+def adam(params, grads, ms, vs, step, lr, b1, b2, eps=1e-8, step_dev=None):
     for p, g, m, v in zip(params, grads, ms, vs):
         m.mul_(b1).add_(g, alpha=1 - b1)
         v.mul_(b2).addcmul_(g, g, value=1 - b2)

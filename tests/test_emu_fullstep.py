@@ -14,6 +14,15 @@ def test_full_step_matches_reference_trace(monkeypatch, proj_impl):
     fs = fullstep_check.run_and_check(dev="cpu", proj_impl=proj_impl)
     # T = 1: iteration 0 collected pairs, iteration 1 built graphs from them, iteration 2 rebuilt from empty lists
     assert fs.idx == 3 and fs.hs.graphs[2].nnz == 0 and fs.hs.graphs[4].nnz == 0
+    # ... and from here on nothing changes any more: the iteration is a fixed sequence of launches (CUDA-graph capturable)
+    assert fs.steady()
+    g_before = fs.hs.graphs
+    z, c = fullstep_check.load_trace()
+    import numpy as np
+    import torch
+    t = lambda a: torch.from_numpy(np.asarray(a)).clone()
+    out = fs.step(*(t(z["sample"][0][j]) for j in range(3)))
+    assert fs.hs.graphs is g_before and fs.steady() and bool(torch.isfinite(out["batch_loss"]))
 
 
 @pytest.fixture(params=["fwd", "rev"])

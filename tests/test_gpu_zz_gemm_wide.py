@@ -45,3 +45,48 @@ def test_gan_side_on_tensor_cores(monkeypatch):
     G.test_d_step_on_gpu_matches_reference_trace()
     G.test_usim_and_real_rows(19445, 7050, 1024, 64)
     fullstep_check.run_and_check(dev="cuda", proj_impl="tc")
+
+
+def test_full_step_cuda_graph_replay_equals_eager():
+    """FullStep.capture(): the steady-state iteration as one CUDA graph == the same iterations run eagerly (same injected draws)."""
+    import numpy as np
+    from mmssl_b200.engine import LIVE
+    from tests import fullstep_check
+    z, c = fullstep_check.load_trace()
+    runs = []
+    for use_graph in (False, True):
+        fs, P, t = fullstep_check.build(z, c, "cuda")
+        torch.manual_seed(1)
+        for s in range(3):                                   # the three recorded iterations bring the step into its steady state
+            fs.step(*(t(z["sample"][s][j]) for j in range(3)))
+        assert fs.steady()
+        if use_graph:
+            fs.capture()                                     # one warm-up iteration with its own draws + the capture
+        else:
+            torch.manual_seed(99)
+            fs.step(*(t(z["sample"][0][j]) for j in range(3)))     # stands for the warm-up iteration; draws differ -> compare from a reset
+        runs.append((fs, P))
+    # identical starting point for the comparison: copy the eager twin's state into the graph twin
+    (fe, Pe), (fg, Pg) = runs
+    for k in LIVE:
+        Pg[k].copy_(Pe[k]); fg.hs.m[k].copy_(fe.hs.m[k]); fg.hs.v[k].copy_(fe.hs.v[k])
+    fg.hs.step_dev.copy_(fe.hs.step_dev)
+    from mmssl_b200 import gan
+    for k in gan.PARAMS + gan.BUFFERS:
+        fg.D.t[k].copy_(fe.D.t[k])
+    for k in gan.PARAMS:
+        fg.D.m[k].copy_(fe.D.m[k]); fg.D.v[k].copy_(fe.D.v[k])
+    fg.D.step_dev.copy_(fe.D.step_dev); fg.D.step = fe.D.step
+    g = torch.Generator().manual_seed(5)
+    B, I, d = c["B"], c["I"], c["d"]
+    for s in range(3):
+        mk = lambda n, w, p: ((torch.rand(n, w, generator=g) >= p) / (1 - p)).float().cuda()
+        draws = dict(model_masks=[mk(I, d, 0.2) for _ in range(4)], d_masks1=[mk(2 * B, I // 4, 0.31) for _ in range(4)],
+                     d_masks2=[mk(2 * B, I // 8, 0.5) for _ in range(4)], gumbel_u=torch.rand(B, I, generator=g).cuda(),
+                     alpha=torch.rand(2 * B, generator=g).cuda())
+        batch = [t(z["sample"][s][j]) for j in range(3)]
+        oe, og = fe.step(*batch, **draws), fg.step(*batch, **draws)
+        for k in ("batch_loss", "gp", "loss_D"):
+            assert abs(float(oe[k]) - float(og[k])) <= 1e-5 * abs(float(oe[k])) + 1e-7, (s, k)
+    for k in LIVE:
+        assert rel_err(Pg[k], Pe[k]) < 1e-5, k
