@@ -83,9 +83,11 @@ def d_backward(K, D: DiscriminatorState, c: Dict[str, torch.Tensor], coef: float
     da1, dy1, dg1, dbe1 = K.bn_bwd(dh1, c["m1"], t["net.2.weight"], c["ah1"], c["r1"])
     if grads is not None:
         for k, g in (("net.8.weight", dw3.view_as(t["net.8.weight"])), ("net.8.bias", db3), ("net.6.weight", dg2), ("net.6.bias", dbe2),
-                     ("net.4.weight", K.mm(da2, c["h1"], ta=True)), ("net.4.bias", K.colsum(da2)), ("net.2.weight", dg1),
-                     ("net.2.bias", dbe1), ("net.0.weight", K.mm(da1, c["x"], ta=True)), ("net.0.bias", K.colsum(da1))):
+                     ("net.4.bias", K.colsum(da2)), ("net.2.weight", dg1), ("net.2.bias", dbe1), ("net.0.bias", K.colsum(da1))):
             K.add_scaled(grads[k], g, scale)
+        # the two weight gradients accumulate in the GEMM epilogue: no [I/4, I] temporary, no extra pass over it
+        K.mm_acc(grads["net.4.weight"], da2, c["h1"], ta=True, alpha=scale)
+        K.mm_acc(grads["net.0.weight"], da1, c["x"], ta=True, alpha=scale)
     if keep is not None:
         keep.update(dz=dz, dy2=dy2, da2=da2, dy1=dy1, da1=da1)
     return K.mm(da1, t["net.0.weight"]) if need_dx else None
@@ -102,11 +104,11 @@ def gradient_penalty(K, D: DiscriminatorState, inter: torch.Tensor, m1, m2, lam:
     gp, gbar = K.gp_rows(gx, lam)
     # reverse of the first-order backward sweep
     q1 = K.mm(gbar, t["net.0.weight"], tb=True)
-    K.add_scaled(grads["net.0.weight"], K.mm(k["da1"], gbar, ta=True), scale)
+    K.mm_acc(grads["net.0.weight"], k["da1"], gbar, ta=True, alpha=scale)
     dh1_bar, ah1_bar, r1_bar, gg1 = K.gp_rev_bn(q1, k["dy1"], c["ah1"], c["r1"], t["net.2.weight"], c["m1"])
     K.add_scaled(grads["net.2.weight"], gg1, scale)
     q2 = K.mm(dh1_bar, t["net.4.weight"], tb=True)
-    K.add_scaled(grads["net.4.weight"], K.mm(k["da2"], dh1_bar, ta=True), scale)
+    K.mm_acc(grads["net.4.weight"], k["da2"], dh1_bar, ta=True, alpha=scale)
     dh2_bar, ah2_bar, r2_bar, gg2 = K.gp_rev_bn(q2, k["dy2"], c["ah2"], c["r2"], t["net.6.weight"], c["m2"])
     K.add_scaled(grads["net.6.weight"], gg2, scale)
     # reverse of the forward sweep, seeded with the adjoints collected above
@@ -116,13 +118,13 @@ def gradient_penalty(K, D: DiscriminatorState, inter: torch.Tensor, m1, m2, lam:
     a2_bar, gg2b, gbe2 = K.bn_fwd_rev(h_bar, c["m2"], t["net.6.weight"], c["ah2"], c["r2"], ah2_bar, r2_bar)
     K.add_scaled(grads["net.6.weight"], gg2b, scale)
     K.add_scaled(grads["net.6.bias"], gbe2, scale)
-    K.add_scaled(grads["net.4.weight"], K.mm(a2_bar, c["h1"], ta=True), scale)
+    K.mm_acc(grads["net.4.weight"], a2_bar, c["h1"], ta=True, alpha=scale)
     K.add_scaled(grads["net.4.bias"], K.colsum(a2_bar), scale)
     h1_bar = K.mm(a2_bar, t["net.4.weight"])
     a1_bar, gg1b, gbe1 = K.bn_fwd_rev(h1_bar, c["m1"], t["net.2.weight"], c["ah1"], c["r1"], ah1_bar, r1_bar)
     K.add_scaled(grads["net.2.weight"], gg1b, scale)
     K.add_scaled(grads["net.2.bias"], gbe1, scale)
-    K.add_scaled(grads["net.0.weight"], K.mm(a1_bar, c["x"], ta=True), scale)
+    K.mm_acc(grads["net.0.weight"], a1_bar, c["x"], ta=True, alpha=scale)
     K.add_scaled(grads["net.0.bias"], K.colsum(a1_bar), scale)
     return gp
 
@@ -139,7 +141,7 @@ def u_sim_backward(K, c: Dict[str, torch.Tensor], g: torch.Tensor, item_final, i
     """Adds the gradients of ``sum(g * u_sim)`` into the full [U, d] / [I, d] gradient tables."""
     d_raw = K.usim_bwd_pre(g, c["y"], c["nrm"], c["users"], indptr, indices)
     K.scatter_add_rows(g_user_final, c["users"], K.mm(d_raw, item_final))
-    K.add_scaled(g_item_final, K.mm(d_raw, c["ub"], ta=True), 1.0)
+    K.mm_acc(g_item_final, d_raw, c["ub"], ta=True, alpha=1.0)
 
 
 # ------------------------------------------------------------------------------------------ the two entry points

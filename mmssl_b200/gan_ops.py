@@ -44,6 +44,20 @@ def mm(a, b, ta=False, tb=False, alpha=1.0):
     return ops.sgemm(a, b, _new(m, n, like=a), trans_a=ta, trans_b=tb, alpha=alpha)
 
 
+def mm_acc(dst, a, b, ta=False, tb=False, alpha=1.0):
+    """dst += alpha * op(a) @ op(b), accumulated in the GEMM epilogue (no temporary)."""
+    a, b = _c(a), _c(b)
+    assert dst.is_contiguous() and dst.dim() == 2
+    m, n = dst.shape
+    if GEMM_IMPL == "tc":
+        k = a.shape[0] if ta else a.shape[1]
+        a_hi, a_lo = ops.split_bf16_t(a) if ta else ops.split_bf16(a)
+        b_hi, b_lo = ops.split_bf16(b) if tb else ops.split_bf16_t(b)
+        ops.gemm_bf16x3_wide(a_hi, a_lo, b_hi, b_lo, m, n, k, dst, alpha=alpha, accumulate=True)
+    else:
+        ops.sgemm(a, b, dst, trans_a=ta, trans_b=tb, alpha=alpha, beta=1.0)
+
+
 def gather_rows(table, users):
     table = _c(table)
     out = _new(users.numel(), table.shape[1], like=table)

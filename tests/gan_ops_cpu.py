@@ -12,6 +12,11 @@ def mm(a, b, ta=False, tb=False, alpha=1.0):
     return alpha * ((a.T if ta else a) @ (b.T if tb else b))
 
 
+def mm_acc(dst, a, b, ta=False, tb=False, alpha=1.0):
+    """dst += alpha * op(a) @ op(b)"""
+    dst.add_(mm(a, b, ta, tb, alpha))
+
+
 def gather_rows(table, users):
     return table[users]
 
