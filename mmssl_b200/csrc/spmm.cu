@@ -30,10 +30,14 @@ namespace mmssl {
 // UNR neighbour gathers are issued back to back before the first FMA consumes one, and the next
 // chunk of (col, val) pairs is prefetched while the current one is processed, so a row walk costs
 // about one memory round trip per UNR non-zeros instead of one per load.
-template <int G, int C, int R, int UMUL, int MINB>
+// PRE (impl bit 6, candidate awaiting measurement): the row-indexed epilogue operands -- alpha*C[row], the saved softmax
+// output, the running-sum base -- are requested as soon as the work item is known, so that they travel while the
+// index -> gather chain runs instead of adding one more dependent round trip after it.  Only for R*C <= 2 (register cost).
+template <int G, int C, int R, int UMUL, int MINB, bool PRE = false>
 __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p) {
     pdl_wait();
     constexpr int RC = R * C;
+    constexpr bool PRE_ON = PRE && RC <= 2;
     constexpr int UNR0 = ((8 / RC) >= 2 ? (8 / RC) : 2) * UMUL;
     constexpr int UNR = UNR0 > G ? G : UNR0;
     const unsigned gmask = group_mask<G>();
@@ -44,6 +48,21 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
     const int row = item.x;
     if (row < 0) return;   // whole group exits together (items are per group)
     const int begin = item.y, end = item.z;
+
+    float4 pre_c[PRE_ON ? R : 1][PRE_ON ? C : 1], pre_e[PRE_ON ? R : 1][PRE_ON ? C : 1];
+    if (PRE_ON) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int64_t cofs = lane * 4 + c * (4 * G);
+                pre_c[r][c] = (p.has_c && p.c[r] != nullptr) ? ld4(p.c[r] + (int64_t)row * p.ldc[r] + cofs) : f4zero();
+                if (p.epilogue == MMSSL_EPI_SOFTMAX_BWD) pre_e[r][c] = ldg4(p.ys[r] + (int64_t)row * p.ldys[r] + cofs);
+                else if (p.s_mode == 1 && p.s[r] != nullptr) pre_e[r][c] = ld4(p.s[r] + (int64_t)row * p.lds[r] + cofs);
+                else if (p.s_mode == 2 && p.s[r] != nullptr) pre_e[r][c] = ldg4(p.sb[r] + (int64_t)row * p.ldsb[r] + cofs);
+                else pre_e[r][c] = f4zero();
+            }
+    }
 
     float4 acc[R][C];
 #pragma unroll
@@ -166,7 +185,7 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
         if (p.has_c && p.c[r] != nullptr) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const float4 cv = ld4(p.c[r] + (int64_t)row * p.ldc[r] + col0 + c * (4 * G));   // may alias Y
+                const float4 cv = PRE_ON ? pre_c[r][c] : ld4(p.c[r] + (int64_t)row * p.ldc[r] + col0 + c * (4 * G));   // may alias Y
                 fma4(acc[r][c], p.alpha, cv);
             }
         }
@@ -191,7 +210,7 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
             float dotp = 0.f;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                yv[c] = ldg4(p.ys[r] + (int64_t)row * p.ldys[r] + col0 + c * (4 * G));
+                yv[c] = PRE_ON ? pre_e[r][c] : ldg4(p.ys[r] + (int64_t)row * p.ldys[r] + col0 + c * (4 * G));
                 dotp += dot4(acc[r][c], yv[c]);
             }
             dotp = group_sum<G>(dotp, gmask);
@@ -217,28 +236,31 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 float* sp = p.s[r] + (int64_t)row * p.lds[r] + col0 + c * (4 * G);
-                const float4 prev = (p.s_mode == 1) ? ld4(sp)
-                                                    : ldg4(p.sb[r] + (int64_t)row * p.ldsb[r] + col0 + c * (4 * G));
+                const float4 prev = PRE_ON ? pre_e[r][c]
+                                           : (p.s_mode == 1) ? ld4(sp) : ldg4(p.sb[r] + (int64_t)row * p.ldsb[r] + col0 + c * (4 * G));
                 st4(sp, add4(prev, acc[r][c]));
             }
         }
     }
 }
 
-template <int G, int C, int R, int UMUL, int MINB>
+template <int G, int C, int R, int UMUL, int MINB, bool PRE = false>
 static int launch_spmm_v(const SpmmParams& p, cudaStream_t stream, int T) {
     const int64_t groups_per_block = T / G;
     const int64_t blocks = (p.n_items + groups_per_block - 1) / groups_per_block;
     if (blocks == 0) return 0;
     if (blocks > 0x7fffffffll) return fail("mmssl_spmm_csr_f32", "grid too large");
-    MMSSL_CUDA_LAUNCH((spmm_csr_kernel<G, C, R, UMUL, MINB>), dim3((unsigned)blocks), dim3(T), 0, stream, p);
+    MMSSL_CUDA_LAUNCH((spmm_csr_kernel<G, C, R, UMUL, MINB, PRE>), dim3((unsigned)blocks), dim3(T), 0, stream, p);
     MMSSL_LAUNCH_OK();
     return 0;
 }
 
-// impl bit 3 (8): twice as many gathers in flight per lane; bit 4 (16): cap registers for 6 blocks/SM
+// impl bit 3 (8): twice as many gathers in flight per lane; bit 4 (16): cap registers for 6 blocks/SM;
+// bit 6 (64): early epilogue-operand prefetch (only with the two policy defaults, i.e. bit 3 clear)
 template <int G, int C, int R>
 static int launch_spmm(const SpmmParams& p, cudaStream_t stream, int T, int impl) {
+    if ((impl & 64) && R * C <= 2 && !(impl & 8))
+        return (impl & 16) ? launch_spmm_v<G, C, R, 1, 6, true>(p, stream, T) : launch_spmm_v<G, C, R, 1, 1, true>(p, stream, T);
     switch ((impl >> 3) & 3) {
         case 1: return launch_spmm_v<G, C, R, 2, 1>(p, stream, T);
         case 2: return launch_spmm_v<G, C, R, 1, 6>(p, stream, T);

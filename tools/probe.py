@@ -61,6 +61,13 @@ def small(name):
         out[f"ui_impl{impl}_us"] = round(graph_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu], impl=impl), inner=20), 2)
         out[f"iu_impl{impl}_us"] = round(graph_time(lambda: ops.spmm(g_iu.fwd, [yu], [yi], impl=impl), inner=20), 2)
         out[f"ui2_impl{impl}_us"] = round(graph_time(lambda: ops.spmm(g_ui.fwd, [x2[:, :d], x2[:, d:]], [y2[:, :d], y2[:, d:]], impl=impl), inner=20), 2)
+    # the GCN-layer forms of the call (epilogue operands indexed by the row): default vs early prefetch (impl bit 6)
+    su = torch.zeros(U, d, device=dev); cu = torch.randn(U, d, device=dev); ysv = torch.softmax(torch.randn(U, d, device=dev), -1)
+    for impl in (4, 68, 16, 80):
+        out[f"gcn_fwd_impl{impl}_us"] = round(graph_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu], epilogue=ops.EPI_SOFTMAX, ss=[su], s_mode=1,
+                                                                          impl=impl), inner=20), 2)
+        out[f"gcn_bwd_impl{impl}_us"] = round(graph_time(lambda: ops.spmm(g_iu.bwd, [xi], [yu], cs=[cu], alpha=0.33, epilogue=ops.EPI_SOFTMAX_BWD,
+                                                                          ysaved=[ysv], impl=impl), inner=20), 2)
     out["axpby_in_graph_us"] = graph_time(lambda: ops.axpby(xi, 1.0, 0.0, yi), inner=40)     # ~launch floor
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)
     out["spmm_ui_cold_us"] = cold_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu]), flush)
