@@ -29,7 +29,7 @@ def test_bpr(emu, d):
     T.test_bpr_fused_and_autograd(d)
 
 
-@pytest.mark.parametrize("n,d", [(64, 64), (257, 64), (130, 128), (96, 256)])
+@pytest.mark.parametrize("n,d", [(64, 64), (257, 64), (130, 128), (96, 256), (1500, 64)])
 def test_infonce(emu, n, d):
     T.test_infonce_forward_backward(n, d)
 

@@ -361,8 +361,10 @@ def test_bpr_fused_and_autograd(d):
         assert rel_err(got, want) < 2e-5
 
 
-@pytest.mark.parametrize("n,d", [(64, 64), (257, 64), (1024, 64), (130, 128), (96, 256)])
+@pytest.mark.parametrize("n,d", [(64, 64), (257, 64), (1024, 64), (130, 128), (96, 256), (1500, 64), (2304, 128)])
 def test_infonce_forward_backward(n, d):
+    """(1500, 64), (2304, 128): more rows than one 1024-block of main.py:228-246, not a multiple of it (SURVEY 8c edge case);
+    the reference's double loop over blocks equals the full matrix (oracle.infonce_literal == oracle.infonce)."""
     from oracle import mmssl_oracle as O
     from mmssl_b200.functional import batched_contrastive_loss
     torch.manual_seed(7)
