@@ -317,6 +317,36 @@ def cpu_baseline(name, seed, steps, batch, threads=0):
             "cpu_model": model, "os_cpu_count": os.cpu_count(), "s_per_step": round(med, 4)}
 
 
+def cpu_full_step_baseline(name, seed, steps, batch, d_state, threads=0):
+    """Same role as ``cpu_baseline`` for the whole training iteration (main.py:333-434, oracle/gan_oracle.py:FullStep): used by
+    tools/fullstep_bench.py, not by this file's own bench line.  ``d_state``: the Discriminator's initial state_dict (CPU)."""
+    from oracle import gan_oracle as GO, mmssl_oracle as O
+    from mmssl_b200.synthetic import TripleSampler
+    ds, P, feats_cpu, _, _ = build_problem(name, seed, None)
+    torch.set_num_threads(min(os.cpu_count(), threads if threads > 0 else CPU_THREADS_DEFAULT))
+    d, I = ds.embed_size, ds.n_items
+    h1, h2 = int(I / 4), int(I / 8)
+    cfg = O.HotPathConfig(embed_size=d, n_layers=ds.n_layers, batch_size=batch)
+    R = ds.train.tocsr()
+    R.sort_indices()
+    cpu = GO.FullStep({k: v.clone() for k, v in P.items()}, {k: v.clone() for k, v in d_state.items()}, feats_cpu[0], feats_cpu[1], R, cfg,
+                      GO.GanConfig())
+    smp = TripleSampler(ds.train, seed=seed)
+    gen = torch.Generator().manual_seed(seed + 3)
+    mk = lambda n, w, q: ((torch.rand(n, w, generator=gen) >= q) / (1 - q)).float()
+    times = []
+    for i in range(steps):
+        u, p, n = smp.sample(batch)
+        draws = ([mk(I, d, 0.2) for _ in range(4)], [mk(2 * batch, h1, 0.31) for _ in range(4)], [mk(2 * batch, h2, 0.5) for _ in range(4)],
+                 torch.rand(batch, I, generator=gen), torch.rand(2 * batch, 1, generator=gen))
+        t0 = time.perf_counter()
+        cpu.step(u.tolist(), p.tolist(), n.tolist(), *draws)
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": round(batch / med, 1), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} full iterations (oracle/gan_oracle.py:FullStep) of config '{name}' (B={batch}), median", "s_per_step": round(med, 4)}
+
+
 # ----------------------------------------------------------------------------------------------
 def main():
     a = parse()

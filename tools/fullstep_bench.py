@@ -87,21 +87,6 @@ res = {"metric": "bpr_triples_per_sec_full_step", "unit": "triples/s", "value": 
        "gpu_launches_per_step": launches, "batch_loss": float(out["batch_loss"]), "loss_D": float(out["loss_D"]),
        "big_gemm_gflop_per_step": 11 * 2 * 2 * B * I * h1 / 1e9}
 
-if a.cpu_steps > 0:          # the oracle's restatement of the same iteration on the host (all threads), a bounded sample
-    import scipy.sparse as sp  # noqa: F401
-    from oracle import gan_oracle as GO, mmssl_oracle as O
-    ocfg = O.HotPathConfig(embed_size=d, n_layers=ds.n_layers, batch_size=B)
-    _, Pc, fc, _, _ = bench.build_problem(a.config, a.seed, None)
-    cpu = GO.FullStep({k: v.clone() for k, v in Pc.items()}, {k: v.clone() for k, v in S_cpu.items()}, fc[0], fc[1], R, ocfg, GO.GanConfig())
-    gen = torch.Generator().manual_seed(3)
-    p = 0.2
-    mk = lambda n, w, q: ((torch.rand(n, w, generator=gen) >= q) / (1 - q)).float()
-    t0 = time.time()
-    for s in range(a.cpu_steps):
-        u, po, ne = (x.cpu() for x in batches[s % len(batches)])
-        cpu.step(u.tolist(), po.tolist(), ne.tolist(), [mk(I, d, p) for _ in range(4)], [mk(2 * B, h1, 0.31) for _ in range(4)],
-                 [mk(2 * B, h2, 0.5) for _ in range(4)], torch.rand(B, I, generator=gen), torch.rand(2 * B, 1, generator=gen))
-    dt = (time.time() - t0) / a.cpu_steps
-    res["cpu_baseline"] = {"value": B / dt, "unit": "triples/s", "cores": torch.get_num_threads(), "kind": "port",
-                           "sample": f"{a.cpu_steps} full iterations of oracle/gan_oracle.py:FullStep"}
+if a.cpu_steps > 0:          # the oracle's restatement of the same iteration on the host cores, a bounded sample (bench.py owns that leg)
+    res["cpu_baseline"] = bench.cpu_full_step_baseline(a.config, a.seed, a.cpu_steps, B, S_cpu)
 print(json.dumps(res))
