@@ -46,7 +46,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--config", default="baby")
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "stock-gpu"],
+                    help="'stock-gpu': comparator only -- the reference's torch ops (torch.sparse.mm, nn.Linear math, autograd, torch AdamW) on THIS GPU")
     ap.add_argument("--proj", default="tc", choices=["tc", "simt"])
     ap.add_argument("--spmm-impl", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -317,6 +318,40 @@ def cpu_baseline(name, seed, steps, batch, threads=0):
             "cpu_model": model, "os_cpu_count": os.cpu_count(), "s_per_step": round(med, 4)}
 
 
+def stock_gpu_baseline(name, seed, steps, warmup, batch, device):
+    """SURVEY 8d's second comparator: what the unmodified reference's hot path costs on the same B200 through stock PyTorch
+    (cuSPARSE / cuBLAS / ATen element-wise kernels, autograd, torch.optim.AdamW, one float(loss) sync per step like
+    main.py:431) -- the restatement in oracle/mmssl_oracle.py run on CUDA tensors.  A comparator, not the product and not the
+    target; timed with CUDA events around `steps` steps after `warmup`."""
+    from oracle import mmssl_oracle as O
+    from mmssl_b200.synthetic import TripleSampler
+    ds, P, feats_cpu, _, _ = build_problem(name, seed, None)
+    cfg = O.HotPathConfig(embed_size=ds.embed_size, n_layers=ds.n_layers, batch_size=batch)
+    ui, iu = O.to_torch_coo(ds.ui_norm).to(device), O.to_torch_coo(ds.iu_norm).to(device)
+    step = O.CpuHotStep({k: v.to(device) for k, v in P.items()}, feats_cpu[0].to(device), feats_cpu[1].to(device),
+                        (ui, iu, ui, iu, ui, iu), ds.n_items, cfg)
+    smp = TripleSampler(ds.train, seed=seed)
+    batches = [tuple(torch.from_numpy(x).to(device) for x in smp.sample(batch)) for _ in range(8)]
+    for i in range(warmup):
+        step.step(*batches[i % 8])
+    cuda = torch.device(device).type == "cuda"
+    if cuda:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step.step(*batches[i % 8])
+    if cuda:
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    else:
+        ms = (time.perf_counter() - t0) / steps * 1e3
+    return {"value": round(batch / ms * 1e3, 1), "unit": UNIT, "ms_per_step": round(ms, 4), "kind": "stock torch %s on %s" % (torch.__version__, device),
+            "sample": f"{steps} hot steps of config '{name}' (B={batch}) after {warmup} warm-up"}
+
+
 def cpu_full_step_baseline(name, seed, steps, batch, d_state, threads=0):
     """Same role as ``cpu_baseline`` for the whole training iteration (main.py:333-434, oracle/gan_oracle.py:FullStep): used by
     tools/fullstep_bench.py, not by this file's own bench line.  ``d_state``: the Discriminator's initial state_dict (CPU)."""
@@ -373,6 +408,15 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
+        return
+
+    if a.impl == "stock-gpu":
+        if rank != 0:
+            return
+        sg = stock_gpu_baseline(a.config, a.seed, min(a.steps, 200), max(a.warmup, 3), BATCH, os.environ.get("MMSSL_STOCK_DEVICE", "cuda:0"))
+        print(json.dumps({"impl": "stock-torch-gpu", "metric": METRIC, "value": sg["value"], "unit": UNIT, "n_gpus": 1, "steps": min(a.steps, 200),
+                          "warmup": max(a.warmup, 3), "ms_per_step": sg["ms_per_step"], "higher_is_better": True, "dtype": "f32",
+                          "data": "synthetic", "config": config, "comparator": sg}))
         return
 
     torch.cuda.set_device(local)
