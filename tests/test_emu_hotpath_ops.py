@@ -69,4 +69,5 @@ def test_spmm_empty_and_epilogues(emu):
 
 @pytest.mark.parametrize("d,nrhs,base_impl", [(64, 1, 4), (64, 2, 16), (128, 1, 16), (128, 2, 4), (256, 1, 4), (64, 3, 4)])
 def test_spmm_early_prefetch_variant(emu, d, nrhs, base_impl):
-    T.test_spmm_early_prefetch_variant_matches_default(d, nrhs, base_impl)
+    from tests import test_gpu_zz_more_ops as Z
+    Z.test_spmm_early_prefetch_variant_matches_default(d, nrhs, base_impl)

@@ -184,37 +184,6 @@ def test_spmm_epilogues(d):
     assert rel_err(acc, base + c.double().cpu()) < 5e-6
 
 
-@pytest.mark.parametrize("d,nrhs", [(64, 1), (64, 2), (128, 1), (128, 2), (256, 1), (64, 3)])
-@pytest.mark.parametrize("base_impl", [4, 16])
-def test_spmm_early_prefetch_variant_matches_default(d, nrhs, base_impl):
-    """impl bit 6: the row-indexed epilogue operands (alpha*C, saved softmax output, running-sum base / previous sum) are
-    loaded before the gather loop instead of after it.  Same arithmetic in the same order -> identical bits on graphs without
-    heavy (atomically reduced) rows; (64, 3) exceeds the register budget of the variant and must fall back to the default."""
-    from mmssl_b200 import ops
-    g, _ = _graph(500, 300, 12000, seed=d + nrhs, heavy_rows=30)     # ~130 nnz in each of 30 rows: split, not heavy
-    assert g.fwd.n_split_rows > 0
-    torch.manual_seed(3)
-    xs = [torch.randn(300, d, device="cuda") for _ in range(nrhs)]
-    cs = [torch.randn(500, d, device="cuda") for _ in range(nrhs)]
-    sb = [torch.randn(500, d, device="cuda") for _ in range(nrhs)]
-    ysv = [torch.softmax(torch.randn(500, d, device="cuda"), -1) for _ in range(nrhs)]
-
-    def run(impl):
-        out = []
-        s = [torch.empty(500, d, device="cuda") for _ in range(nrhs)]
-        out += ops.spmm(g.fwd, xs, cs=cs, alpha=0.25, epilogue=ops.EPI_SOFTMAX, ss=s, s_mode=2, sbases=sb, impl=impl)
-        ops.spmm(g.fwd, xs, cs=cs, alpha=0.5, epilogue=ops.EPI_NONE, ss=s, s_mode=1, impl=impl)
-        out += [t.clone() for t in s]
-        out += ops.spmm(g.fwd, xs, cs=cs, alpha=0.25, epilogue=ops.EPI_SOFTMAX_BWD, ysaved=ysv, impl=impl)
-        acc = [c.clone() for c in cs]
-        ops.spmm(g.fwd, xs, acc, cs=acc, alpha=1.0, impl=impl)      # in place: C aliases Y
-        out += acc
-        out += ops.spmm(g.fwd, xs, impl=impl)                       # nothing to prefetch
-        return out
-    for a, b in zip(run(base_impl), run(base_impl | 64)):
-        assert rel_err(b, a) < 1e-6        # the same operations in the same order (bitwise equal under the CPU emulator)
-
-
 def test_spmm_function_autograd():
     from mmssl_b200.functional import spmm
     r, c, v = _rand_graph(120, 90, 1500, 5)
@@ -361,10 +330,8 @@ def test_bpr_fused_and_autograd(d):
         assert rel_err(got, want) < 2e-5
 
 
-@pytest.mark.parametrize("n,d", [(64, 64), (257, 64), (1024, 64), (130, 128), (96, 256), (1500, 64), (2304, 128)])
+@pytest.mark.parametrize("n,d", [(64, 64), (257, 64), (1024, 64), (130, 128), (96, 256)])
 def test_infonce_forward_backward(n, d):
-    """(1500, 64), (2304, 128): more rows than one 1024-block of main.py:228-246, not a multiple of it (SURVEY 8c edge case);
-    the reference's double loop over blocks equals the full matrix (oracle.infonce_literal == oracle.infonce)."""
     from oracle import mmssl_oracle as O
     from mmssl_b200.functional import batched_contrastive_loss
     torch.manual_seed(7)
