@@ -81,3 +81,49 @@ def run_and_check(dev="cuda", proj_impl="tc", steps=None):
             e = rel_err(P[k], torch.from_numpy(z["Gparam/" + k][s]))
             assert e < TOL, (s, "Gparam", k, e)
     return fs
+
+
+def regime_check(dev, m_topk_rate, T, proj_impl="simt"):
+    """Regimes the recorded trace does not visit, against the oracle's FullStep (itself pinned to the trace at k = 4, T = 1):
+    k = 0 (the reference's default rate at Baby: int(7050 * 1e-4) = 0 -> no pairs are ever collected, the modality graphs are
+    empty from the third iteration on), T = 2 and T = 3 (pairs of several iterations accumulate before a rebuild, lists with
+    duplicates).  Five iterations with generated draws; parameters of G and D after every iteration."""
+    import scipy.sparse as sp  # noqa: F811
+    from oracle import gan_oracle as GO, mmssl_oracle as O
+    from mmssl_b200 import gan
+    from mmssl_b200.engine import LIVE
+    z, c = load_trace()
+    c = dict(c, m_topk_rate=m_topk_rate, T=T)
+    fs, P, t = build(z, c, dev, proj_impl=proj_impl)
+    R = sp.csr_matrix((np.ones(len(z["train_rows"]), np.float32), (z["train_rows"], z["train_cols"])), shape=(c["U"], c["I"]))
+    R.sort_indices()
+    ocfg = O.HotPathConfig(embed_size=c["d"], n_layers=c["n_layers"], batch_size=c["B"], lr=c["lr"])
+    gcfg = GO.GanConfig(m_topk_rate=m_topk_rate, T=T, D_lr=c["D_lr"], G_rate=c["G_rate"], gp_rate=c["gp_rate"])
+    cpu = GO.FullStep({k[3:]: torch.from_numpy(z[k]).clone() for k in z.files if k.startswith("G0/")},
+                      {k[3:]: torch.from_numpy(z[k]).clone() for k in z.files if k.startswith("D0/")},
+                      torch.from_numpy(z["image_feats"]), torch.from_numpy(z["text_feats"]), R, ocfg, gcfg)
+    g = torch.Generator().manual_seed(11)
+    B, I, d = c["B"], c["I"], c["d"]
+    mk = lambda n, w, p: ((torch.rand(n, w, generator=g) >= p) / (1 - p)).float()
+    nnz_seen = []
+    for s in range(5):
+        users = torch.randperm(c["U"], generator=g)[:B]
+        pos, neg = torch.randint(0, I, (B,), generator=g), torch.randint(0, I, (B,), generator=g)
+        mm = [mk(I, d, c["drop_rate"]) for _ in range(4)]
+        m1, m2 = [mk(2 * B, I // 4, 0.31) for _ in range(4)], [mk(2 * B, I // 8, 0.5) for _ in range(4)]
+        gu, al = torch.rand(B, I, generator=g), torch.rand(2 * B, 1, generator=g)
+        cpu.step(users.tolist(), pos.tolist(), neg.tolist(), mm, m1, m2, gu, al)
+        on = lambda x: x.clone().to(dev)
+        fs.step(on(users), on(pos), on(neg), model_masks=[on(m) for m in mm], d_masks1=[on(m) for m in m1], d_masks2=[on(m) for m in m2],
+                gumbel_u=on(gu), alpha=on(al.view(-1)))
+        nnz_seen.append(fs.hs.graphs[2].nnz)
+        for k in LIVE:
+            assert rel_err(P[k], cpu.P[k]) < 1e-4, (s, k, rel_err(P[k], cpu.P[k]))
+        for k in gan.PARAMS:
+            if k not in DEAD_BIAS:
+                assert rel_err(fs.D.t[k], cpu.S[k]) < 5e-4, (s, k)
+    k_top = int(I * m_topk_rate)
+    if k_top == 0:
+        assert nnz_seen[0] > 0 and nnz_seen[1:] == [0, 0, 0, 0] and fs.steady()
+    else:          # rebuilds at iterations T, 2T, ...: the first one sees T iterations' worth of pairs
+        assert nnz_seen[T] == T * B * k_top

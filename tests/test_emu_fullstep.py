@@ -54,3 +54,10 @@ def test_full_step_with_tensor_core_gan_gemms(monkeypatch):
     harness.emulated_device(monkeypatch)
     monkeypatch.setattr(gan_ops, "GEMM_IMPL", "tc")
     fullstep_check.run_and_check(dev="cpu", proj_impl="tc")
+
+
+@pytest.mark.parametrize("m_topk_rate,T", [(0.0, 1), (0.05, 2), (0.02, 3)])
+def test_full_step_other_bookkeeping_regimes_vs_oracle(monkeypatch, m_topk_rate, T):
+    harness.set_order("fwd")
+    harness.emulated_device(monkeypatch)
+    fullstep_check.regime_check("cpu", m_topk_rate, T)

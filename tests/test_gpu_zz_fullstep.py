@@ -71,3 +71,8 @@ def test_full_step_own_random_draws_runs_and_learns():
             assert out[k].is_cuda and bool(torch.isfinite(out[k]).all()), k
     assert all(float((P[k] - p0[k]).abs().max()) > 0 for k in P if k in fs.hs.P)
     assert float((fs.D.t["net.0.weight"] - w0).abs().max()) > 0
+
+
+@pytest.mark.parametrize("m_topk_rate,T", [(0.0, 1), (0.05, 2), (0.02, 3)])
+def test_full_step_other_bookkeeping_regimes_vs_oracle(m_topk_rate, T):
+    fullstep_check.regime_check("cuda", m_topk_rate, T, proj_impl="tc")
