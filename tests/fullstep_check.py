@@ -127,3 +127,57 @@ def regime_check(dev, m_topk_rate, T, proj_impl="simt"):
         assert nnz_seen[0] > 0 and nnz_seen[1:] == [0, 0, 0, 0] and fs.steady()
     else:          # rebuilds at iterations T, 2T, ...: the first one sees T iterations' worth of pairs
         assert nnz_seen[T] == T * B * k_top
+
+
+def random_problem_check(dev, d=128, U=150, I=97, B=24, n_layers=3, m_topk_rate=0.04, steps=3, proj_impl="simt"):
+    """A problem that shares nothing with the recorded trace -- other embedding width (other kernel instantiations), item count
+    not a multiple of 8 (Discriminator widths int(I/4), int(I/8)), 3 GCN layers -- product FullStep vs the oracle's FullStep."""
+    import scipy.sparse as sp  # noqa: F811
+    from oracle import gan_oracle as GO, mmssl_oracle as O
+    from mmssl_b200 import gan
+    from mmssl_b200.engine import LIVE, FeatureStore
+    from mmssl_b200.fullstep import FullStep, FullStepConfig
+    from mmssl_b200.graph import BipartiteGraph
+    from mmssl_b200.hotstep import HotStepConfig
+    from mmssl_b200.synthetic import csr_norm, make_bipartite
+    g = torch.Generator().manual_seed(d + I)
+    R = make_bipartite(U, I, 6 * U, seed=d).tocsr().astype(np.float32)
+    R.sort_indices()
+    xav = lambda a, b: (torch.rand(a, b, generator=g) * 2 - 1) * (6.0 / (a + b)) ** 0.5
+    dv, dt, h1, h2 = 20, 12, int(I / 4), int(I / 8)
+    P = {"image_trans.weight": xav(d, dv), "image_trans.bias": torch.randn(d, generator=g) * 0.1, "text_trans.weight": xav(d, dt),
+         "text_trans.bias": torch.randn(d, generator=g) * 0.1, "user_id_embedding.weight": xav(U, d), "item_id_embedding.weight": xav(I, d),
+         "weight_dict.w_self_attention_cat": xav(4 * d, d), "weight_dict.w_q": xav(d, d), "weight_dict.w_k": xav(d, d)}
+    kn = lambda o, i: torch.randn(o, i, generator=g) * (2.0 / i) ** 0.5
+    S = {"net.0.weight": kn(h1, I), "net.0.bias": torch.zeros(h1), "net.2.weight": torch.ones(h1), "net.2.bias": torch.zeros(h1),
+         "net.2.running_mean": torch.zeros(h1), "net.2.running_var": torch.ones(h1), "net.2.num_batches_tracked": torch.zeros((), dtype=torch.int64),
+         "net.4.weight": kn(h2, h1), "net.4.bias": torch.zeros(h2), "net.6.weight": torch.ones(h2), "net.6.bias": torch.zeros(h2),
+         "net.6.running_mean": torch.zeros(h2), "net.6.running_var": torch.ones(h2), "net.6.num_batches_tracked": torch.zeros((), dtype=torch.int64),
+         "net.8.weight": kn(1, h2), "net.8.bias": torch.zeros(1)}
+    feats = (torch.randn(I, dv, generator=g), torch.randn(I, dt, generator=g))
+    ocfg = O.HotPathConfig(embed_size=d, n_layers=n_layers, batch_size=B)
+    cpu = GO.FullStep({k: v.clone() for k, v in P.items()}, {k: v.clone() for k, v in S.items()}, feats[0], feats[1], R, ocfg,
+                      GO.GanConfig(m_topk_rate=m_topk_rate))
+    on = lambda x: x.clone().to(dev)
+    Pd = {k: on(v).contiguous() for k, v in P.items()}
+    cfg = FullStepConfig(hot=HotStepConfig(embed_size=d, n_layers=n_layers, batch_size=B, proj_impl=proj_impl), gan=gan.GanHyper(),
+                         m_topk_rate=m_topk_rate)
+    fs = FullStep(Pd, {k: on(v) for k, v in S.items()}, tuple(FeatureStore(on(f)) for f in feats), on(torch.from_numpy(R.indptr.astype(np.int64))),
+                  on(torch.from_numpy(R.indices.astype(np.int64))), BipartiteGraph.from_scipy(csr_norm(R), device=dev),
+                  BipartiteGraph.from_scipy(csr_norm(R.T.tocsr()), device=dev), cfg, batch=B)
+    mk = lambda n, w, p: ((torch.rand(n, w, generator=g) >= p) / (1 - p)).float()
+    for s in range(steps):
+        users = torch.randperm(U, generator=g)[:B]
+        pos, neg = torch.randint(0, I, (B,), generator=g), torch.randint(0, I, (B,), generator=g)
+        mm = [mk(I, d, 0.2) for _ in range(4)]
+        m1, m2 = [mk(2 * B, h1, 0.31) for _ in range(4)], [mk(2 * B, h2, 0.5) for _ in range(4)]
+        gu, al = torch.rand(B, I, generator=g), torch.rand(2 * B, 1, generator=g)
+        cpu.step(users.tolist(), pos.tolist(), neg.tolist(), mm, m1, m2, gu, al)
+        fs.step(on(users), on(pos), on(neg), model_masks=[on(m) for m in mm], d_masks1=[on(m) for m in m1], d_masks2=[on(m) for m in m2],
+                gumbel_u=on(gu), alpha=on(al.view(-1)))
+        for k in LIVE:
+            assert rel_err(Pd[k], cpu.P[k]) < TOL, (s, k, rel_err(Pd[k], cpu.P[k]))
+        for k in gan.PARAMS:
+            if k not in DEAD_BIAS:
+                assert rel_err(fs.D.t[k], cpu.S[k]) < 5e-4, (s, k, rel_err(fs.D.t[k], cpu.S[k]))
+    return fs

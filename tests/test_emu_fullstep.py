@@ -61,3 +61,10 @@ def test_full_step_other_bookkeeping_regimes_vs_oracle(monkeypatch, m_topk_rate,
     harness.set_order("fwd")
     harness.emulated_device(monkeypatch)
     fullstep_check.regime_check("cpu", m_topk_rate, T)
+
+
+@pytest.mark.parametrize("d,I", [(128, 97), (256, 50)])
+def test_full_step_other_shapes_vs_oracle(monkeypatch, d, I):
+    harness.set_order("fwd")
+    harness.emulated_device(monkeypatch)
+    fullstep_check.random_problem_check("cpu", d=d, I=I)

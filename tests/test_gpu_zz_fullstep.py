@@ -76,3 +76,8 @@ def test_full_step_own_random_draws_runs_and_learns():
 @pytest.mark.parametrize("m_topk_rate,T", [(0.0, 1), (0.05, 2), (0.02, 3)])
 def test_full_step_other_bookkeeping_regimes_vs_oracle(m_topk_rate, T):
     fullstep_check.regime_check("cuda", m_topk_rate, T, proj_impl="tc")
+
+
+@pytest.mark.parametrize("d,I", [(128, 97), (256, 50)])
+def test_full_step_other_shapes_vs_oracle(d, I):
+    fullstep_check.random_problem_check("cuda", d=d, I=I, proj_impl="tc")
