@@ -4,7 +4,9 @@ here, every call goes through the C ABI and raises when the extension or a CUDA 
 GEMMs: ``GEMM_IMPL = "tc"`` routes every product through the general-width tcgen05 kernel (csrc/gemm_wide.cu; operands
 split into bf16 hi/lo pairs, K-major, by the same split kernels as the projection); ``"simt"`` is the fp32 CUDA-core GEMM.
 The default stays "simt" until gemm_wide.cu has passed its GPU test (it was written without GPU access); set
-``MMSSL_GAN_GEMM=tc`` or assign ``gan_ops.GEMM_IMPL``."""
+``MMSSL_GAN_GEMM=tc`` or assign ``gan_ops.GEMM_IMPL``.  ``"cublas"`` sends the same products to the vendor library through
+``torch.mm`` / ``addmm`` (fp32, TF32 off): the library baseline the tensor-core kernel is measured against
+(tools/fullstep_bench.py --gemm cublas), not the product path."""
 from __future__ import annotations
 
 import os
@@ -39,8 +41,10 @@ def mm(a, b, ta=False, tb=False, alpha=1.0):
         a_hi, a_lo = ops.split_bf16_t(a) if ta else ops.split_bf16(a)          # [m][ceil8(k)], K-major
         b_hi, b_lo = ops.split_bf16(b) if tb else ops.split_bf16_t(b)          # [n][ceil8(k)], K-major
         return ops.gemm_bf16x3_wide(a_hi, a_lo, b_hi, b_lo, m, n, k, _new(m, n, like=a), alpha=alpha)
+    if GEMM_IMPL == "cublas":
+        return torch.mm(a.t() if ta else a, b.t() if tb else b).mul_(alpha)
     if GEMM_IMPL != "simt":
-        raise ValueError("gan_ops.GEMM_IMPL must be 'tc' or 'simt'")
+        raise ValueError("gan_ops.GEMM_IMPL must be 'tc', 'simt' or 'cublas'")
     return ops.sgemm(a, b, _new(m, n, like=a), trans_a=ta, trans_b=tb, alpha=alpha)
 
 
@@ -54,6 +58,8 @@ def mm_acc(dst, a, b, ta=False, tb=False, alpha=1.0):
         a_hi, a_lo = ops.split_bf16_t(a) if ta else ops.split_bf16(a)
         b_hi, b_lo = ops.split_bf16(b) if tb else ops.split_bf16_t(b)
         ops.gemm_bf16x3_wide(a_hi, a_lo, b_hi, b_lo, m, n, k, dst, alpha=alpha, accumulate=True)
+    elif GEMM_IMPL == "cublas":
+        dst.addmm_(a.t() if ta else a, b.t() if tb else b, alpha=alpha)
     else:
         ops.sgemm(a, b, dst, trans_a=ta, trans_b=tb, alpha=alpha, beta=1.0)
 

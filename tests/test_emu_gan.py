@@ -63,3 +63,10 @@ def test_tensor_core_gemm_route_operand_layouts(emu, tc_gemm, ta, tb):
 def test_d_step_trace_with_tensor_core_gemms(emu, tc_gemm):
     G.test_d_step_on_gpu_matches_reference_trace()
     G.test_usim_and_real_rows(120, 96, 32, 64)
+
+
+def test_d_step_trace_with_library_gemms(emu, monkeypatch):
+    """GEMM_IMPL = "cublas": the comparison route through torch.mm / addmm (the vendor library on a GPU)."""
+    from mmssl_b200 import gan_ops
+    monkeypatch.setattr(gan_ops, "GEMM_IMPL", "cublas")
+    G.test_d_step_on_gpu_matches_reference_trace()

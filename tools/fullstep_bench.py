@@ -2,7 +2,7 @@
 GPU, timed with CUDA events, next to the hot step alone and to the oracle's CPU restatement of the same iteration.
 SURVEY 8d: "also report full step for C1-C3".  Prints one JSON line.
 
-    python tools/fullstep_bench.py [config=baby] [--steps K] [--warmup W] [--gemm tc|simt] [--cpu-steps N]
+    python tools/fullstep_bench.py [config=baby] [--steps K] [--warmup W] [--gemm tc|simt|cublas] [--cpu-steps N]
 
 Not part of bench.py's contract (the headline metric is the hot step); written when round 1 had no GPU time left -- first run
 is a round-2 task."""
@@ -21,7 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("config", nargs="?", default="baby")
 ap.add_argument("--steps", type=int, default=50)
 ap.add_argument("--warmup", type=int, default=5)
-ap.add_argument("--gemm", default=os.environ.get("MMSSL_GAN_GEMM", "simt"), choices=["tc", "simt"])
+ap.add_argument("--gemm", default=os.environ.get("MMSSL_GAN_GEMM", "simt"), choices=["tc", "simt", "cublas"])
 ap.add_argument("--cpu-steps", type=int, default=2)
 ap.add_argument("--seed", type=int, default=2022)
 ap.add_argument("--batch", type=int, default=0, help="0 = bench.BATCH (1024, the reference default)")
