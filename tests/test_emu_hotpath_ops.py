@@ -71,3 +71,10 @@ def test_spmm_empty_and_epilogues(emu):
 def test_spmm_early_prefetch_variant(emu, d, nrhs, base_impl):
     from tests import test_gpu_zz_more_ops as Z
     Z.test_spmm_early_prefetch_variant_matches_default(d, nrhs, base_impl)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+def test_sgemm_large_tiles(emu, ta, tb):
+    from tests import test_gpu_zz_more_ops as Z
+    Z.test_sgemm_large_tiles(ta, tb, 300, 700, 130)
+    Z.test_sgemm_large_tiles(ta, tb, 128, 512, 8)

@@ -46,3 +46,23 @@ def test_infonce_beyond_one_block(n, d):
     """More rows than one 1024-block of main.py:228-246 and not a multiple of it (SURVEY 8c edge case): the reference's double
     loop over blocks equals the full matrix (oracle.infonce_literal == oracle.infonce)."""
     _infonce(n, d)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("m,n,k", [(300, 700, 130), (128, 512, 8), (2048, 1762, 705)])
+def test_sgemm_large_tiles(ta, tb, m, n, k):
+    """The 128 x 128 register-blocked kernel mmssl_sgemm selects for m >= 128 and n >= 512 (the GAN side's products on the
+    CUDA-core route): ragged edges in all three dimensions, the four operand layouts, alpha / beta, split-K."""
+    from mmssl_b200 import ops
+    g = torch.Generator().manual_seed(m + n + k)
+    a = torch.randn((k, m) if ta else (m, k), generator=g).cuda()
+    b = torch.randn((n, k) if tb else (k, n), generator=g).cuda()
+    c0 = torch.randn(m, n, generator=g)
+    out = c0.clone().cuda()
+    ops.sgemm(a, b, out, trans_a=ta, trans_b=tb, alpha=0.5, beta=2.0)
+    A = a.double().cpu().t() if ta else a.double().cpu()
+    B = b.double().cpu().t() if tb else b.double().cpu()
+    assert rel_err(out, 0.5 * A @ B + 2.0 * c0.double()) < 1e-5
+    out2 = c0.clone().cuda()
+    ops.sgemm(a, b, out2, trans_a=ta, trans_b=tb, alpha=-1.5, beta=1.0, split_k=3)
+    assert rel_err(out2, -1.5 * A @ B + c0.double()) < 1e-5
