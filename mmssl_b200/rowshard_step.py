@@ -56,6 +56,19 @@ class RowBlockGraph:
         return cls(op(mat, part_rows), op(mat.T.tocsr(), part_cols), (part_rows.block, part_cols.block), mat.nnz)
 
 
+    @classmethod
+    def from_csr_blocks(cls, fwd_blk, bwd_blk, nnz: int, device) -> "RowBlockGraph":
+        """From two ``dataset.CsrBlock``s (the rank's rows of A and of A^T as ``ShardedDataset.operand`` maps them from disk:
+        indptr rebased to 0, global column ids): a rank never sees the rest of the graph."""
+        def op(blk):
+            rows = np.repeat(np.arange(blk.shape[0], dtype=np.int64), np.diff(blk.indptr))
+            t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).astype(dt)).to(device)
+            o = SparseOperand(t(rows, "int64"), t(blk.indices, "int64"), t(blk.values, "float32"), blk.shape[0], blk.shape[1])
+            o.tighten()
+            return o
+        return cls(op(fwd_blk), op(bwd_blk), (fwd_blk.shape[0], bwd_blk.shape[0]), nnz)
+
+
 def gather_owned(table: torch.Tensor, idx: torch.Tensor, lo: int, hi: int, out: torch.Tensor) -> torch.Tensor:
     lib = _lib.load(require_device=True)
     _lib.check(lib.mmssl_gather_owned(ptr(table), table.stride(0), ptr(idx), lo, hi, idx.numel(), table.shape[1], ptr(out),
@@ -211,10 +224,31 @@ def shard_problem(P_full: Dict[str, torch.Tensor], feats_full: Sequence[torch.Te
     part_u, part_i).  The full problem only has to exist on the host."""
     U, I = ui_norm.shape
     pu, pi = RowPartition(U, world), RowPartition(I, world)
-    P = {k: P_full[k].to(device).contiguous() for k in REPLICATED}
+    P = {k: P_full[k].to(device).clone().contiguous() for k in REPLICATED}      # private copies: the step updates them in place
     P[P_EU] = pu.local(P_full[P_EU], rank).to(device).contiguous()
     P[P_EI] = pi.local(P_full[P_EI], rank).to(device).contiguous()
     feats = tuple(FeatureStore(pi.local(f, rank).to(device).contiguous(), keep_fp32=True) for f in feats_full)
     g_ui = RowBlockGraph.from_scipy(ui_norm, pu, pi, rank, device)
     g_iu = RowBlockGraph.from_scipy(iu_norm, pi, pu, rank, device)
     return P, feats, (g_ui, g_iu, g_ui, g_iu, g_ui, g_iu), pu, pi
+
+
+def shard_problem_from_disk(root: str, P_full: Dict[str, torch.Tensor], rank: int, world: int, device):
+    """Same pieces as ``shard_problem`` but read from a shard directory written once by ``dataset.write_shards``:
+    every rank memory-maps only its row blocks of the four operands and its item rows of the two feature matrices."""
+    from .dataset import ShardedDataset
+    sh = ShardedDataset.open(root, rank, world)
+    pu, pi = sh.part["user"], sh.part["item"]
+    P = {k: P_full[k].to(device).clone().contiguous() for k in REPLICATED}      # private copies: the step updates them in place
+    P[P_EU] = pu.local(P_full[P_EU], rank).to(device).contiguous()
+    P[P_EI] = pi.local(P_full[P_EI], rank).to(device).contiguous()
+    feats = []
+    for which in ("image", "text"):
+        f = torch.zeros(pi.block, sh.meta[f"{which}_dim"], dtype=torch.float32)
+        rows = sh.features(which)
+        f[:rows.shape[0]] = torch.from_numpy(np.ascontiguousarray(rows))
+        feats.append(FeatureStore(f.to(device), keep_fp32=True))
+    nnz = sh.meta["operands"]["ui"]["nnz"]
+    g_ui = RowBlockGraph.from_csr_blocks(sh.operand("ui"), sh.operand("uiT"), nnz, device)
+    g_iu = RowBlockGraph.from_csr_blocks(sh.operand("iu"), sh.operand("iuT"), nnz, device)
+    return P, tuple(feats), (g_ui, g_iu, g_ui, g_iu, g_ui, g_iu), pu, pi

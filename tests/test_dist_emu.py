@@ -119,3 +119,56 @@ def test_row_sharded_hot_step_matches_single_process(modal):
         bad = {k: v for k, v in e.items() if not v < 2e-5}
         assert not bad, (rank, bad)
         assert gathers > 0
+
+
+def _disk_worker(rank, port, shard_dir, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        from tests.cuemu import harness
+        harness.set_order("fwd")
+        harness.emulated_device(_MP())
+        from mmssl_b200.dataset import ReferenceDataset
+        from mmssl_b200.engine import LIVE
+        from mmssl_b200.hotstep import HotStepConfig
+        from mmssl_b200.rowshard_step import RowShardedHotStep, shard_problem, shard_problem_from_disk
+        from mmssl_b200.synthetic import csr_norm
+        from tests.golden_util import rel_err
+        ds = ReferenceDataset.load(os.path.join(os.path.dirname(__file__), "golden", "dataset_small"))
+        R = ds.train_mat.astype(np.float32).tocsr()
+        U, I = R.shape
+        d, B = 64, 16
+        g = torch.Generator().manual_seed(4)
+        xav = lambda a, b: (torch.rand(a, b, generator=g) * 2 - 1) * (6.0 / (a + b)) ** 0.5
+        P = {"image_trans.weight": xav(d, ds.image_feats.shape[1]), "image_trans.bias": torch.zeros(d),
+             "text_trans.weight": xav(d, ds.text_feats.shape[1]), "text_trans.bias": torch.zeros(d),
+             "user_id_embedding.weight": xav(U, d), "item_id_embedding.weight": xav(I, d), "weight_dict.w_self_attention_cat": xav(4 * d, d)}
+        users = torch.randperm(U, generator=g)[:B]
+        pos, neg = torch.randint(0, I, (B,), generator=g), torch.randint(0, I, (B,), generator=g)
+        cfg = HotStepConfig(embed_size=d, n_layers=2, batch_size=B, drop_rate=0.0, proj_impl="simt")
+        feats = (torch.from_numpy(np.asarray(ds.image_feats, np.float32)), torch.from_numpy(np.asarray(ds.text_feats, np.float32)))
+        steps = []
+        for build in (lambda: shard_problem(P, feats, csr_norm(R), csr_norm(R.T.tocsr()), rank, WORLD, "cpu"),
+                      lambda: shard_problem_from_disk(shard_dir, P, rank, WORLD, "cpu")):
+            Pl, fl, gl, pu, pi = build()
+            sh = RowShardedHotStep(Pl, fl, gl, cfg, B, pu, pi, rank)
+            sh.set_indices(users, pos, neg)
+            out = sh.run().clone()
+            steps.append((out, {k: sh.P[k].clone() for k in LIVE}))
+        (o_mem, p_mem), (o_disk, p_disk) = steps
+        ret[rank] = dict(loss=float((o_mem - o_disk).abs().max()), params=max(rel_err(p_disk[k], p_mem[k]) for k in LIVE))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_step_from_memory_mapped_shards(tmp_path):
+    """dataset.write_shards -> ShardedDataset (every rank maps only its row blocks) -> RowShardedHotStep: identical to the step
+    built from the full in-memory matrices."""
+    from mmssl_b200.dataset import ReferenceDataset, write_shards
+    ds = ReferenceDataset.load(os.path.join(os.path.dirname(__file__), "golden", "dataset_small"))
+    write_shards(ds, str(tmp_path))
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_disk_worker, args=(port, str(tmp_path), ret), nprocs=WORLD, join=True)
+    for rank in range(WORLD):
+        assert ret[rank]["loss"] == 0.0 and ret[rank]["params"] == 0.0, dict(ret[rank])
