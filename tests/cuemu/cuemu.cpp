@@ -256,9 +256,16 @@ void run_grid(dim3 grid, dim3 block, size_t smem, void (*thunk)(void*), void* ar
     const std::vector<int> order = fiber_order((int)nthreads);
     const int nwarps = (int)((nthreads + 31) / 32);
 
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) {
+    // Blocks run one after the other; CUEMU_BLOCK_ORDER=rev runs them from the last to the first, so that code which relies
+    // on an arrival order between blocks (last-arriver reductions, self-resetting counters) is exercised in both directions.
+    const char* bo = getenv("CUEMU_BLOCK_ORDER");
+    const bool brev = bo != nullptr && strcmp(bo, "rev") == 0;
+    const uint64_t nblocks = (uint64_t)grid.x * grid.y * grid.z;
+    for (uint64_t bi = 0; bi < nblocks; ++bi) {
+            {
+                const uint64_t lin = brev ? nblocks - 1 - bi : bi;
+                const unsigned bx = (unsigned)(lin % grid.x), by = (unsigned)((lin / grid.x) % grid.y), bz = (unsigned)(lin / ((uint64_t)grid.x * grid.y));
+                {
                 blockIdx = {bx, by, bz};
                 g_fibers.assign(nthreads, Fiber());
                 g_warps.assign(nwarps, Warp());
@@ -308,7 +315,9 @@ void run_grid(dim3 grid, dim3 block, size_t smem, void (*thunk)(void*), void* ar
                     }
                 }
                 if (g_abandon) return;
+                }
             }
+    }
 }
 
 }  // namespace cuemu

@@ -40,8 +40,9 @@ def emu_lib():
 
 
 def set_order(order: str) -> None:
-    """fwd | rev | shuffle:<seed> -- the order in which the fibers of a block get the CPU."""
-    os.environ["CUEMU_ORDER"] = order
+    """fwd | rev | shuffle:<seed> -- the order in which the fibers of a block get the CPU.  CUEMU_ORDER_FORCE overrides the
+    tests' own choice (to sweep the whole emulated suite under another thread order)."""
+    os.environ["CUEMU_ORDER"] = os.environ.get("CUEMU_ORDER_FORCE", order)
 
 
 class _NullStream:

@@ -11,7 +11,7 @@
 //   * static __shared__ variables are function-local statics (one block at a time), dynamic shared memory is a
 //     per-launch buffer re-poisoned with NaN bytes for every block;
 //   * the fiber order inside a block is selectable (CUEMU_ORDER=fwd|rev|shuffle:<seed>) so that a missing barrier
-//     shows up as a result that depends on the order;
+//     shows up as a result that depends on the order; CUEMU_BLOCK_ORDER=rev runs the blocks of a grid last to first;
 //   * a block in which every live fiber waits at a barrier that cannot complete is reported as a deadlock
 //     (divergent __syncthreads, a shuffle mask naming a lane that went elsewhere).
 // What it cannot run: inline PTX (tcgen05, TMA, multimem, mbarrier) -- cuemu::ptx() fails the launch -- and CUB.
