@@ -105,7 +105,7 @@ def reference_sample(data: ReferenceDataset, batch_size: int, n_items: Optional[
 
 class Trainer:
     def __init__(self, data: ReferenceDataset, args=None, device: str = "cuda", sampler: str = "reference",
-                 log: Optional[Callable[[str], None]] = print, proj_impl: str = "tc"):
+                 log: Optional[Callable[[str], None]] = print, proj_impl: str = "tc", cuda_graph: bool = False):
         import mmssl_b200.Models as M
         self.args = args = args if args is not None else TrainerArgs()
         self.data, self.log, self.device = data, (log or (lambda s: None)), torch.device(device)
@@ -150,6 +150,9 @@ class Trainer:
             raise ValueError("sampler must be 'reference' or 'device'")
         self.sampler = sampler
         self._n_sampled = 0
+        # replay the steady-state iteration as one CUDA graph once the modality graphs have stopped changing
+        # (FullStep.capture; experimental until its first GPU run -- off by default)
+        self.cuda_graph = cuda_graph
 
     @staticmethod
     def _weights_init(m):                                          # main.py:133-136
@@ -182,6 +185,8 @@ class Trainer:
             self.step.start_epoch()
             for _ in range(n_batch):
                 users, pos, neg = self.sample()
+                if self.cuda_graph and self.step._graph is None and self.step.steady():
+                    self.step.capture()
                 out = self.step.step(users, pos, neg)
                 acc[0] += out["batch_loss"].reshape(())
                 acc[1:3] += out["loss5"][1:3]
