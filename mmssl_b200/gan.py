@@ -17,7 +17,7 @@ numerically noisy) gradients like every other parameter because the reference's 
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional, Sequence
 
 import torch
 

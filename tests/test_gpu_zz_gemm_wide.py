@@ -49,7 +49,6 @@ def test_gan_side_on_tensor_cores(monkeypatch):
 
 def test_full_step_cuda_graph_replay_equals_eager():
     """FullStep.capture(): the steady-state iteration as one CUDA graph == the same iterations run eagerly (same injected draws)."""
-    import numpy as np
     from mmssl_b200.engine import LIVE
     from tests import fullstep_check
     z, c = fullstep_check.load_trace()

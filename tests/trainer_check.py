@@ -9,7 +9,6 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def run_life_cycle(device: str, sampler: str, epochs: int = 3):
-    import torch
     from mmssl_b200.trainer import Trainer, TrainerArgs, set_seed
     ds = ReferenceDataset.load(os.path.join(GOLD, "dataset_small"))
     args = TrainerArgs(dataset="dataset_small", epoch=epochs, batch_size=16, verbose=2, early_stopping_patience=1, m_topk_rate=0.05,
