@@ -14,9 +14,11 @@
 // side) is hinted evict-last.  Rows / columns beyond m / n: TMA zero-fills the loads, the epilogue masks the stores;
 // C's leading dimension is arbitrary (I/4 is not a multiple of 4), 128-bit stores are used when the row is aligned.
 //
-// NOT YET RUN ON A GPU (written when round 1 had no GPU time left).  The host-side contract around it is exercised on the CPU
-// (tests/cuemu/gemm_bf16x3_host.cpp); its GPU test is gated by MMSSL_RUN_UNVALIDATED=1 and mmssl_b200.gan_ops keeps the
-// fp32 CUDA-core GEMM as default until that test has passed on a B200.  mbar_wait traps instead of hanging.
+// NOT YET RUN ON A GPU (written when round 1 had no GPU time left).  It has been executed on the CPU through a functional model
+// of the PTX it issues (tests/cuemu/cuemu_ptx.cpp, calibrated on proj_tc.cu which is green on hardware; tests/test_emu_tensor_core.py:
+// multi-tile N, ragged edges, both epilogues; a wrong TMA coordinate, barrier phase or epilogue row mapping is caught there).
+// Its GPU test is gated by MMSSL_RUN_UNVALIDATED=1 and mmssl_b200.gan_ops keeps the fp32 CUDA-core GEMM as default until that
+// test has passed on a B200.  mbar_wait traps instead of hanging.
 #include "tc_common.cuh"
 #include "../../include/mmssl_b200.h"
 

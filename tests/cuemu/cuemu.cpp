@@ -147,13 +147,13 @@ void fail(const char* what) {
     if (cur) park_forever();
 }
 
-void ptx(const char* text) {
-    if (strstr(text, "griddepcontrol") != nullptr) return;   // programmatic dependent launch: blocks run in order anyway
-    std::string m = std::string("inline PTX is not emulated: ") + text;
-    fail(m.c_str());
-}
-
 void* dyn_smem() { return g_smem; }
+size_t dyn_smem_bytes() { return g_smem_bytes; }
+void yield_blocked() {
+    yield();
+    if (g_abandon) park_forever();
+}
+void note_progress() { ++g_events; }
 
 static void wait_bar(Bar& b, unsigned my_gen) {
     while (b.gen == my_gen) {
@@ -247,7 +247,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem, void (*thunk)(void*), void* ar
     if (g_smem_bytes < smem + 128) {
         free(g_smem);
         g_smem_bytes = smem + 128;
-        g_smem = static_cast<unsigned char*>(aligned_alloc(128, (g_smem_bytes + 127) / 128 * 128));
+        g_smem = static_cast<unsigned char*>(aligned_alloc(1024, (g_smem_bytes + 1023) / 1024 * 1024));
     }
     g_thunk = thunk;
     g_thunk_arg = arg;
@@ -271,6 +271,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem, void (*thunk)(void*), void* ar
                 g_warps.assign(nwarps, Warp());
                 g_block_bar = Bar();
                 memset(g_smem, 0xFF, g_smem_bytes);
+                ptx_block_reset();
                 for (size_t t = 0; t < nthreads; ++t) {
                     Fiber& f = g_fibers[t];
                     f.lin = (int)t;

@@ -1,8 +1,8 @@
 // cuemu -- a host-side executor for plain CUDA C++ kernels.  TEST INFRASTRUCTURE ONLY.
 //
 // Purpose: the build container has nvcc but no GPU.  This header lets g++ compile the *unmodified kernel bodies* of
-// mmssl_b200/csrc/*.cu (after tests/cuemu/build.py rewrites the two pieces of syntax g++ cannot parse: `<<<...>>>`
-// launches and `extern __shared__` declarations) and run them on the CPU with CUDA's execution model:
+// mmssl_b200/csrc/*.cu (after tests/cuemu/build.py rewrites the three pieces of syntax g++ cannot parse: `<<<...>>>`
+// launches, `extern __shared__` declarations and inline asm statements) and run them on the CPU with CUDA's execution model:
 //   * one fiber per CUDA thread, all fibers of a block alive at the same time, blocks executed one after the other;
 //   * __syncthreads / __syncthreads_or|and|count are block barriers, __shfl_*_sync / __ballot_sync / __syncwarp are
 //     barriers over the lanes named by the mask, with the value exchange in between (exited lanes are ignored, like
@@ -14,9 +14,12 @@
 //     shows up as a result that depends on the order; CUEMU_BLOCK_ORDER=rev runs the blocks of a grid last to first;
 //   * a block in which every live fiber waits at a barrier that cannot complete is reported as a deadlock
 //     (divergent __syncthreads, a shuffle mask naming a lane that went elsewhere).
-// What it cannot run: inline PTX (tcgen05, TMA, multimem, mbarrier) -- cuemu::ptx() fails the launch -- and CUB.
-// It proves indexing, reduction order, barrier placement and the host-side argument marshalling; it says nothing
-// about performance, memory coalescing or sm_100a-specific behaviour.  Nothing under mmssl_b200/ includes this.
+//   * inline PTX is routed to cuemu_ptx.cpp: a functional model of the subset the tensor-core kernels use (mbarrier, 2-D
+//     TMA tensor copies with the 128-byte swizzle, tcgen05 alloc / mma / commit / ld, TMEM), calibrated on the kernel
+//     that is parity-green on real B200s; anything else (multimem, 1-D bulk copies) fails the launch;
+//   * CUB's two device primitives are host shims.
+// It proves indexing, reduction order, barrier / pipeline protocol and the host-side argument marshalling; it says nothing
+// about performance, memory coalescing, true asynchrony or device math rounding.  Nothing under mmssl_b200/ includes this.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -98,9 +101,21 @@ void syncwarp(unsigned mask);
 void exchange_begin(unsigned mask, uint64_t bits);   // deposit + barrier
 uint64_t exchange_peek(int lane, bool* valid);
 void exchange_end(unsigned mask);
-void ptx(const char* text);
+// Inline PTX, as rewritten by build.py: template text, pointers to / sizes of the outputs, the inputs as 64-bit values.
+// cuemu_ptx.cpp models the subset the library uses (mbarrier, 2-D TMA tensor copies with the 128-byte swizzle, tcgen05
+// alloc / mma kind::f16 / commit / ld 32x32b, griddepcontrol) and fails the launch on anything else (multimem, ...).
+void ptx_op(const char* text, void** outs, const int* out_sizes, int n_out, const uint64_t* ins, int n_in);
+void ptx_block_reset();
+void yield_blocked();                                 // give the CPU to the other fibers of the block (a failed try_wait)
+void note_progress();
+size_t dyn_smem_bytes();
 const char* error_text();
 void fail(const char* what);
+
+static inline uint64_t as_u64(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline uint64_t as_u64(double d) { uint64_t u; memcpy(&u, &d, 8); return u; }
+template <typename T> static inline uint64_t as_u64(T* p) { return (uint64_t)(uintptr_t)p; }
+template <typename T> static inline typename std::enable_if<std::is_integral<T>::value || std::is_enum<T>::value, uint64_t>::type as_u64(T v) { return (uint64_t)v; }
 
 template <typename T> struct ident { typedef T type; };
 
@@ -156,6 +171,9 @@ static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* c, void (
 }
 
 // ------------------------------------------------------------------------------------------ barriers and warp primitives
+// shared-memory "addresses" are byte offsets into the block's dynamic shared memory (1024-byte aligned base)
+static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)((const char*)p - (const char*)cuemu::dyn_smem()); }
+static inline void __trap() { cuemu::fail("__trap()"); }
 static inline void __syncthreads() { cuemu::syncthreads(); }
 static inline int __syncthreads_or(int p) { return cuemu::syncthreads_red(p, 0); }
 static inline int __syncthreads_and(int p) { return cuemu::syncthreads_red(p, 1); }

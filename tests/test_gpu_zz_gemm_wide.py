@@ -1,9 +1,9 @@
 """General-width tcgen05 GEMM (csrc/gemm_wide.cu) against fp64, and the GAN side running on it.
 
-NOT YET RUN ON A GPU: the kernel was written when round 1 had no GPU time left.  Unlike the plain-CUDA kernels it cannot
-be executed by the CPU emulator (TMA / TMEM / tcgen05 PTX); only the host contract around it is checked there
-(tests/test_emu_gan.py).  Gated by MMSSL_RUN_UNVALIDATED=1 until its first green GPU run; gan_ops.GEMM_IMPL stays "simt"
-by default until then."""
+NOT YET RUN ON A GPU: the kernel was written when round 1 had no GPU time left.  On the CPU it runs through the emulator's
+functional model of the PTX it issues (tests/test_emu_tensor_core.py) -- protocol and indexing, not timing or true
+asynchrony.  Gated by MMSSL_RUN_UNVALIDATED=1 until its first green GPU run; gan_ops.GEMM_IMPL stays "simt" by default
+until then."""
 import os
 
 import pytest
