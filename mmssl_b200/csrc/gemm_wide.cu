@@ -10,21 +10,20 @@
 // Same anatomy as proj_tc.cu (warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread MMA issuer, warps 2-5 = epilogue),
 // but tiled over N as well: CTA (m_tile, n_tile) owns a 128 x NT tile of C for the whole K range (no split-K: every
 // shape on this path gives >= 100 tiles), accumulates it in NT TMEM columns and writes it straight to C with the alpha /
-// beta epilogue.  Both operands are re-read from L2 by the other tiles of their row / column of the grid; B (the weight
-// side) is hinted evict-last.  Rows / columns beyond m / n: TMA zero-fills the loads, the epilogue masks the stores;
+// beta epilogue.  Both operands are re-read from L2 by the other tiles of their row / column of the grid, so both are
+// hinted evict-last (the policy constant proj_tc.cu already uses on hardware).  Rows / columns beyond m / n: TMA zero-fills the loads, the epilogue masks the stores;
 // C's leading dimension is arbitrary (I/4 is not a multiple of 4), 128-bit stores are used when the row is aligned.
 //
 // NOT YET RUN ON A GPU (written when round 1 had no GPU time left).  It has been executed on the CPU through a functional model
 // of the PTX it issues (tests/cuemu/cuemu_ptx.cpp, calibrated on proj_tc.cu which is green on hardware; tests/test_emu_tensor_core.py:
 // multi-tile N, ragged edges, both epilogues; a wrong TMA coordinate, barrier phase or epilogue row mapping is caught there).
-// Its GPU test is gated by MMSSL_RUN_UNVALIDATED=1 and mmssl_b200.gan_ops keeps the fp32 CUDA-core GEMM as default until that
-// test has passed on a B200.  mbar_wait traps instead of hanging.
+// Its GPU test (tests/test_gpu_zzz_gemm_wide.py, sorts last) runs with the suite; mmssl_b200.gan_ops keeps the fp32 CUDA-core GEMM
+// as default until that test has passed on a B200.  mbar_wait traps instead of hanging.
 #include "tc_common.cuh"
 #include "../../include/mmssl_b200.h"
 
 namespace mmssl {
 
-constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 
 template <int NT>
 struct WideCfg {
@@ -82,8 +81,8 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 uint8_t* st = smem + s * Cfg::kStageBytes;
                 mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
                 const int kx = i * kBlockK;
-                tma_load_2d(&tm_a_hi, &full_bar[s], st, kx, m_tile * kBlockM, kEvictNormal);
-                tma_load_2d(&tm_a_lo, &full_bar[s], st + kTileABytes, kx, m_tile * kBlockM, kEvictNormal);
+                tma_load_2d(&tm_a_hi, &full_bar[s], st, kx, m_tile * kBlockM, kEvictLast);
+                tma_load_2d(&tm_a_lo, &full_bar[s], st + kTileABytes, kx, m_tile * kBlockM, kEvictLast);
                 tma_load_2d(&tm_b_hi, &full_bar[s], st + 2 * kTileABytes, kx, n_tile * NT, kEvictLast);
                 tma_load_2d(&tm_b_lo, &full_bar[s], st + 2 * kTileABytes + Cfg::kTileBBytes, kx, n_tile * NT, kEvictLast);
             }

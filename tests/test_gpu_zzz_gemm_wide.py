@@ -2,8 +2,9 @@
 
 NOT YET RUN ON A GPU: the kernel was written when round 1 had no GPU time left.  On the CPU it runs through the emulator's
 functional model of the PTX it issues (tests/test_emu_tensor_core.py) -- protocol and indexing, not timing or true
-asynchrony.  Gated by MMSSL_RUN_UNVALIDATED=1 until its first green GPU run; gan_ops.GEMM_IMPL stays "simt" by default
-until then."""
+asynchrony; it shares its descriptor / swizzle / pipeline helpers with proj_tc.cu, which is green on hardware, and
+mbar_wait traps instead of hanging.  The file sorts last in the GPU suite.  gan_ops.GEMM_IMPL stays "simt" by default until
+these tests have passed on a B200; the CUDA-graph capture test stays gated by MMSSL_RUN_UNVALIDATED=1."""
 import os
 
 import pytest
@@ -11,9 +12,9 @@ import torch
 
 from tests.golden_util import rel_err
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MMSSL_RUN_UNVALIDATED") != "1",
-                                 reason="gemm_wide.cu not yet validated on a GPU (set MMSSL_RUN_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
+_unvalidated = pytest.mark.skipif(os.environ.get("MMSSL_RUN_UNVALIDATED") != "1",
+                                  reason="CUDA-graph capture of the full step has not run on a GPU yet (set MMSSL_RUN_UNVALIDATED=1)")
 
 
 @pytest.mark.parametrize("m,n,k", [(64, 24, 96), (300, 200, 96), (2048, 1762, 7050), (1762, 7050, 2048), (2048, 7050, 1762),
@@ -47,6 +48,7 @@ def test_gan_side_on_tensor_cores(monkeypatch):
     fullstep_check.run_and_check(dev="cuda", proj_impl="tc")
 
 
+@_unvalidated
 def test_full_step_cuda_graph_replay_equals_eager():
     """FullStep.capture(): the steady-state iteration as one CUDA graph == the same iterations run eagerly (same injected draws)."""
     from mmssl_b200.engine import LIVE

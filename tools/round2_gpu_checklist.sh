@@ -19,7 +19,7 @@ for f in tests/test_gpu_zz_eval.py tests/test_gpu_zz_gan.py tests/test_gpu_zz_fu
     run 600 "pytest_$(basename "$f" .py).log" python -m pytest "$f" -m gpu -q
 done
 # 2. the tcgen05 wide GEMM and the CUDA-graph capture of the full step (gated: never run on hardware before)
-run 600 pytest_gemm_wide.log env MMSSL_RUN_UNVALIDATED=1 python -m pytest tests/test_gpu_zz_gemm_wide.py -m gpu -q
+run 600 pytest_gemm_wide.log env MMSSL_RUN_UNVALIDATED=1 python -m pytest tests/test_gpu_zzz_gemm_wide.py -m gpu -q
 # 3. headline bench (unchanged path) + the stock-torch comparator
 run 600 bench_default.json python bench.py
 run 600 bench_stock_gpu.json python bench.py --impl stock-gpu --steps 100
