@@ -107,6 +107,8 @@ class FullStep:
         self.hs = HotStep(params, feats, graphs, cfg.hot, batch=batch, optimizer_step=True, allow_alias=False)
         self.hs.post_forward = self._generator_side
         self.D = gan.DiscriminatorState(d_state)
+        if hasattr(self.K, "register_weights"):          # tensor-core route: the weights' bf16 splits are cached per optimiser step
+            self.K.register_weights([self.D.t["net.0.weight"], self.D.t["net.4.weight"]])
         self.idx = 0                                    # iteration inside the epoch (main.py:333)
         self.pairs: Dict[str, List[Tuple[torch.Tensor, torch.Tensor]]] = {"image": [], "text": []}
         self.k = int(self.I * cfg.m_topk_rate)

@@ -32,14 +32,41 @@ def _new(*shape, like):
     return torch.empty(*shape, dtype=torch.float32, device=like.device)
 
 
+# ---- bf16 hi/lo operand splits of the Discriminator's weights are reused by every product of an iteration (W1 alone enters 6 of
+# them, 100 MB of traffic per split at Baby); activations are split per call.  Only tensors registered as weights are cached;
+# `adam` (the only writer of the weights on this path) drops the cache, `weights_changed()` does it for any other writer.
+_weight_ptrs = set()
+_split_cache = {}
+
+
+def register_weights(tensors) -> None:
+    for t in tensors:
+        _weight_ptrs.add(t.data_ptr())
+
+
+def weights_changed() -> None:
+    _split_cache.clear()
+
+
+def _split(t, transposed: bool):
+    if t.data_ptr() not in _weight_ptrs:
+        return ops.split_bf16_t(t) if transposed else ops.split_bf16(t)
+    key = (t.data_ptr(), tuple(t.shape), transposed, t._version)
+    hit = _split_cache.get(key)
+    if hit is None:
+        hit = ops.split_bf16_t(t) if transposed else ops.split_bf16(t)
+        _split_cache[key] = hit
+    return hit
+
+
 def mm(a, b, ta=False, tb=False, alpha=1.0):
     a, b = _c(a), _c(b)
     m = a.shape[1] if ta else a.shape[0]
     n = b.shape[0] if tb else b.shape[1]
     if GEMM_IMPL == "tc":
         k = a.shape[0] if ta else a.shape[1]
-        a_hi, a_lo = ops.split_bf16_t(a) if ta else ops.split_bf16(a)          # [m][ceil8(k)], K-major
-        b_hi, b_lo = ops.split_bf16(b) if tb else ops.split_bf16_t(b)          # [n][ceil8(k)], K-major
+        a_hi, a_lo = _split(a, ta)                                             # [m][ceil8(k)], K-major
+        b_hi, b_lo = _split(b, not tb)                                         # [n][ceil8(k)], K-major
         return ops.gemm_bf16x3_wide(a_hi, a_lo, b_hi, b_lo, m, n, k, _new(m, n, like=a), alpha=alpha)
     if GEMM_IMPL == "cublas":
         return torch.mm(a.t() if ta else a, b.t() if tb else b).mul_(alpha)
@@ -55,8 +82,8 @@ def mm_acc(dst, a, b, ta=False, tb=False, alpha=1.0):
     m, n = dst.shape
     if GEMM_IMPL == "tc":
         k = a.shape[0] if ta else a.shape[1]
-        a_hi, a_lo = ops.split_bf16_t(a) if ta else ops.split_bf16(a)
-        b_hi, b_lo = ops.split_bf16(b) if tb else ops.split_bf16_t(b)
+        a_hi, a_lo = _split(a, ta)
+        b_hi, b_lo = _split(b, not tb)
         ops.gemm_bf16x3_wide(a_hi, a_lo, b_hi, b_lo, m, n, k, dst, alpha=alpha, accumulate=True)
     elif GEMM_IMPL == "cublas":
         dst.addmm_(a.t() if ta else a, b.t() if tb else b, alpha=alpha)
@@ -198,4 +225,5 @@ def adam(params, grads, ms, vs, step, lr, b1, b2, eps=1e-8, step_dev=None):
         step_dev = torch.tensor([int(step)], dtype=torch.int32, device=params[0].device)
     else:
         ops.step_tick(step_dev)
+    weights_changed()
     ops.adamw(list(params), [_c(g) for g in grads], list(ms), list(vs), step_dev, lr, b1, b2, eps, 0.0)

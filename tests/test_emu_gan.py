@@ -70,3 +70,32 @@ def test_d_step_trace_with_library_gemms(emu, monkeypatch):
     from mmssl_b200 import gan_ops
     monkeypatch.setattr(gan_ops, "GEMM_IMPL", "cublas")
     G.test_d_step_on_gpu_matches_reference_trace()
+
+
+def test_weight_split_cache(emu, tc_gemm, monkeypatch):
+    """tc route: the bf16 splits of registered weights are computed once per optimiser step, activations every call."""
+    import torch
+    from mmssl_b200 import gan_ops as K, ops
+    from tests.golden_util import rel_err
+    calls = {"n": 0}
+    real = ops.split_bf16
+
+    def counting(x, *a, **k):
+        calls["n"] += 1
+        return real(x, *a, **k)
+    monkeypatch.setattr(ops, "split_bf16", counting)
+    g = torch.Generator().manual_seed(0)
+    w, x = torch.randn(40, 72, generator=g), torch.randn(24, 72, generator=g)
+    K.weights_changed()
+    K.register_weights([w])
+    y1 = K.mm(x, w, tb=True)
+    n1 = calls["n"]                                  # x and w split
+    y2 = K.mm(x, w, tb=True)
+    assert calls["n"] == n1 + 1                      # only the activation again
+    assert rel_err(y1, x.double() @ w.double().t()) < 2e-5 and torch.equal(y1, y2)
+    w.mul_(2.0)                                      # a torch-side in-place change is seen through the version counter
+    y3 = K.mm(x, w, tb=True)
+    assert rel_err(y3, 2 * (x.double() @ w.double().t()) / 2 * 2) < 2e-5 and calls["n"] == n1 + 3
+    K.weights_changed()                              # what adam() calls after the kernel has rewritten the weights
+    K.mm(x, w, tb=True)
+    assert calls["n"] == n1 + 5
