@@ -14,6 +14,7 @@ are rebuilt by the trainer and simply miss the cache).
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from typing import Dict, Optional, Tuple
 
@@ -69,6 +70,8 @@ class SparseOperand:
         self._hot = None
         self.desc = CsrDesc(ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), n_rows, n_cols, nnz, ptr(self.items),
                             self.items_cap, ptr(self.split_table), ptr(self.counters), self.segs_cap)
+        if os.environ.get("MMSSL_SPMM_SORT") == "1" and nnz > 0:
+            self.sort_items_by_length()
 
     def work_area(self, width: int):
         """(partials, counters) for launches whose right-hand sides total `width` floats per row.
@@ -111,6 +114,18 @@ class SparseOperand:
             self.desc.segs_cap = max(self.n_segs, 0)
             self.segs_cap = self.n_segs
             self._keepalive = ()
+
+    def sort_items_by_length(self) -> None:
+        """Candidate awaiting measurement (MMSSL_SPMM_SORT=1): reorder the work items longest first.  Every item is
+        self-contained (row, [begin, end), split slot), so any order gives the same result; what changes is who shares a warp
+        (at d = 64 two items do: similar lengths waste fewer lanes) and that the long items start first (shorter tail)."""
+        self.tighten()
+        n = self._n_items_exact
+        if n <= 1:
+            return
+        it = self.items[:4 * n].view(n, 4)
+        order = torch.argsort(it[:, 2] - it[:, 1], descending=True, stable=True)
+        self.items[:4 * n] = it[order].reshape(-1)
 
     def to_scipy(self):
         import numpy as np

@@ -78,3 +78,9 @@ def test_sgemm_large_tiles(emu, ta, tb):
     from tests import test_gpu_zz_more_ops as Z
     Z.test_sgemm_large_tiles(ta, tb, 300, 700, 130)
     Z.test_sgemm_large_tiles(ta, tb, 128, 512, 8)
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_spmm_length_sorted_work_items(emu, monkeypatch, d):
+    from tests import test_gpu_zz_more_ops as Z
+    Z.test_spmm_length_sorted_work_items(d, monkeypatch)

@@ -66,3 +66,22 @@ def test_sgemm_large_tiles(ta, tb, m, n, k):
     out2 = c0.clone().cuda()
     ops.sgemm(a, b, out2, trans_a=ta, trans_b=tb, alpha=-1.5, beta=1.0, split_k=3)
     assert rel_err(out2, -1.5 * A @ B + c0.double()) < 1e-5
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_spmm_length_sorted_work_items(d, monkeypatch):
+    """MMSSL_SPMM_SORT=1: the work items of the plan are processed longest first -- same results (rows up to 1024 non-zeros are
+    reduced in a fixed order whatever the item order), split and plain rows, forward and transposed operand."""
+    from mmssl_b200 import ops
+    g0, ref = _graph(700, 500, 30000, seed=d, heavy_rows=40)
+    monkeypatch.setenv("MMSSL_SPMM_SORT", "1")
+    g1, _ = _graph(700, 500, 30000, seed=d, heavy_rows=40)
+    n = g1.fwd._n_items_exact
+    it = g1.fwd.items[:4 * n].view(n, 4).cpu()
+    lens = (it[:, 2] - it[:, 1])
+    assert bool((lens[:-1] >= lens[1:]).all()) and g1.fwd.n_split_rows > 0
+    torch.manual_seed(0)
+    x, xt = torch.randn(500, d, device="cuda"), torch.randn(700, d, device="cuda")
+    for a, b in ((ops.spmm(g0.fwd, [x])[0], ops.spmm(g1.fwd, [x])[0]), (ops.spmm(g0.bwd, [xt])[0], ops.spmm(g1.bwd, [xt])[0])):
+        assert torch.equal(a, b)
+    assert rel_err(ops.spmm(g1.fwd, [x])[0], torch.from_numpy(ref @ x.double().cpu().numpy())) < 2e-6

@@ -1,6 +1,7 @@
 """GPU probe: in-graph (warm) latency of kernel chains at small scale, SpMM throughput at large scale.
 Usage (under gpurun): python tools/probe.py [small] [large]"""
-import json, os, sys, time
+import json
+import os, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
@@ -68,6 +69,13 @@ def small(name):
                                                                           impl=impl), inner=20), 2)
         out[f"gcn_bwd_impl{impl}_us"] = round(graph_time(lambda: ops.spmm(g_iu.bwd, [xi], [yu], cs=[cu], alpha=0.33, epilogue=ops.EPI_SOFTMAX_BWD,
                                                                           ysaved=[ysv], impl=impl), inner=20), 2)
+    # work items processed longest first (MMSSL_SPMM_SORT=1, plan-level candidate): same kernels, other item order
+    os.environ["MMSSL_SPMM_SORT"] = "1"
+    gs_ui = BipartiteGraph.from_scipy(ds.ui_norm); gs_iu = BipartiteGraph.from_scipy(ds.iu_norm)
+    del os.environ["MMSSL_SPMM_SORT"]
+    out["ui_sorted_us"] = round(graph_time(lambda: ops.spmm(gs_ui.fwd, [xi], [yu]), inner=20), 2)
+    out["iu_sorted_us"] = round(graph_time(lambda: ops.spmm(gs_iu.fwd, [yu], [yi]), inner=20), 2)
+    out["ui2_sorted_us"] = round(graph_time(lambda: ops.spmm(gs_ui.fwd, [x2[:, :d], x2[:, d:]], [y2[:, :d], y2[:, d:]]), inner=20), 2)
     out["axpby_in_graph_us"] = graph_time(lambda: ops.axpby(xi, 1.0, 0.0, yi), inner=40)     # ~launch floor
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)
     out["spmm_ui_cold_us"] = cold_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu]), flush)

@@ -22,8 +22,9 @@ done
 run 600 pytest_gemm_wide.log env MMSSL_RUN_UNVALIDATED=1 python -m pytest tests/test_gpu_zzz_gemm_wide.py -m gpu -q
 # 3. headline bench (unchanged path) + the stock-torch comparator
 run 600 bench_default.json python bench.py
+run 600 bench_sorted_items.json env MMSSL_SPMM_SORT=1 python bench.py --no-cpu-baseline
 run 600 bench_stock_gpu.json python bench.py --impl stock-gpu --steps 100
-# 4. SpMM probes incl. the early-prefetch variant (gcn_*_impl{4,68,16,80})
+# 4. SpMM probes incl. the early-prefetch variant (gcn_*_impl{4,68,16,80}) and the length-sorted work items (*_sorted_us)
 run 600 probe_baby.json python tools/probe.py baby
 run 600 probe_sports.json python tools/probe.py sports
 # 5. the full training iteration: CUDA-core route, library route, tensor-core route
