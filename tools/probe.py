@@ -1,7 +1,7 @@
 """GPU probe: in-graph (warm) latency of kernel chains at small scale, SpMM throughput at large scale.
 Usage (under gpurun): python tools/probe.py [small] [large]"""
 import json
-import os, os, sys, time
+import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
