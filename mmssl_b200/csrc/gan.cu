@@ -7,16 +7,17 @@
 // The GEMMs between them go through the library's GEMM entry points.  All of this is HBM-bound reduction work on
 // [2B, I/4], [2B, I/8] and [B, I] fp32 tiles (I/4 is not a multiple of 4 in general, so loads are scalar and coalesced
 // along the row).  Two kernel shapes:
-//   * column ops  -- CTA = 32 columns x 8 row lanes; a column's statistics are reduced in a fixed order (deterministic);
-//                    multi-pass kernels re-read their 32-column stripe from L2.
+//   * column ops  -- CTA = 8 columns x 32 row lanes (h = I/4 = 1762 at Baby gives 221 CTAs: the 148 SMs are covered, which a
+//                    32-column CTA would not do); a column's statistics are reduced in a fixed order (deterministic);
+//                    multi-pass kernels re-read their 8-column stripe from L2.
 //   * row ops     -- one CTA (256 threads) or one warp per row, block reductions in a fixed order.
 #include "common.cuh"
 #include "../../include/mmssl_b200.h"
 
 namespace mmssl {
 
-constexpr int kCT = 32;   // columns per CTA
-constexpr int kRL = 8;    // row lanes per CTA
+constexpr int kCT = 8;    // columns per CTA: 8 consecutive floats = one 32-byte sector per row
+constexpr int kRL = 32;   // row lanes per CTA (a warp covers 4 rows x 8 columns: 4 full sectors per load instruction)
 constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
 
 // Sum over the kRL row lanes of every column; every thread of the column gets the result.
@@ -218,9 +219,13 @@ __global__ void __launch_bounds__(kCT* kRL) head_bwd_kernel(const float* __restr
             t += dz;
         }
         t = col_reduce(t, sh);                              // per threadIdx.x partial over the row lanes ...
-        if (threadIdx.y == 0) {                             // ... then over the 32 columns, fixed order
-            t = warp_sum(t);
-            if (threadIdx.x == 0) db3[0] = t;
+        if (threadIdx.y == 0) sh[0][threadIdx.x] = t;       // ... then over the kCT column slots, fixed order
+        __syncthreads();
+        if (tid == 0) {
+            float tot = 0.f;
+#pragma unroll
+            for (int x = 0; x < kCT; ++x) tot += sh[0][x];
+            db3[0] = tot;
         }
     }
 }
@@ -249,9 +254,13 @@ __global__ void __launch_bounds__(kCT* kRL) gp_head_rev_cols_kernel(const float*
         float t = 0.f;
         for (int64_t r = tid; r < n; r += kCT * kRL) t += z_bar[r];
         t = col_reduce(t, sh);
-        if (threadIdx.y == 0) {
-            t = warp_sum(t);
-            if (threadIdx.x == 0) g_b3[0] = t;
+        if (threadIdx.y == 0) sh[0][threadIdx.x] = t;
+        __syncthreads();
+        if (tid == 0) {
+            float tot = 0.f;
+#pragma unroll
+            for (int x = 0; x < kCT; ++x) tot += sh[0][x];
+            g_b3[0] = tot;
         }
     }
 }
