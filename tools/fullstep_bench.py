@@ -24,6 +24,7 @@ ap.add_argument("--gemm", default=os.environ.get("MMSSL_GAN_GEMM", "simt"), choi
 ap.add_argument("--cpu-steps", type=int, default=2)
 ap.add_argument("--seed", type=int, default=2022)
 ap.add_argument("--batch", type=int, default=0, help="0 = bench.BATCH (1024, the reference default)")
+ap.add_argument("--phases", action="store_true", help="CUDA-event breakdown: first forward, 3x u_sim, D step, G step (hot step + generator side)")
 a = ap.parse_args()
 
 import bench  # noqa: E402  (problem builder shared with the headline benchmark)
@@ -69,6 +70,28 @@ def run(n):
     return out
 
 
+phase_ev = {}
+if a.phases:                 # wrap the pieces of FullStep._body with event pairs (eager mode only)
+    from mmssl_b200 import fullstep as _F
+
+    def timed(name, fn):
+        def w(*x, **k):
+            e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            e[0].record()
+            r = fn(*x, **k)
+            e[1].record()
+            phase_ev.setdefault(name, []).append(e)
+            return r
+        return w
+    fs.hs.engine.forward = timed("forward (each of the 2 per iteration)", fs.hs.engine.forward)
+    fs.hs.engine.backward = timed("backward", fs.hs.engine.backward)
+    _F.gan.u_sim_forward = timed("u_sim forward (each of the 5)", _F.gan.u_sim_forward)
+    _F.gan.u_sim_backward = timed("u_sim backward (each of the 2)", _F.gan.u_sim_backward)
+    _F.gan.d_step = timed("D step (3 D calls + penalty sweeps + Adam)", _F.gan.d_step)
+    _F.gan.g_side = timed("G side (D call + input gradient)", _F.gan.g_side)
+    fs.hs.run = timed("G step total (HotStep.run incl. generator side, backward, AdamW)", fs.hs.run)
+
+
 run(a.warmup)
 torch.cuda.synchronize()
 from mmssl_b200 import _lib  # noqa: E402
@@ -80,11 +103,14 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
 launches = _lib.launch_count / a.steps
+phases = {k: round(sum(e0.elapsed_time(e1) for e0, e1 in v[-a.steps:]) / max(1, len(v[-a.steps:])), 4) for k, v in phase_ev.items()}
 res = {"metric": "bpr_triples_per_sec_full_step", "unit": "triples/s", "value": B / ms * 1e3, "ms_per_step": ms, "n_gpus": 1,
        "steps": a.steps, "warmup": a.warmup, "config": {"workload": a.config, "U": U, "I": I, "nnz": int(ds.nnz), "d": d, "batch": B,
                                                           "gan_gemm": a.gemm, "graph_capture": False, "modality_graphs": "empty after iteration 1 (T=1, reference quirk)"},
        "gpu_launches_per_step": launches, "batch_loss": float(out["batch_loss"]), "loss_D": float(out["loss_D"]),
        "big_gemm_gflop_per_step": 11 * 2 * 2 * B * I * h1 / 1e9}
+if phases:
+    res["phase_ms_per_call"] = phases
 
 if a.cpu_steps > 0:          # the oracle's restatement of the same iteration on the host cores, a bounded sample (bench.py owns that leg)
     res["cpu_baseline"] = bench.cpu_full_step_baseline(a.config, a.seed, a.cpu_steps, B, S_cpu)

@@ -28,9 +28,9 @@ run 600 bench_stock_gpu.json python bench.py --impl stock-gpu --steps 100
 run 600 probe_baby.json python tools/probe.py baby
 run 600 probe_sports.json python tools/probe.py sports
 # 5. the full training iteration: CUDA-core route, library route, tensor-core route
-run 900 fullstep_simt.json python tools/fullstep_bench.py baby --gemm simt --steps 20 --cpu-steps 1
+run 900 fullstep_simt.json python tools/fullstep_bench.py baby --gemm simt --steps 20 --cpu-steps 1 --phases
 run 600 fullstep_cublas.json python tools/fullstep_bench.py baby --gemm cublas --steps 20 --cpu-steps 0
-run 600 fullstep_tc.json python tools/fullstep_bench.py baby --gemm tc --steps 20 --cpu-steps 0
+run 600 fullstep_tc.json python tools/fullstep_bench.py baby --gemm tc --steps 20 --cpu-steps 0 --phases
 # 6. launch list of the full step (one iteration under ncu, serialised)
 run 900 ncu_fullstep.log ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/fullstep_launches.csv \
     python tools/fullstep_bench.py baby --gemm simt --steps 1 --warmup 3 --cpu-steps 0
