@@ -6,7 +6,7 @@ The sources are mmssl_b200/csrc/*.cu, untouched except for three pieces of synta
   extern __shared__ [__align__(n)] T name[];    ->  T* name = (T*)cuemu::dyn_smem();
   asm volatile("ptx" : outs : ins : ...);       ->  cuemu::ptx_op("ptx", &outs, sizes, n, ins, n)   (cuemu_ptx.cpp: a functional model of
                                                     the mbarrier / TMA / tcgen05 subset the library uses; anything else fails the launch)
-CUB's SortPairs / ExclusiveSum are host shims (include/cub/cub.cuh).  spmm_hot.cu (cp.async.bulk 1-D copies) is left out.
+CUB's SortPairs / ExclusiveSum are host shims (include/cub/cub.cuh).  Every .cu of the library is compiled.
 
     python -m tests.cuemu.build [--force]
 """
@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "mmssl_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libmmssl_emu.so")
-SOURCES = ["core.cu", "gan.cu", "eval.cu", "sgemm.cu", "adamw.cu", "rowops.cu", "loss.cu", "idfuse.cu", "sampler.cu", "spmm.cu", "graph.cu", "proj_common.cu", "regraph.cu", "shard.cu", "proj_tc.cu", "gemm_wide.cu"]
+SOURCES = ["core.cu", "gan.cu", "eval.cu", "sgemm.cu", "adamw.cu", "rowops.cu", "loss.cu", "idfuse.cu", "sampler.cu", "spmm.cu", "graph.cu", "proj_common.cu", "regraph.cu", "shard.cu", "proj_tc.cu", "gemm_wide.cu", "spmm_hot.cu"]
 HEADERS = ["common.cuh", "spmm_common.cuh", "tc_common.cuh"]
 CXX = os.environ.get("CXX", "g++")
 FLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-fno-strict-aliasing", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",

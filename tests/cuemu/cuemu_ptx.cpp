@@ -2,6 +2,7 @@
 //
 // Scope = exactly what csrc/tc_common.cuh, proj_tc.cu and gemm_wide.cu issue:
 //   mbarrier.init / arrive.expect_tx / try_wait.parity          phase + pending-arrival + transaction-byte counters
+//   cp.async.bulk (1-D) ... mbarrier::complete_tx::bytes       contiguous copy global -> shared (spmm_hot.cu)
 //   cp.async.bulk.tensor.2d ... mbarrier::complete_tx::bytes    box copy global -> shared through the tensor map: out-of-bounds
 //                                                               elements read as zero, SWIZZLE_128B (address bits [4:6] ^= [7:9])
 //   tcgen05.alloc / dealloc / relinquish_alloc_permit           a 128-lane x 512-column fp32 TMEM per block
@@ -115,7 +116,10 @@ void ptx_op(const char* text, void** outs, const int* out_sizes, int n_out, cons
         MBar& b = bar_at(in[0], false);
         b = MBar();
         b.init = true;
-        b.expected = b.pending = (int)in[1];
+        int count = 0;
+        if (n_in >= 2) count = (int)in[1];
+        else if (const char* c = strrchr(text, ',')) count = atoi(c + 1);          // immediate count in the template
+        b.expected = b.pending = count;
         if (b.expected <= 0) fail("mbarrier.init with a non-positive count");
         return;
     }
@@ -131,6 +135,16 @@ void ptx_op(const char* text, void** outs, const int* out_sizes, int n_out, cons
         const bool done = b.phase != parity;     // the phase with this parity has completed
         out32(outs, out_sizes, 0, done ? 1u : 0u);
         if (!done) yield_blocked();
+        return;
+    }
+    if (has("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes")) {      // 1-D bulk copy: dst, src, bytes, barrier
+        const uint64_t dst = in[0], bytes = in[2];
+        if ((dst % 16) || (in[1] % 16) || (bytes % 16)) fail("cp.async.bulk: addresses and size must be multiples of 16 bytes");
+        memcpy(smem_at(dst, bytes), reinterpret_cast<const void*>((uintptr_t)in[1]), bytes);
+        MBar& b = bar_at(in[3]);
+        b.tx -= (int64_t)bytes;
+        note_progress();
+        bar_check(b);
         return;
     }
     if (has("cp.async.bulk.tensor.2d")) {
