@@ -10,6 +10,7 @@ The default stays "simt" until gemm_wide.cu has passed its GPU test (it was writ
 from __future__ import annotations
 
 import os
+import weakref
 
 import torch
 
@@ -35,21 +36,24 @@ def _new(*shape, like):
 # ---- bf16 hi/lo operand splits of the Discriminator's weights are reused by every product of an iteration (W1 alone enters 6 of
 # them, 100 MB of traffic per split at Baby); activations are split per call.  Only tensors registered as weights are cached;
 # `adam` (the only writer of the weights on this path) drops the cache, `weights_changed()` does it for any other writer.
-_weight_ptrs = set()
+_weights = {}            # data_ptr -> weak reference to the registered tensor OBJECT (an address alone could be reused)
 _split_cache = {}
 
 
 def register_weights(tensors) -> None:
     for t in tensors:
-        _weight_ptrs.add(t.data_ptr())
+        _weights[t.data_ptr()] = weakref.ref(t)
 
 
 def weights_changed() -> None:
     _split_cache.clear()
+    for k in [k for k, r in _weights.items() if r() is None]:
+        del _weights[k]
 
 
 def _split(t, transposed: bool):
-    if t.data_ptr() not in _weight_ptrs:
+    ref = _weights.get(t.data_ptr())
+    if ref is None or ref() is not t:
         return ops.split_bf16_t(t) if transposed else ops.split_bf16(t)
     key = (t.data_ptr(), tuple(t.shape), transposed, t._version)
     hit = _split_cache.get(key)

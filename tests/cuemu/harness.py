@@ -85,7 +85,7 @@ class _Guard:
         buf = self.real_empty(n * es + 2 * self.PAD, dtype=torch.uint8)
         buf[:self.PAD] = 0xA5
         buf[self.PAD + n * es:] = 0xA5
-        view = buf[self.PAD:self.PAD + n * es].view(dtype).view(*shape) if n else self.real_empty(*shape, dtype=dtype)
+        view = buf[self.PAD:self.PAD + n * es].view(dtype).reshape(tuple(shape)) if n else self.real_empty(tuple(shape), dtype=dtype)
         if fill is not None and n:
             view.fill_(fill)
         if n:
