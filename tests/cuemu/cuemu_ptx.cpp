@@ -10,12 +10,14 @@
 //                                                               shared memory through K-major SWIZZLE_128B descriptors
 //   tcgen05.commit ... mbarrier::arrive::one                    (the model executes an MMA when it is issued, so commit = arrive)
 //   tcgen05.ld.sync.aligned.32x32b.x32                          lane t of warp w reads TMEM lane 32*(w%4)+t, 32 columns
+//   multimem.ld_reduce.add.v4.f32 / multimem.st.v4.f32         over multicast groups registered by the test (cuemu_mc_register):
+//                                                               several ranks' replicas in one process
 //   fences, prefetch.tensormap, tcgen05.wait::ld, griddepcontrol.wait   no-ops
 // What the model asserts on the way: 1024-byte aligned swizzled tiles, transaction bytes that add up, barrier phases, a warp
 // touching only its TMEM lane quarter, descriptor fields the kernels are supposed to encode.  It is calibrated by running
 // proj_tc.cu -- which is parity-green on real B200s -- through it (tests/test_emu_tensor_core.py): a kernel that passes here
 // and shares tc_common.cuh's descriptor / swizzle code with it differs from hardware-proven code only in its own logic.
-// It says nothing about timing, asynchrony bugs that need real concurrency, or PTX outside this list (multimem: fails).
+// It says nothing about timing, asynchrony bugs that need real concurrency, or PTX outside this list (fails the launch).
 #include <map>
 #include <string>
 #include <vector>
@@ -43,6 +45,19 @@ struct MBar {
     unsigned phase = 0;
 };
 std::map<uint32_t, MBar> g_bars;
+
+// NVSwitch multicast objects, for tests that play several ranks in one process: a fake "multicast address range" stands for n
+// replicas (one buffer per rank).  multimem.st writes every replica, multimem.ld_reduce.add sums them in rank order.
+struct McGroup { uint64_t base, bytes; std::vector<uint8_t*> replicas; };
+std::vector<McGroup> g_mc;
+const McGroup& mc_find(uint64_t addr, size_t bytes, uint64_t* off) {
+    for (const McGroup& g : g_mc)
+        if (addr >= g.base && addr + bytes <= g.base + g.bytes) { *off = addr - g.base; return g; }
+    fail("multimem: the address is not inside a registered multicast group");
+    static McGroup none{};
+    *off = 0;
+    return none;
+}
 std::vector<uint32_t> g_tmem;              // [128 lanes][512 columns]
 int g_tmem_cols = 0;
 
@@ -252,9 +267,42 @@ void ptx_op(const char* text, void** outs, const int* out_sizes, int n_out, cons
         for (int j = 0; j < 32; ++j) out32(outs, out_sizes, j, g_tmem[(size_t)(lane_base + cur->lane) * 512 + col0 + j]);
         return;
     }
+    if (has("multimem.ld_reduce") && has("add.v4.f32")) {
+        uint64_t off;
+        const McGroup& g = mc_find(in[0], 16, &off);
+        if (in[0] % 16) fail("multimem.ld_reduce.v4: misaligned address");
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (uint8_t* r : g.replicas) {
+            float v[4];
+            memcpy(v, r + off, 16);
+            for (int k = 0; k < 4; ++k) acc[k] += v[k];
+        }
+        for (int k = 0; k < 4; ++k) {
+            uint32_t u;
+            memcpy(&u, &acc[k], 4);
+            out32(outs, out_sizes, k, u);
+        }
+        return;
+    }
+    if (has("multimem.st") && has("v4.f32")) {
+        uint64_t off;
+        const McGroup& g = mc_find(in[0], 16, &off);
+        if (in[0] % 16) fail("multimem.st.v4: misaligned address");
+        uint32_t v[4] = {(uint32_t)in[1], (uint32_t)in[2], (uint32_t)in[3], (uint32_t)in[4]};
+        for (uint8_t* r : g.replicas) memcpy(r + off, v, 16);
+        return;
+    }
     (void)n_in;
     std::string m = std::string("inline PTX is not emulated: ") + text;
     fail(m.c_str());
 }
 
 }  // namespace cuemu
+
+extern "C" void cuemu_mc_register(uint64_t base, uint64_t bytes, int n, void** replicas) {
+    cuemu::McGroup g;
+    g.base = base; g.bytes = bytes;
+    for (int i = 0; i < n; ++i) g.replicas.push_back(static_cast<uint8_t*>(replicas[i]));
+    cuemu::g_mc.push_back(g);
+}
+extern "C" void cuemu_mc_clear() { cuemu::g_mc.clear(); }
