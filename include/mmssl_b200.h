@@ -306,6 +306,12 @@ int mmssl_gather_owned(const float* table, int64_t ld, const int64_t* idx, int64
                        int64_t ldo, void* stream);
 int mmssl_scatter_add_owned(float* table, int64_t ld, const int64_t* idx, int64_t lo, int64_t hi, int64_t n, int d,
                             const float* src, int64_t lds, void* stream);
+/* All-gather without NCCL: this rank's rows src[rows, d] are stored at dst (+ the same offset in every peer table):
+ * y_mode 1: dst is the NVSwitch MULTICAST address of the rank's row block in a symmetric table (one multimem.st per 16 bytes,
+ * replicated into every GPU's copy, the local one included); y_mode 2: dst is the local block, peers[n_peers] (host array) the
+ * peer-mapped addresses of the same block on the other GPUs; y_mode 0: plain local copy.  Same store paths as the SpMM epilogue. */
+int mmssl_publish_rows(const float* src, int64_t lds, int64_t rows, int d, float* dst, int64_t ldd, int y_mode, int n_peers,
+                       float* const* peers, void* stream);
 
 /* ------------------------------------------------------------------ modality-graph bookkeeping of the full step (regraph.cu)
  * mmssl_topk_rows: ids[rows, k] (int64) = columns of the k largest entries of every row of x[rows, w], best first, equal

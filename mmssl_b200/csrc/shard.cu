@@ -57,3 +57,43 @@ extern "C" int mmssl_scatter_add_owned(float* table, int64_t ld, const int64_t* 
     MMSSL_LAUNCH_OK();
     return 0;
 }
+
+// ---- all-gather of a rank's row block without NCCL: every rank PUBLISHES its rows into every rank's copy of the full table
+// (CUDA symmetric memory) -- one multimem.st per 16 bytes through the NVSwitch multicast address (y_mode 1; the switch replicates
+// the store, the local copy included), or a local store plus one NVLink store per peer-mapped table (y_mode 2).  The same store
+// paths as the SpMM epilogue (spmm.cu), for operands that are not SpMM outputs (projection, id fusion, parameter blocks,
+// gradients).  The caller orders producers and consumers with the symmetric memory's signal-pad barrier.
+namespace mmssl {
+struct PublishPeers { float* p[8]; };
+
+__global__ void __launch_bounds__(256) publish_rows_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int d4,
+                                                           float* dst, int64_t ldd, int y_mode, int n_peers, PublishPeers peers) {
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= rows * d4) return;
+    const int64_t r = t / d4;
+    const int c = (int)(t - r * d4) * 4;
+    const float4 v = ld4(src + r * lds + c);
+    const int64_t off = r * ldd + c;
+    if (y_mode == 1) {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+    } else {
+        st4(dst + off, v);
+        for (int q = 0; q < n_peers; ++q) st4(peers.p[q] + off, v);
+    }
+}
+}  // namespace mmssl
+
+extern "C" int mmssl_publish_rows(const float* src, int64_t lds, int64_t rows, int d, float* dst, int64_t ldd, int y_mode, int n_peers,
+                                  float* const* peers, void* stream_) {
+    MMSSL_REQUIRE(d % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && aligned16(src) && aligned16(dst), "alignment");
+    MMSSL_REQUIRE((y_mode == 1 && n_peers == 0) || (y_mode == 2 && n_peers >= 0 && n_peers <= 8) || (y_mode == 0 && n_peers == 0),
+                  "y_mode 0 (local), 1 (multicast address) or 2 (local + up to 8 peers)");
+    if (rows == 0) return 0;
+    PublishPeers pp{};
+    for (int q = 0; q < n_peers; ++q) { MMSSL_REQUIRE(aligned16(peers[q]), "peer table alignment"); pp.p[q] = peers[q]; }
+    publish_rows_kernel<<<(unsigned)((rows * (d / 4) + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(src, lds, rows, d / 4, dst, ldd, y_mode,
+                                                                                                     n_peers, pp);
+    MMSSL_LAUNCH_OK();
+    return 0;
+}

@@ -82,6 +82,52 @@ def scatter_add_owned(table: torch.Tensor, idx: torch.Tensor, lo: int, hi: int, 
                                            src.stride(0), stream()))
 
 
+def publish_rows(src: torch.Tensor, dst_local: torch.Tensor, y_mode: int = 0, y_raw: Optional[int] = None,
+                 y_peers: Optional[Sequence[int]] = None) -> None:
+    """mmssl_publish_rows: src -> the rank's row block of a (symmetric) table on every rank (see SymmetricTable.out_spec)."""
+    import ctypes as C
+    lib = _lib.load(require_device=True)
+    peers = list(y_peers or [])
+    arr = (C.c_void_p * max(len(peers), 1))(*peers)
+    dst = C.c_void_p(int(y_raw)) if y_mode == 1 else ptr(dst_local)
+    _lib.check(lib.mmssl_publish_rows(ptr(src), src.stride(0), src.shape[0], src.shape[1], dst, dst_local.stride(0), y_mode, len(peers), arr,
+                                      stream()))
+
+
+class MulticastExchange:
+    """The exchange of the row-sharded step WITHOUT NCCL: every operand lives in a full-size table in CUDA symmetric memory
+    (parallel.SymmetricTable, the class the fused SpMM + all-gather uses); a rank publishes its rows into every rank's copy with
+    ONE kernel -- multimem.st through the NVSwitch multicast address, or peer stores when the allocation has no multicast
+    address -- and ONE device-side signal-pad barrier orders producers and consumers.  Two tables per (row space, width) are
+    used alternately: a table is overwritten only two exchanges later, i.e. after a barrier that every rank can only have
+    reached once it had consumed the older contents.
+    Tables are created lazily, in the (identical) order the ranks first need them: creation is a collective rendezvous."""
+
+    def __init__(self, part_u: RowPartition, part_i: RowPartition, rank: int, device, group=None):
+        self.parts = {"u": part_u, "i": part_i}
+        self.rank, self.device, self.group = rank, device, group
+        self.tabs: Dict[Tuple[str, int], list] = {}
+        self.turn: Dict[Tuple[str, int], int] = {}
+
+    def _table(self, space: str, width: int):
+        from .parallel import SymmetricTable
+        key = (space, width)
+        if key not in self.tabs:
+            self.tabs[key] = [SymmetricTable(self.parts[space], width, self.rank, self.device, self.group) for _ in range(2)]
+            self.turn[key] = 0
+        t = self.tabs[key][self.turn[key]]
+        self.turn[key] ^= 1
+        return t
+
+    def gather(self, x: torch.Tensor, space: str) -> torch.Tensor:
+        tab = self._table(space, x.shape[1])
+        spec = tab.out_spec()
+        publish_rows(x, tab.local_rows(), y_mode=spec["y_mode"], y_raw=spec["y_raw"][0] if "y_raw" in spec else None,
+                     y_peers=spec["y_peers"][0] if "y_peers" in spec else None)
+        tab.barrier()
+        return tab.full()
+
+
 class RowShardedHotStep:
     """One rank of the row-sharded hot step.  ``params``: the rank's padded row blocks of the two embedding tables
     (``RowPartition.local``) and full copies of the five small parameters; ``feats``: FeatureStores of the rank's item rows;
@@ -89,13 +135,17 @@ class RowShardedHotStep:
 
     def __init__(self, params: Dict[str, torch.Tensor], feats: Sequence[FeatureStore], graphs: Sequence[RowBlockGraph],
                  cfg: HotStepConfig, batch: int, part_u: RowPartition, part_i: RowPartition, rank: int, group=None,
-                 optimizer_step: bool = True):
+                 optimizer_step: bool = True, exchange: str = "nccl"):
         self.cfg, self.batch, self.pu, self.pi, self.rank, self.group = cfg, batch, part_u, part_i, rank, group
         self.P = {k: params[k] for k in LIVE}
         self.feats, self.graphs = tuple(feats), tuple(graphs)
         self.engine = Engine(cfg.embed_size, cfg.n_layers, cfg.head_num, cfg.id_cat_rate, cfg.model_cat_rate, cfg.proj_impl)
         self.engine.two_streams = False                     # the collectives order the work on one stream
         self.engine.exchange = self._exchange
+        # "nccl": all_gather_into_tensor (gloo in the CPU tests); "multicast": MulticastExchange (symmetric memory, no NCCL)
+        self.mc = MulticastExchange(part_u, part_i, rank, self.P[P_EU].device, group) if exchange == "multicast" and part_u.world > 1 else None
+        if exchange not in ("nccl", "multicast"):
+            raise ValueError("exchange must be 'nccl' or 'multicast'")
         self.optimizer_step = optimizer_step
         self.n_gathers, self.gathered_bytes = 0, 0
         dev = self.P[P_EU].device
@@ -141,7 +191,7 @@ class RowShardedHotStep:
         for x in xs:
             self.n_gathers += 1
             self.gathered_bytes += x.numel() * x.element_size() * (part.world - 1)
-            out.append(all_gather_rows(x, part, self.group))
+            out.append(self.mc.gather(x.contiguous(), space) if self.mc is not None else all_gather_rows(x, part, self.group))
         return out
 
     def _masks(self):

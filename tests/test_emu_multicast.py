@@ -81,3 +81,26 @@ def test_spmm_epilogue_multicast_store(emu):
         want[rank * block:(rank + 1) * block] = torch.from_numpy(m.tocsr() @ x.double().numpy())
     for t in tables:                                                      # both ranks hold both row blocks
         assert rel_err(t, want) < 2e-6
+
+
+@pytest.mark.parametrize("y_mode", [1, 2])
+def test_publish_rows_is_an_all_gather(emu, y_mode):
+    """mmssl_publish_rows played for 3 ranks: afterwards every rank's table holds every rank's row block -- through the fake
+    multicast address (mode 1) and through peer pointers (mode 2); strided source (a column half of a wider buffer)."""
+    from mmssl_b200.rowshard_step import publish_rows
+    world, block, d = 3, 17, 64
+    g = torch.Generator().manual_seed(y_mode)
+    tables = [torch.zeros(world * block, d) for _ in range(world)]
+    keep, mc = _register(emu, tables)
+    wide = [torch.randn(block, 2 * d, generator=g) for _ in range(world)]
+    for rank in range(world):
+        src = wide[rank][:, d:]                                            # ld = 2d
+        local = tables[rank][rank * block:(rank + 1) * block]
+        off = rank * block * d * 4
+        if y_mode == 1:
+            publish_rows(src, local, y_mode=1, y_raw=mc + off)
+        else:
+            publish_rows(src, local, y_mode=2, y_peers=[tables[r].data_ptr() + off for r in range(world) if r != rank])
+    want = torch.cat([w[:, d:] for w in wide])
+    for t in tables:
+        assert torch.equal(t, want)

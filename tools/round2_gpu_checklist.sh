@@ -34,4 +34,5 @@ run 600 fullstep_tc.json python tools/fullstep_bench.py baby --gemm tc --steps 2
 # 6. launch list of the full step (one iteration under ncu, serialised)
 run 900 ncu_fullstep.log ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/fullstep_launches.csv \
     python tools/fullstep_bench.py baby --gemm simt --steps 1 --warmup 3 --cpu-steps 0
+# (multi-GPU, separate call with --gpus 2):  torchrun --nproc-per-node 2 --master-addr 127.0.0.1 tools/rowshard_step_bench.py sports check [mc]
 echo done | tee -a gpurun_out/checklist.log

@@ -1,7 +1,7 @@
 """Row-sharded WHOLE hot step (mmssl_b200/rowshard_step.py) on N GPUs of one box: parity against the single-GPU
 fused HotStep on the same problem (`check`) and time per step (CUDA events, max over ranks).  One JSON line from rank 0.
 
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/rowshard_step_bench.py [config] [check] [--steps K] [--batch B]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/rowshard_step_bench.py [config] [check] [mc] [--steps K] [--batch B]     (mc: exchange through the multicast publish kernel instead of NCCL)
 
 Written when round 1 had no GPU time left; the same class runs in tests/test_dist_emu.py with 2 gloo ranks on the CPU emulator."""
 import json
@@ -20,7 +20,7 @@ from mmssl_b200.rowshard_step import RowShardedHotStep, shard_problem  # noqa: E
 from mmssl_b200.synthetic import TripleSampler  # noqa: E402
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
-name = args[0] if args and args[0] != "check" else "tiktok"
+name = args[0] if args and args[0] not in ("check", "mc") else "tiktok"
 check = "check" in args
 steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 20
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -32,13 +32,14 @@ B = int(sys.argv[sys.argv.index("--batch") + 1]) if "--batch" in sys.argv else b
 ds, P_cpu, feats_cpu, _, _ = bench.build_problem(name, 2022, None)           # the same seeded problem on every rank (host)
 cfg = HotStepConfig(embed_size=ds.embed_size, n_layers=ds.n_layers, batch_size=B)
 Pl, fl, gl, pu, pi = shard_problem(P_cpu, feats_cpu, ds.ui_norm, ds.iu_norm, rank, world, dev)
-sh = RowShardedHotStep(Pl, fl, gl, cfg, B, pu, pi, rank)
+mode = "multicast" if "mc" in args and world > 1 else "nccl"
+sh = RowShardedHotStep(Pl, fl, gl, cfg, B, pu, pi, rank, exchange=mode)
 smp = TripleSampler(ds.train, seed=2022)
 batches = [tuple(torch.from_numpy(x).to(dev) for x in smp.sample(B)) for _ in range(4)]
 g = torch.Generator().manual_seed(7)
 full_masks = tuple(((torch.rand(ds.n_items, ds.embed_size, generator=g) >= cfg.drop_rate) / (1 - cfg.drop_rate)).float() for _ in range(2))
 sh.masks = tuple(pi.local(m, rank).to(dev) for m in full_masks)
-res = {"config": name, "n_gpus": world, "scheme": "row-sharded whole hot step, NCCL all-gather per SpMM operand", "batch": B}
+res = {"config": name, "n_gpus": world, "scheme": "row-sharded whole hot step", "exchange": ("publish kernel over NVSwitch multicast / peer stores + signal-pad barrier (no NCCL)" if mode == "multicast" else "NCCL all-gather per SpMM operand"), "batch": B}
 
 if check:
     _, Pd, feats, graphs, _ = bench.build_problem(name, 2022, dev)
