@@ -312,6 +312,9 @@ int mmssl_scatter_add_owned(float* table, int64_t ld, const int64_t* idx, int64_
  * peer-mapped addresses of the same block on the other GPUs; y_mode 0: plain local copy.  Same store paths as the SpMM epilogue. */
 int mmssl_publish_rows(const float* src, int64_t lds, int64_t rows, int d, float* dst, int64_t ldd, int y_mode, int n_peers,
                        float* const* peers, void* stream);
+/* All-reduce(sum) without NCCL: dst[0..n) = sum over the ranks' copies of a symmetric buffer, read through its multicast address
+ * (multimem.ld_reduce, the switch adds the replicas).  The caller barriers all ranks before (contributions written) and after. */
+int mmssl_mc_allreduce_sum(const float* src_mc, float* dst, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------ modality-graph bookkeeping of the full step (regraph.cu)
  * mmssl_topk_rows: ids[rows, k] (int64) = columns of the k largest entries of every row of x[rows, w], best first, equal

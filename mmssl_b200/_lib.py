@@ -107,6 +107,7 @@ _SIGS = {
     "mmssl_gather_owned": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "mmssl_scatter_add_owned": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "mmssl_publish_rows": (C.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_i64, c_i32, c_i32, C.POINTER(c_vp), c_vp]),
+    "mmssl_mc_allreduce_sum": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "mmssl_topk_rows": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp]),
     "mmssl_pair_append": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "mmssl_degree_values": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
@@ -136,7 +137,7 @@ KERNELS_PER_CALL = {
     "mmssl_gan_head_fwd": 2, "mmssl_gan_head_bwd": 1, "mmssl_gan_gp_rows": 2, "mmssl_gan_gp_head_rev": 2, "mmssl_gan_usim_finish": 1,
     "mmssl_gan_usim_bwd_pre": 1, "mmssl_gan_real_rows": 1, "mmssl_gan_interpolate": 1, "mmssl_gan_add_scaled": 1,
     "mmssl_gan_gather_rows": 1, "mmssl_gan_scatter_add_rows": 1,
-    "mmssl_topk_rows": 1, "mmssl_pair_append": 1, "mmssl_degree_values": 2, "mmssl_gather_owned": 1, "mmssl_scatter_add_owned": 1, "mmssl_publish_rows": 1,
+    "mmssl_topk_rows": 1, "mmssl_pair_append": 1, "mmssl_degree_values": 2, "mmssl_gather_owned": 1, "mmssl_scatter_add_owned": 1, "mmssl_publish_rows": 1, "mmssl_mc_allreduce_sum": 1,
 }
 launch_count = 0
 call_log = None   # set to a list to record (name) of every kernel-launching call

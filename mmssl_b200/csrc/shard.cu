@@ -97,3 +97,28 @@ extern "C" int mmssl_publish_rows(const float* src, int64_t lds, int64_t rows, i
     MMSSL_LAUNCH_OK();
     return 0;
 }
+
+// ---- all-reduce(sum) without NCCL: every rank wrote its contribution into its copy of a symmetric buffer; after a barrier each
+// rank reads the SUM over all copies through the buffer's multicast address (multimem.ld_reduce: the switch adds the replicas)
+// into a private result.  A second barrier lets the buffer be rewritten.  Used for the [5, B, d] batch rows and the small
+// replicated gradients of the row-sharded step.
+namespace mmssl {
+__global__ void __launch_bounds__(256) mc_allreduce_kernel(const float* src_mc, float* __restrict__ dst, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+        float4 v;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src_mc + i * 4) : "memory");
+        st4(dst + i * 4, v);
+    }
+}
+}  // namespace mmssl
+
+extern "C" int mmssl_mc_allreduce_sum(const float* src_mc, float* dst, int64_t n, void* stream_) {
+    MMSSL_REQUIRE(n >= 0 && n % 4 == 0 && aligned16(src_mc) && aligned16(dst), "count must be a multiple of 4 floats, 16-byte aligned buffers");
+    if (n == 0) return 0;
+    int64_t blocks = (n / 4 + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    mc_allreduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(src_mc, dst, n / 4);
+    MMSSL_LAUNCH_OK();
+    return 0;
+}

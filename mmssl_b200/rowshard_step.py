@@ -128,6 +128,34 @@ class MulticastExchange:
         return tab.full()
 
 
+class MulticastAllReduce:
+    """Sum over the ranks of a flat fp32 buffer without NCCL: ``buffer`` (this rank's copy of a symmetric allocation) is where
+    the contribution is written; ``reduce_into(out)`` = barrier, one kernel reading the sum through the multicast address
+    (mmssl_mc_allreduce_sum), barrier.  Needs an NVSwitch multicast address (raises otherwise: the caller keeps NCCL then)."""
+
+    def __init__(self, numel: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        n = (numel + 3) // 4 * 4
+        g = group if group is not None else dist.group.WORLD
+        self.buffer = symm.empty(n, dtype=torch.float32, device=device)
+        self.buffer.zero_()
+        self.h = symm.rendezvous(self.buffer, g.group_name)
+        self.mc = int(self.h.multicast_ptr)
+        if self.mc == 0:
+            raise RuntimeError("NVSwitch multicast is not available for symmetric memory on this system")
+        torch.cuda.synchronize(device)
+        self.h.barrier()
+
+    def reduce_into(self, out: torch.Tensor) -> torch.Tensor:
+        import ctypes as C
+        lib = _lib.load(require_device=True)
+        assert out.is_contiguous() and out.numel() % 4 == 0 and out.numel() <= self.buffer.numel()
+        self.h.barrier()                         # every rank's contribution is in its copy
+        _lib.check(lib.mmssl_mc_allreduce_sum(C.c_void_p(self.mc), ptr(out), out.numel(), stream()))
+        self.h.barrier()                         # every rank has read: the buffer may be rewritten
+        return out
+
+
 class RowShardedHotStep:
     """One rank of the row-sharded hot step.  ``params``: the rank's padded row blocks of the two embedding tables
     (``RowPartition.local``) and full copies of the five small parameters; ``feats``: FeatureStores of the rank's item rows;
@@ -153,6 +181,8 @@ class RowShardedHotStep:
         f = dict(dtype=torch.float32, device=dev)
         self.idx = torch.zeros(3, B, dtype=torch.int64, device=dev)
         self.rows = torch.zeros(5, B, d, **f)               # u_f[users], i_f[pos], i_f[neg], Uvid[users], Utid[users]
+        self.rows_part = self.rows                          # where the rank's contribution is written (== rows with NCCL: in place)
+        self.ar_rows = self.ar_flat = None
         self.g_rows = torch.zeros(5, B, d, **f)
         self.g_uf = torch.zeros(part_u.block, d, **f)
         self.g_if = torch.zeros(part_i.block, d, **f)
@@ -172,9 +202,21 @@ class RowShardedHotStep:
         # the small replicated gradients travel in one flat buffer
         n = sum((self.grads[k].numel() + 3) // 4 * 4 for k in REPLICATED)
         self._flat = torch.zeros(n, **f)
+        self._flat_part = self._flat
+        if self.mc is not None:                             # all-reduce through multimem.ld_reduce instead of NCCL, when there is multicast
+            try:
+                self.ar_rows = MulticastAllReduce(5 * B * d, dev, group)
+                self.ar_flat = MulticastAllReduce(n, dev, group)
+                self.rows_part = self.ar_rows.buffer[:5 * B * d].view(5, B, d)
+                self._flat_part = self.ar_flat.buffer[:n]
+            except RuntimeError:
+                self.ar_rows = self.ar_flat = None
+        # Engine.backward writes the small gradients into views of the contribution buffer; AdamW reads views of the reduced one
+        self.grads_part = dict(self.grads)
         o = 0
         for k in REPLICATED:
             g = self.grads[k]
+            self.grads_part[k] = self._flat_part[o:o + g.numel()].view_as(g)
             self.grads[k] = self._flat[o:o + g.numel()].view_as(g)
             o += (g.numel() + 3) // 4 * 4
 
@@ -221,13 +263,16 @@ class RowShardedHotStep:
         u_f, i_f, _, _, _, _, u_vid, u_tid, _, _ = outs
         alias = self.alias
         # ---- the batch rows of the full tables: owned rows + one all-reduce
-        gather_owned(u_f, users, ulo, uhi, self.rows[0])
-        gather_owned(i_f, pos, ilo, ihi, self.rows[1])
-        gather_owned(i_f, neg, ilo, ihi, self.rows[2])
-        gather_owned(u_vid, users, ulo, uhi, self.rows[3])
+        part = self.rows_part
+        gather_owned(u_f, users, ulo, uhi, part[0])
+        gather_owned(i_f, pos, ilo, ihi, part[1])
+        gather_owned(i_f, neg, ilo, ihi, part[2])
+        gather_owned(u_vid, users, ulo, uhi, part[3])
         if not alias:
-            gather_owned(u_tid, users, ulo, uhi, self.rows[4])
-        if self.pu.world > 1:
+            gather_owned(u_tid, users, ulo, uhi, part[4])
+        if self.ar_rows is not None:
+            self.ar_rows.reduce_into(self.rows)
+        elif self.pu.world > 1:
             dist.all_reduce(self.rows, op=dist.ReduceOp.SUM, group=self.group)
         ub, pb, nb, zv, zt = self.rows
         g_ub, g_pb, g_nb, g_zv, g_zt = self.g_rows
@@ -258,8 +303,12 @@ class RowShardedHotStep:
                 scatter_add_owned(self.g_utid, users, ulo, uhi, g_zt)
         grads = [self.g_uf, self.g_if, None, None, None, None, self.g_uvid if st.fused else None,
                  (None if alias else self.g_utid) if st.fused else None, None, None]
-        self.engine.backward(st, self.P, self.feats, grads, feat_reg_coef=cfg.feat_reg_decay / self.pi.n, out=self.grads)
-        if self.pu.world > 1:                               # dW, db, dWcat: sums over the ranks' rows
+        self.engine.backward(st, self.P, self.feats, grads, feat_reg_coef=cfg.feat_reg_decay / self.pi.n, out=self.grads_part)
+        for k in (P_EU, P_EI):                              # the table gradients are private to the rank (same tensors in both dicts)
+            self.grads[k] = self.grads_part[k]
+        if self.ar_flat is not None:                        # dW, db, dWcat: sums over the ranks' rows
+            self.ar_flat.reduce_into(self._flat)
+        elif self.pu.world > 1:
             dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
         if self.optimizer_step:
             ops.step_tick(self.step_dev)

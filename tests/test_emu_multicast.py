@@ -104,3 +104,18 @@ def test_publish_rows_is_an_all_gather(emu, y_mode):
     want = torch.cat([w[:, d:] for w in wide])
     for t in tables:
         assert torch.equal(t, want)
+
+
+def test_multicast_all_reduce_kernel(emu):
+    """mmssl_mc_allreduce_sum for 3 ranks: everyone reads the sum of the three copies through the (fake) multicast address."""
+    from mmssl_b200 import _lib
+    lib = _lib.load()
+    world, n = 3, 4 * 333
+    g = torch.Generator().manual_seed(9)
+    copies = [torch.randn(n, generator=g) for _ in range(world)]
+    keep, mc = _register(emu, copies)
+    want = copies[0].double() + copies[1].double() + copies[2].double()
+    for rank in range(world):
+        out = torch.empty(n)
+        _lib.check(lib.mmssl_mc_allreduce_sum(C.c_void_p(mc), _lib.ptr(out), n, None))
+        assert rel_err(out, want) < 1e-6
