@@ -200,7 +200,8 @@ class RowShardedHotStep:
         self.masks: Optional[tuple] = None                  # injected [I_block, d] keep-masks of the rank's item rows
         self.training = True
         # the small replicated gradients travel in one flat buffer
-        n = sum((self.grads[k].numel() + 3) // 4 * 4 for k in REPLICATED)
+        n = sum((self.grads[k].numel() + 3) // 4 * 4 for k in REPLICATED) + 4      # + one slot for the local feat_reg term
+        self._feat_slot = n - 4
         self._flat = torch.zeros(n, **f)
         self._flat_part = self._flat
         if self.mc is not None:                             # all-reduce through multimem.ld_reduce instead of NCCL, when there is multicast
@@ -288,11 +289,6 @@ class RowShardedHotStep:
         nce1, nce2 = parts[0], parts[-1]
         ops.loss_assemble(bpr_part, n_bpr, B, reg_coef, st.sumsq_u, st.sumsq_i, 0.5 * cfg.feat_reg_decay / self.pi.n, nce1, nce2, B,
                           cfg.cl_rate, self.out5)
-        if self.pu.world > 1:                               # feat_reg was summed over the local rows only
-            feat = self.out5[3].clone()
-            dist.all_reduce(feat, op=dist.ReduceOp.SUM, group=self.group)
-            self.out5[0] += feat - self.out5[3]
-            self.out5[3] = feat
         # ---- gradient rows go back to their owners
         scatter_add_owned(self.g_uf, users, ulo, uhi, g_ub)
         scatter_add_owned(self.g_if, pos, ilo, ihi, g_pb)
@@ -304,12 +300,18 @@ class RowShardedHotStep:
         grads = [self.g_uf, self.g_if, None, None, None, None, self.g_uvid if st.fused else None,
                  (None if alias else self.g_utid) if st.fused else None, None, None]
         self.engine.backward(st, self.P, self.feats, grads, feat_reg_coef=cfg.feat_reg_decay / self.pi.n, out=self.grads_part)
+        self._flat_part[self._feat_slot:self._feat_slot + 1] = self.out5[3:4]       # feat_reg was summed over the local rows only:
+                                                                                    # it rides along with the small gradients
         for k in (P_EU, P_EI):                              # the table gradients are private to the rank (same tensors in both dicts)
             self.grads[k] = self.grads_part[k]
         if self.ar_flat is not None:                        # dW, db, dWcat: sums over the ranks' rows
             self.ar_flat.reduce_into(self._flat)
         elif self.pu.world > 1:
             dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
+        if self.pu.world > 1:
+            feat = self._flat[self._feat_slot]
+            self.out5[0] += feat - self.out5[3]
+            self.out5[3] = feat
         if self.optimizer_step:
             ops.step_tick(self.step_dev)
             keys = list(LIVE)
