@@ -68,3 +68,34 @@ def test_full_step_other_shapes_vs_oracle(monkeypatch, d, I):
     harness.set_order("fwd")
     harness.emulated_device(monkeypatch)
     fullstep_check.random_problem_check("cpu", d=d, I=I)
+
+
+def test_steady_state_body_has_no_host_reads(monkeypatch):
+    """CUDA-graph capturability of the steady-state iteration, as far as it can be checked without a GPU: no tensor is read back
+    by the host (item / tolist / cpu / numpy / float() / int() / bool() / index) anywhere inside FullStep._body."""
+    import torch
+    from mmssl_b200 import gan_ops
+    harness.set_order("fwd")
+    harness.emulated_device(monkeypatch)
+    monkeypatch.setattr(gan_ops, "GEMM_IMPL", "tc")
+    z, c = fullstep_check.load_trace()
+    fs, P, t = fullstep_check.build(z, c, "cpu", proj_impl="tc")
+    for s in range(3):
+        fs.step(*(t(z["sample"][s][j]) for j in range(3)))
+    assert fs.steady()
+    hits, state = [], {"on": False}
+
+    def trap(name, orig):
+        def f(self, *a, **k):
+            if state["on"] and self.numel() >= 1:
+                hits.append(name)
+            return orig(self, *a, **k)
+        return f
+    for name in ("item", "tolist", "cpu", "numpy", "__float__", "__int__", "__bool__", "__index__"):
+        monkeypatch.setattr(torch.Tensor, name, trap(name, getattr(torch.Tensor, name)))
+    draws = fs._draws(None, None, None, None, None)
+    fs.hs.set_indices(*(t(z["sample"][0][j]) for j in range(3)))
+    state["on"] = True
+    fs._body(*draws)
+    state["on"] = False
+    assert hits == []
