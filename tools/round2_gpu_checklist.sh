@@ -34,5 +34,10 @@ run 600 fullstep_tc.json python tools/fullstep_bench.py baby --gemm tc --steps 2
 # 6. launch list of the full step (one iteration under ncu, serialised)
 run 900 ncu_fullstep.log ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/fullstep_launches.csv \
     python tools/fullstep_bench.py baby --gemm simt --steps 1 --warmup 3 --cpu-steps 0
+# 7. one full capture of the wide tensor-core GEMM and of the large CUDA-core GEMM (read here with `ncu -i ... --page raw --csv`)
+run 900 ncu_gemm_wide.log ncu --set full --clock-control none --import-source on -k regex:gemm_wide_kernel -c 2 -f -o gpurun_out/gemm_wide \
+    python tools/fullstep_bench.py baby --gemm tc --steps 1 --warmup 2 --cpu-steps 0
+run 900 ncu_sgemm_large.log ncu --set full --clock-control none --import-source on -k regex:sgemm_large_kernel -c 2 -f -o gpurun_out/sgemm_large \
+    python tools/fullstep_bench.py baby --gemm simt --steps 1 --warmup 2 --cpu-steps 0
 # (multi-GPU, separate call with --gpus 2):  torchrun --nproc-per-node 2 --master-addr 127.0.0.1 tools/rowshard_step_bench.py sports check [mc]
 echo done | tee -a gpurun_out/checklist.log
