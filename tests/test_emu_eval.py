@@ -47,3 +47,27 @@ def test_eval_many_compactions(emu):
 
     users = np.arange(U, dtype=np.int64)[::-1].copy()
     E._check_against_oracle(ev, ua, ia, users, csr(train), csr(held), Ks, False)
+
+
+def test_eval_random_tie_heavy_cases(emu):
+    """Small-integer embeddings (many exactly equal scores), random sizes, widths, cut-offs, training rows from empty to almost
+    everything: ranking incl. tie order, hit lists and fp64 metrics exactly equal to the oracle."""
+    from mmssl_b200.evaluate import Evaluator
+    rng = np.random.default_rng(123)
+    for case in range(12):
+        U, I = int(rng.integers(1, 40)), int(rng.integers(1, 700))
+        d = int(rng.choice([4, 8, 64, 128]))
+        Ks = sorted(set(int(k) for k in rng.integers(1, 65, int(rng.integers(1, 4)))))
+        ua = rng.integers(-2, 3, (U, d)).astype(np.float32)
+        ia = rng.integers(-2, 3, (I, d)).astype(np.float32)
+        train = {u: sorted(rng.choice(I, size=int(rng.integers(0, I)), replace=False).tolist()) for u in range(U)}
+        held = {u: rng.choice(I, size=int(rng.integers(1, min(6, I) + 1)), replace=False).tolist() for u in range(U)}
+        ev = Evaluator({u: v for u, v in train.items() if v}, held, {}, U, I, Ks)
+
+        def csr(rows):
+            ptr = np.zeros(U + 1, np.int64)
+            for u in range(U):
+                ptr[u + 1] = ptr[u] + len(rows.get(u, []))
+            idx = np.concatenate([np.sort(np.asarray(rows.get(u, []), np.int64)) for u in range(U)]) if ptr[-1] else np.zeros(0, np.int64)
+            return ptr, idx
+        E._check_against_oracle(ev, ua, ia, rng.permutation(U).astype(np.int64), csr(train), csr(held), Ks, False)
