@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = the count that measured fastest on this host class (tools/cpu_threads.py)")
     ap.add_argument("--seed", type=int, default=2022)
+    ap.add_argument("--batch", type=int, default=BATCH,
+                    help="triples per GPU per step (reference default 1024, parser.py:54; SURVEY 8d also asks for 16384 at the synthetic configs)")
     ap.add_argument("--dp", default="fused", choices=["fused", "nccl"],
                     help="N>1 optimiser step: 'fused' = one multimem kernel (reduce-scatter + sharded AdamW + all-gather over "
                          "NVSwitch multicast, falls back to nccl when multicast is unavailable); 'nccl' = all-reduce + replicated AdamW")
@@ -384,7 +386,9 @@ def cpu_full_step_baseline(name, seed, steps, batch, d_state, threads=0):
 
 # ----------------------------------------------------------------------------------------------
 def main():
+    global BATCH
     a = parse()
+    BATCH = a.batch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
