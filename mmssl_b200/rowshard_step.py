@@ -320,6 +320,38 @@ class RowShardedHotStep:
         return self.out5
 
 
+def _capture_methods():
+    def capture(self, warmup: int = 2) -> None:
+        """Capture ``run`` into a CUDA graph (static buffers; update the indices with ``set_indices`` between replays).  Only with the
+        multicast exchange or a single rank: every exchange is then a kernel plus a device-side signal-pad barrier, which a graph
+        can hold; NCCL collectives inside a capture hung in round 1 and are refused here.  EXPERIMENTAL until its first GPU run."""
+        if self.pu.world > 1 and self.mc is None:
+            raise RuntimeError("capture() needs exchange='multicast' (NCCL collectives are not captured)")
+        if self.pu.world > 1 and self.ar_rows is None:
+            raise RuntimeError("capture() needs the multicast all-reduce (no NVSwitch multicast address on this system)")
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.run()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self._graph = g
+
+    def replay(self) -> torch.Tensor:
+        if getattr(self, "_graph", None) is None:
+            raise RuntimeError("call capture() first")
+        self._graph.replay()
+        return self.out5
+    return capture, replay
+
+
+RowShardedHotStep.capture, RowShardedHotStep.replay = _capture_methods()
+
+
 def shard_problem(P_full: Dict[str, torch.Tensor], feats_full: Sequence[torch.Tensor], ui_norm, iu_norm, rank: int, world: int, device):
     """Rank-local pieces of a full problem: (params, FeatureStores, six RowBlockGraphs with the modality graphs aliased,
     part_u, part_i).  The full problem only has to exist on the host."""

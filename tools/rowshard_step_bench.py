@@ -1,7 +1,7 @@
 """Row-sharded WHOLE hot step (mmssl_b200/rowshard_step.py) on N GPUs of one box: parity against the single-GPU
 fused HotStep on the same problem (`check`) and time per step (CUDA events, max over ranks).  One JSON line from rank 0.
 
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/rowshard_step_bench.py [config] [check] [mc] [--steps K] [--batch B]     (mc: exchange through the multicast publish kernel instead of NCCL)
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/rowshard_step_bench.py [config] [check] [mc] [graph] [--steps K] [--batch B]     (mc: exchange through the multicast publish kernel instead of NCCL)
 
 Written when round 1 had no GPU time left; the same class runs in tests/test_dist_emu.py with 2 gloo ranks on the CPU emulator."""
 import json
@@ -20,7 +20,7 @@ from mmssl_b200.rowshard_step import RowShardedHotStep, shard_problem  # noqa: E
 from mmssl_b200.synthetic import TripleSampler  # noqa: E402
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
-name = args[0] if args and args[0] not in ("check", "mc") else "tiktok"
+name = args[0] if args and args[0] not in ("check", "mc", "graph") else "tiktok"
 check = "check" in args
 steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 20
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -60,8 +60,13 @@ if check:
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
     res["max_rel_err_vs_1gpu"] = float(e)
 
+use_graph = "graph" in args
+if use_graph:
+    sh.set_indices(*batches[0])
+    sh.capture()
+step = sh.replay if use_graph else sh.run
 for s in range(3):
-    sh.set_indices(*batches[s % 4]); sh.run()
+    sh.set_indices(*batches[s % 4]); step()
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
@@ -69,14 +74,14 @@ sh.n_gathers = sh.gathered_bytes = 0
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
 for s in range(steps):
-    sh.set_indices(*batches[s % 4]); sh.run()
+    sh.set_indices(*batches[s % 4]); step()
 b.record()
 torch.cuda.synchronize()
 ms = torch.tensor([a.elapsed_time(b) / steps], device=dev)
 if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 res.update(ms_per_step=round(float(ms), 4), triples_per_s=round(B / float(ms) * 1e3, 1), gathers_per_step=sh.n_gathers // steps,
-           gathered_MB_per_rank_per_step=round(sh.gathered_bytes / steps / 1e6, 2), graph_capture=False)
+           gathered_MB_per_rank_per_step=round(sh.gathered_bytes / steps / 1e6, 2), graph_capture=use_graph)
 if rank == 0:
     print(json.dumps(res))
 if world > 1:
