@@ -346,6 +346,9 @@ int mmssl_gemm_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, c
 int mmssl_gemm_bf16x3_wide(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi,
                            const uint16_t* b_lo, int64_t ldb, int64_t m, int64_t n, int64_t k, float alpha, int accumulate,
                            float* c, int64_t ldc, void* stream);
+/* Tuning / test knob of the kernel above: k-blocks (64 of K each) chained into one TMEM accumulator before the epilogue folds
+ * the pass into C with fp32 adds (default 16 = 1024 of K; bounds the tensor core's accumulation error, gemm_wide.cu). */
+int mmssl_gemm_wide_set_chunk(int k_blocks);
 /* y[m][ldy + col_off] = (sum_s partial[s][m][n] + bias[n]) * mask[m][n]     (bias / mask may be NULL) */
 int mmssl_proj_epilogue(const float* partial, int split_k, int64_t m, int64_t n, const float* bias, const float* mask,
                         int64_t ldm, float* y, int64_t ldy, float* y_pre, int64_t ldyp, void* stream);

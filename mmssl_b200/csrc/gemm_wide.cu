@@ -9,12 +9,18 @@
 //
 // Same anatomy as proj_tc.cu (warp 0 = TMA producer, warp 1 = TMEM alloc + single-thread MMA issuer, warps 2-5 = epilogue),
 // but tiled over N as well: CTA (m_tile, n_tile) owns a 128 x NT tile of C for the whole K range (no split-K: every
-// shape on this path gives >= 100 tiles), accumulates it in NT TMEM columns and writes it straight to C with the alpha /
-// beta epilogue.  Both operands are re-read from L2 by the other tiles of their row / column of the grid, so both are
+// shape on this path gives >= 100 tiles).
+//
+// Accumulation length is bounded: the tensor core's fp32 accumulate is not round-to-nearest, so its error grows with the
+// number of MMAs chained into one TMEM accumulator (round 1 on hardware: K = 7050 in one pass -> 2.8e-5 max-norm error, while
+// the split-K projection kernel stays under 1e-5 at the same K).  The K range is therefore cut into passes of `chunk_kb`
+// k-blocks (default 16 = 1024 of K = 192 chained MMAs); each pass accumulates into one of TWO TMEM buffers (2 x NT columns)
+// and the epilogue warps fold a finished pass into C with round-to-nearest fp32 adds (C (+)= alpha * pass; C is L2-resident)
+// while the MMA warp is already filling the other buffer.  Both operands are re-read from L2 by the other tiles of their row / column of the grid, so both are
 // hinted evict-last (the policy constant proj_tc.cu already uses on hardware).  Rows / columns beyond m / n: TMA zero-fills the loads, the epilogue masks the stores;
 // C's leading dimension is arbitrary (I/4 is not a multiple of 4), 128-bit stores are used when the row is aligned.
 //
-// NOT YET RUN ON A GPU (written when round 1 had no GPU time left).  It has been executed on the CPU through a functional model
+// Executed on the CPU through a functional model
 // of the PTX it issues (tests/cuemu/cuemu_ptx.cpp, calibrated on proj_tc.cu which is green on hardware; tests/test_emu_tensor_core.py:
 // multi-tile N, ragged edges, both epilogues; a wrong TMA coordinate, barrier phase or epilogue row mapping is caught there).
 // Its GPU test (tests/test_gpu_zzz_gemm_wide.py, sorts last) runs with the suite; mmssl_b200.gan_ops keeps the fp32 CUDA-core GEMM
@@ -39,14 +45,15 @@ template <int NT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_wide_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                 float* __restrict__ C, int64_t ldc, int M, int Ntot, int nkb, float alpha, int accumulate) {
+                 float* __restrict__ C, int64_t ldc, int M, int Ntot, int nkb, int chunk_kb, float alpha, int accumulate) {
     using Cfg = WideCfg<NT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
     uint64_t* empty_bar = full_bar + Cfg::kStages;
-    uint64_t* accum_bar = empty_bar + Cfg::kStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* acc_full = empty_bar + Cfg::kStages;      // [2]: a pass is complete in TMEM buffer b
+    uint64_t* acc_empty = acc_full + 2;                 // [2]: the epilogue warps have drained buffer b
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x, n_tile = blockIdx.y;
@@ -60,11 +67,11 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-            mbar_init(accum_bar, 1);
+            for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(NT) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * NT) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -92,6 +99,12 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % Cfg::kStages;
                 const uint32_t ph = (uint32_t)(i / Cfg::kStages) & 1u;
+                const int pass = i / chunk_kb, j = i - pass * chunk_kb, b = pass & 1;
+                if (j == 0) {                       // buffer b was last used by pass - 2: wait until it has been drained
+                    mbar_wait(&acc_empty[b], (((uint32_t)(pass >> 1)) & 1u) ^ 1u);
+                    tc_fence_after();
+                }
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(b * NT);
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
@@ -103,13 +116,13 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     const uint32_t off = k * 32;   // 16 bf16 = 32 bytes inside the 128-byte swizzle span
                     const uint64_t dah = make_sw128_kmajor_desc(a_hi + off), dal = make_sw128_kmajor_desc(a_lo + off);
                     const uint64_t dbh = make_sw128_kmajor_desc(b_hi + off), dbl = make_sw128_kmajor_desc(b_lo + off);
-                    umma_bf16(tmem_base, dah, dbh, Cfg::kIdesc, (i > 0 || k > 0) ? 1u : 0u);
-                    umma_bf16(tmem_base, dah, dbl, Cfg::kIdesc, 1u);
-                    umma_bf16(tmem_base, dal, dbh, Cfg::kIdesc, 1u);
+                    umma_bf16(tmem_acc, dah, dbh, Cfg::kIdesc, (j > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16(tmem_acc, dah, dbl, Cfg::kIdesc, 1u);
+                    umma_bf16(tmem_acc, dal, dbh, Cfg::kIdesc, 1u);
                 }
                 umma_commit(&empty_bar[s]);   // frees the smem stage once the MMAs have read it
+                if (j == chunk_kb - 1 || i == nkb - 1) umma_commit(&acc_full[b]);   // this pass is complete
             }
-            umma_commit(accum_bar);           // accumulator complete
         }
     } else {
         const int q = warp & 3;               // TMEM lane quarter this warp may access
@@ -118,43 +131,56 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         float* out = C + row * ldc + col0;
         const bool row_ok = row < M;
         const bool vec_ok = row_ok && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
+        const int n_pass = (nkb + chunk_kb - 1) / chunk_kb;
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int b = pass & 1;
+            const bool add_c = accumulate != 0 || pass > 0;       // later passes fold into what the earlier ones stored
+            mbar_wait(&acc_full[b], ((uint32_t)(pass >> 1)) & 1u);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < NT; c += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);     // warp-collective: every lane executes it
-            if (!row_ok || col0 + c >= Ntot) continue;
-            if (vec_ok && col0 + c + 32 <= Ntot) {
+            for (int c = 0; c < NT; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * NT + c), v);     // warp-collective: every lane executes it
+                if (!row_ok || col0 + c >= Ntot) continue;
+                if (vec_ok && col0 + c + 32 <= Ntot) {
+                    float4 prev[8];
+                    if (add_c) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 r = make_float4(alpha * __uint_as_float(v[j]), alpha * __uint_as_float(v[j + 1]),
-                                           alpha * __uint_as_float(v[j + 2]), alpha * __uint_as_float(v[j + 3]));
-                    if (accumulate) r = add4(r, ld4(out + c + j));
-                    st4(out + c + j, r);
-                }
-            } else {
+                        for (int j = 0; j < 8; ++j) prev[j] = ld4(out + c + 4 * j);
+                    }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (col0 + c + j < Ntot) {
-                        float r = alpha * __uint_as_float(v[j]);
-                        if (accumulate) r += out[c + j];
-                        out[c + j] = r;
+                    for (int j = 0; j < 8; ++j) {
+                        float4 r = make_float4(alpha * __uint_as_float(v[4 * j]), alpha * __uint_as_float(v[4 * j + 1]),
+                                               alpha * __uint_as_float(v[4 * j + 2]), alpha * __uint_as_float(v[4 * j + 3]));
+                        if (add_c) r = add4(r, prev[j]);
+                        st4(out + c + 4 * j, r);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (col0 + c + j < Ntot) {
+                            float r = alpha * __uint_as_float(v[j]);
+                            if (add_c) r += out[c + j];
+                            out[c + j] = r;
+                        }
                     }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[b]);            // 4 epilogue warps -> the MMA warp may overwrite buffer b
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NT) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * NT) : "memory");
     }
 }
 
 template <int NT>
 static int launch_wide(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, float* c,
-                       int64_t ldc, int64_t m, int64_t n, int64_t k, float alpha, int accumulate, cudaStream_t st) {
+                       int64_t ldc, int64_t m, int64_t n, int64_t k, float alpha, int accumulate, int chunk_kb, cudaStream_t st) {
     using Cfg = WideCfg<NT>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -163,7 +189,7 @@ static int launch_wide(const CUtensorMap& ah, const CUtensorMap& al, const CUten
     }
     const int nkb = (int)((k + kBlockK - 1) / kBlockK);
     dim3 grid((unsigned)((m + kBlockM - 1) / kBlockM), (unsigned)((n + NT - 1) / NT));
-    gemm_wide_kernel<NT><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ah, al, bh, bl, c, ldc, (int)m, (int)n, nkb, alpha, accumulate);
+    gemm_wide_kernel<NT><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ah, al, bh, bl, c, ldc, (int)m, (int)n, nkb, chunk_kb, alpha, accumulate);
     MMSSL_LAUNCH_OK();
     return 0;
 }
@@ -171,6 +197,15 @@ static int launch_wide(const CUtensorMap& ah, const CUtensorMap& al, const CUten
 }  // namespace mmssl
 
 using namespace mmssl;
+
+// k-blocks (64 of K each) chained into one TMEM accumulator before the epilogue folds it into C (see the file header).
+static int g_wide_chunk_kb = 16;
+
+extern "C" int mmssl_gemm_wide_set_chunk(int k_blocks) {
+    MMSSL_REQUIRE(k_blocks >= 1, "chunk must be >= 1 k-block");
+    g_wide_chunk_kb = k_blocks;
+    return 0;
+}
 
 extern "C" int mmssl_gemm_bf16x3_wide(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi,
                                       const uint16_t* b_lo, int64_t ldb, int64_t m, int64_t n, int64_t k, float alpha, int accumulate,
@@ -187,6 +222,6 @@ extern "C" int mmssl_gemm_bf16x3_wide(const uint16_t* a_hi, const uint16_t* a_lo
     if (int rc = make_map(&al, a_lo, m, lda, kBlockM)) return rc;
     if (int rc = make_map(&bh, b_hi, n, ldb, nt)) return rc;
     if (int rc = make_map(&bl, b_lo, n, ldb, nt)) return rc;
-    if (nt == 256) return launch_wide<256>(ah, al, bh, bl, c, ldc, m, n, k, alpha, accumulate, st);
-    return launch_wide<128>(ah, al, bh, bl, c, ldc, m, n, k, alpha, accumulate, st);
+    if (nt == 256) return launch_wide<256>(ah, al, bh, bl, c, ldc, m, n, k, alpha, accumulate, g_wide_chunk_kb, st);
+    return launch_wide<128>(ah, al, bh, bl, c, ldc, m, n, k, alpha, accumulate, g_wide_chunk_kb, st);
 }

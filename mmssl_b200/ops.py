@@ -340,6 +340,11 @@ def gemm_bf16x3_wide(a_hi, a_lo, b_hi, b_lo, m, n, k, out, alpha: float = 1.0, a
     return out
 
 
+def gemm_wide_set_chunk(k_blocks: int) -> None:
+    """k-blocks (64 of K) accumulated in TMEM before a pass is folded into C in fp32 (default 16; csrc/gemm_wide.cu)."""
+    _lib.check(_lib_().mmssl_gemm_wide_set_chunk(int(k_blocks)))
+
+
 def gemm_bf16x3_plan(m, n, k):
     lib = _lib_()
     sk = C.c_int(0)

@@ -1,7 +1,7 @@
 // cuemu: functional model of the inline PTX the library uses.  TEST INFRASTRUCTURE ONLY (see include/cuemu.h).
 //
 // Scope = exactly what csrc/tc_common.cuh, proj_tc.cu and gemm_wide.cu issue:
-//   mbarrier.init / arrive.expect_tx / try_wait.parity          phase + pending-arrival + transaction-byte counters
+//   mbarrier.init / arrive / arrive.expect_tx / try_wait.parity         phase + pending-arrival + transaction-byte counters
 //   cp.async.bulk (1-D) ... mbarrier::complete_tx::bytes       contiguous copy global -> shared (spmm_hot.cu)
 //   cp.async.bulk.tensor.2d ... mbarrier::complete_tx::bytes    box copy global -> shared through the tensor map: out-of-bounds
 //                                                               elements read as zero, SWIZZLE_128B (address bits [4:6] ^= [7:9])
@@ -142,6 +142,10 @@ void ptx_op(const char* text, void** outs, const int* out_sizes, int n_out, cons
         MBar& b = bar_at(in[0]);
         b.tx += (int64_t)in[1];
         bar_arrive(b);
+        return;
+    }
+    if (has("mbarrier.arrive.shared::cta.b64 _")) {       // plain arrival (consumer release)
+        bar_arrive(bar_at(in[0]));
         return;
     }
     if (has("mbarrier.try_wait.parity")) {

@@ -61,3 +61,13 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     b = b.detach().double().cpu()
     denom = max(float(b.abs().max()), 1e-30)
     return float((a - b).abs().max()) / denom
+
+
+def elem_err(a: torch.Tensor, b: torch.Tensor, rtol: float = 1e-4, atol_frac: float = 1e-6) -> float:
+    """Per-element form of the 1e-4 contract: max over elements of |a-b| / (rtol*|b| + atol_frac*max|b|); <= 1 passes.
+    (rel_err above is norm-wise: one large entry hides the small ones.  The absolute floor is fp32 noise of the reference's
+    own sums: 1e-6 of the tensor's largest magnitude.)"""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    floor = atol_frac * max(float(b.abs().max()), 1e-30)
+    return float(((a - b).abs() / (rtol * b.abs() + floor)).max()) if b.numel() else 0.0

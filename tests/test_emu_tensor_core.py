@@ -32,6 +32,19 @@ def test_wide_gemm_kernel_through_the_ptx_model(emu, monkeypatch, m, n, k):
     W.test_gemm_wide_vs_fp64(m, n, k)
 
 
+@pytest.mark.parametrize("chunk", [1, 2, 3])
+@pytest.mark.parametrize("m,n,k", [(130, 257, 200), (64, 24, 330)])
+def test_wide_gemm_multi_pass_accumulation(emu, chunk, m, n, k):
+    """The K range cut into several TMEM passes (two accumulator buffers, epilogue folds each pass into C): same result."""
+    from mmssl_b200 import ops
+    from tests import test_gpu_zzz_gemm_wide as W
+    ops.gemm_wide_set_chunk(chunk)
+    try:
+        W.test_gemm_wide_vs_fp64(m, n, k)
+    finally:
+        ops.gemm_wide_set_chunk(16)
+
+
 def test_model_rejects_what_the_hardware_would_not_run(emu):
     """The driver-side checks of the tensor-map encoder the model re-states: strides and base 16-byte aligned."""
     import torch
