@@ -68,6 +68,7 @@ class SparseOperand:
         self._n_items_exact: Optional[int] = None
         self._work = {}
         self._hot = None
+        self._bulk = None
         self.desc = CsrDesc(ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), n_rows, n_cols, nnz, ptr(self.items),
                             self.items_cap, ptr(self.split_table), ptr(self.counters), self.segs_cap)
         if os.environ.get("MMSSL_SPMM_SORT") == "1" and nnz > 0:
@@ -82,6 +83,43 @@ class SparseOperand:
             cnt = torch.zeros(max(self.splits_cap, 1), dtype=torch.int32, device=self.device)
             w = (part, cnt)
             self._work[width] = w
+        return w
+
+    def bulk_plan(self):
+        """Work plan of the bulk-copy SpMM (csrc/spmm_bulk.cu): buckets of 32 non-zeros, rows over 32 non-zeros cut at the
+        bucket boundaries.  Built once per operand on first use; returns (CsrDesc with the bulk items, buckets, n_buckets)."""
+        if self._bulk is None:
+            lib = _lib.load(require_device=True)
+            i32 = dict(dtype=torch.int32, device=self.device)
+            items_cap = lib.mmssl_spmm_bulk_plan_items_cap(self.n_rows, self.nnz)
+            splits_cap = lib.mmssl_spmm_bulk_plan_splits_cap(self.nnz)
+            segs_cap = lib.mmssl_spmm_bulk_plan_segs_cap(self.nnz)
+            n_buckets = lib.mmssl_spmm_bulk_plan_buckets(self.nnz)
+            items = torch.empty(items_cap * 4, **i32)
+            split_table = torch.empty(splits_cap * 4, **i32)
+            counters = torch.empty(splits_cap, **i32)
+            buckets = torch.empty(n_buckets * 8, **i32)
+            totals = torch.empty(3, **i32)
+            pws_bytes = lib.mmssl_spmm_plan_workspace_bytes(self.n_rows)
+            pws = torch.empty(pws_bytes, dtype=torch.uint8, device=self.device)
+            _lib.check(lib.mmssl_spmm_bulk_plan(ptr(self.rowptr), self.n_rows, self.nnz, ptr(items), items_cap, ptr(split_table),
+                                                ptr(counters), splits_cap, ptr(buckets), n_buckets, ptr(totals), ptr(pws), pws_bytes,
+                                                stream()))
+            desc = CsrDesc(ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), self.n_rows, self.n_cols, self.nnz, ptr(items),
+                           items_cap, ptr(split_table), ptr(counters), segs_cap)
+            self._bulk = dict(desc=desc, buckets=buckets, n_buckets=n_buckets, items=items, split_table=split_table, counters=counters,
+                              totals=totals, segs_cap=segs_cap, splits_cap=splits_cap, work={}, keep=pws)
+        return self._bulk
+
+    def bulk_work_area(self, width: int):
+        """(partials, counters) of the bulk plan for launches whose right-hand sides total `width` floats per row."""
+        b = self.bulk_plan()
+        w = b["work"].get(width)
+        if w is None:
+            part = torch.zeros(max(b["segs_cap"] * width, 4), dtype=torch.float32, device=self.device)
+            cnt = torch.zeros(max(b["splits_cap"], 1), dtype=torch.int32, device=self.device)
+            w = (part, cnt)
+            b["work"][width] = w
         return w
 
     def hot_plan(self, max_slots: int = 2048):

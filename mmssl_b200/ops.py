@@ -14,6 +14,7 @@ from .graph import SparseOperand
 
 EPI_NONE, EPI_SOFTMAX, EPI_SOFTMAX_BWD = 0, 1, 2
 SPMM_IMPL_LDG, SPMM_IMPL_TMA = 0, 1     # TMA = shared-memory hot rows staged by cp.async.bulk (large graphs)
+SPMM_IMPL_BULK = 0x1000                 # bulk-copy gather pipeline (csrc/spmm_bulk.cu); low 12 bits = its variant word
 _default_spmm_impl = SPMM_IMPL_LDG
 
 
@@ -76,10 +77,20 @@ def spmm(a: SparseOperand, xs: Sequence[torch.Tensor], ys: Optional[Sequence[tor
                 rhs[r].y_peers[k] = int(pp)
     # split-row work area (partial sums + arrival counters), private to (operand, total width): launches
     # of different widths may run concurrently on two streams, and heavy rows need zeroed slots
+    impl = _default_spmm_impl if impl is None else impl
+    if impl & SPMM_IMPL_BULK and nrhs <= 2 and not (epilogue == EPI_SOFTMAX_BWD and s_mode != 0):
+        b = a.bulk_plan()
+        part, counters = a.bulk_work_area(nrhs * d)
+        desc = type(b["desc"]).from_buffer_copy(b["desc"])
+        desc.counters = counters.data_ptr()
+        _lib.check(lib.mmssl_spmm_bulk_f32(C.byref(desc), ptr(b["buckets"]), b["n_buckets"], d, nrhs, rhs, epilogue, float(alpha),
+                                           s_mode, ptr(part), part.numel(), impl & 0xfff, stream()))
+        return list(ys)
+    if impl & SPMM_IMPL_BULK:
+        impl = 0
     part, counters = a.work_area(nrhs * d)
     desc = type(a.desc).from_buffer_copy(a.desc)
     desc.counters = counters.data_ptr()
-    impl = _default_spmm_impl if impl is None else impl
     if impl == SPMM_IMPL_TMA:
         colidx_hot, hot_ids, n_hot = a.hot_plan()
         _lib.check(lib.mmssl_spmm_hot_f32(C.byref(desc), ptr(colidx_hot), ptr(hot_ids), n_hot, d, nrhs, rhs, epilogue,

@@ -69,17 +69,28 @@ def small(name):
                                                                           impl=impl), inner=20), 2)
         out[f"gcn_bwd_impl{impl}_us"] = round(graph_time(lambda: ops.spmm(g_iu.bwd, [xi], [yu], cs=[cu], alpha=0.33, epilogue=ops.EPI_SOFTMAX_BWD,
                                                                           ysaved=[ysv], impl=impl), inner=20), 2)
-    # work items processed longest first (MMSSL_SPMM_SORT=1, plan-level candidate): same kernels, other item order
-    os.environ["MMSSL_SPMM_SORT"] = "1"
-    gs_ui = BipartiteGraph.from_scipy(ds.ui_norm); gs_iu = BipartiteGraph.from_scipy(ds.iu_norm)
-    del os.environ["MMSSL_SPMM_SORT"]
-    out["ui_sorted_us"] = round(graph_time(lambda: ops.spmm(gs_ui.fwd, [xi], [yu]), inner=20), 2)
-    out["iu_sorted_us"] = round(graph_time(lambda: ops.spmm(gs_iu.fwd, [yu], [yi]), inner=20), 2)
-    out["ui2_sorted_us"] = round(graph_time(lambda: ops.spmm(gs_ui.fwd, [x2[:, :d], x2[:, d:]], [y2[:, :d], y2[:, d:]]), inner=20), 2)
+    # bulk-copy gather pipeline (csrc/spmm_bulk.cu): ring stages x warps per block x buckets per warp
+    B = ops.SPMM_IMPL_BULK
+    for nst in (2, 4):
+        for wpb in (1, 2, 4):
+            for tpw in (1, 2):
+                v = B | nst | (wpb << 4) | (tpw << 8)
+                tag = f"bulk_n{nst}w{wpb}t{tpw}"
+                out[f"ui_{tag}_us"] = round(graph_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu], impl=v), inner=20), 2)
+                out[f"iu_{tag}_us"] = round(graph_time(lambda: ops.spmm(g_iu.fwd, [yu], [yi], impl=v), inner=20), 2)
+                out[f"ui2_{tag}_us"] = round(graph_time(lambda: ops.spmm(g_ui.fwd, [x2[:, :d], x2[:, d:]], [y2[:, :d], y2[:, d:]], impl=v), inner=20), 2)
+    for v, tag in ((B, "bulk_auto"), (B | 2 | (4 << 4), "bulk_n2w4")):
+        out[f"gcn_fwd_{tag}_us"] = round(graph_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu], epilogue=ops.EPI_SOFTMAX, ss=[su], s_mode=1, impl=v), inner=20), 2)
+        out[f"gcn_bwd_{tag}_us"] = round(graph_time(lambda: ops.spmm(g_iu.bwd, [xi], [yu], cs=[cu], alpha=0.33, epilogue=ops.EPI_SOFTMAX_BWD,
+                                                                         ysaved=[ysv], impl=v), inner=20), 2)
+    yb = ops.spmm(g_ui.fwd, [xi], impl=B)[0]; ya = ops.spmm(g_ui.fwd, [xi], impl=0)[0]
+    out["bulk_vs_ldg_max_abs_diff"] = float((ya - yb).abs().max())
     out["axpby_in_graph_us"] = graph_time(lambda: ops.axpby(xi, 1.0, 0.0, yi), inner=40)     # ~launch floor
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)
     out["spmm_ui_cold_us"] = cold_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu]), flush)
     out["spmm_iu_cold_us"] = cold_time(lambda: ops.spmm(g_iu.fwd, [yu], [yi]), flush)
+    out["bulk_ui_cold_us"] = cold_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu], impl=B), flush)
+    out["bulk_iu_cold_us"] = cold_time(lambda: ops.spmm(g_iu.fwd, [yu], [yi], impl=B), flush)
     print(json.dumps(out))
 
 
@@ -105,6 +116,19 @@ def large(U, I, nnz, d, tag):
         gat = 8 * nnz + 4 * (M + 1) + 4 * d * nnz + 4 * d * M
         res[nm] = {"us": round(us, 1), "alg_MB": round(alg / 1e6, 1), "GBs": round(alg / us / 1e3, 1),
                    "frac": round(alg / us / 1e3 / PEAK, 3), "gather_GBs": round(gat / us / 1e3, 1)}
+    B = ops.SPMM_IMPL_BULK
+    if os.environ.get("PROBE_BULK", "1") == "1":
+        for nst in (2, 4):
+            for wpb in (2, 4):
+                for tpw in (1, 4, 16):
+                    v = B | nst | (wpb << 4) | (tpw << 8)
+                    r = {}
+                    for nm, g, x, y in (("ui", g_ui.fwd, xi, yu), ("iu", g_iu.fwd, yu, yi)):
+                        ops.spmm(g, [x], [y], impl=v); torch.cuda.synchronize()
+                        r[nm] = round(cold_time(lambda: ops.spmm(g, [x], [y], impl=v), flush, reps=3), 1)
+                    res[f"bulk_n{nst}w{wpb}t{tpw}_us"] = r
+        ya = ops.spmm(g_ui.fwd, [xi], impl=0)[0]; yb = ops.spmm(g_ui.fwd, [xi], impl=B)[0]
+        res["bulk_vs_ldg_max_abs_diff"] = float((ya - yb).abs().max())
     print(json.dumps(res))
 
 
