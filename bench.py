@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--dp", default="fused", choices=["fused", "nccl"],
                     help="N>1 optimiser step: 'fused' = one multimem kernel (reduce-scatter + sharded AdamW + all-gather over "
                          "NVSwitch multicast, falls back to nccl when multicast is unavailable); 'nccl' = all-reduce + replicated AdamW")
+    ap.add_argument("--extra-configs", default="sports,syn1m",
+                    help="N = 1: also time these configs (hot step, stock-torch comparator, isolated kernels); 'none' to skip")
     ap.add_argument("--graph-comm", action="store_true",
                     help="EXPERIMENTAL (hung in round 1): capture the DP all-reduce + AdamW inside the CUDA graph")
     return ap.parse_args()
@@ -139,6 +141,7 @@ def build_problem(name: str, seed: int, device):
     if device is None:
         return ds, P, feats_cpu, None, None
     Pd = {k: v.to(device).contiguous() for k, v in P.items()}
+    build_problem.last_cpu = (ds, P, feats_cpu)          # the same problem on the host, for the stock-torch comparator
     feats = tuple(FeatureStore(f.to(device), keep_fp32=True) for f in feats_cpu)
     g_ui = BipartiteGraph.from_scipy(ds.ui_norm, device=device)
     g_iu = BipartiteGraph.from_scipy(ds.iu_norm, device=device)
@@ -270,16 +273,47 @@ def roofline_objects(ds, P, feats, graphs, hbm_peak, peak_src, dev):
                    "peak_source": peak_src, "traffic": None,
                    "note": "compulsory bytes are %.1f MB: at HBM peak that is %.1f us, below launch latency -> latency-bound at this scale"
                            % (alg / 1e6, alg / hbm_peak / 1e3)}
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            t = json.load(open(tpath)).get(ds.name, {})
-            for k in out:
-                if k in t:
-                    out[k]["traffic"] = t[k]
-        except Exception:
-            pass
+    # `traffic` (dram__bytes of one launch) needs an ncu capture: it is never copied from a file here.  The captures of the same
+    # kernels are under profiles/ (see profiles/README.md); in-process it stays null.
+    out["library"] = library_kernels(ds, P, feats, graphs, x, y, flush, dev)
     del flush
+    return out
+
+
+def library_kernels(ds, P, feats, graphs, x, y, flush, dev):
+    """The stock-torch kernels of the same two operators on this GPU, isolated, cold L2 ("the Blackwell-capable
+    kernel set to beat"): torch.sparse.mm on the reference's COO tensor (Models.py:69-73: coalesce + COO->CSR + cuSPARSE on every
+    call), the same on a prepared CSR tensor (cuSPARSE SpMM alone), and nn.Linear's fp32 cuBLAS GEMM (Models.py:173)."""
+    import torch.nn.functional as F
+    from mmssl_b200 import ops
+    out = {}
+    coo = ds.ui_norm.tocoo()
+    idx = torch.from_numpy(np.vstack([coo.row, coo.col]).astype(np.int64)).to(dev)
+    val = torch.from_numpy(coo.data.astype(np.float32)).to(dev)
+    a_coo = torch.sparse_coo_tensor(idx, val, coo.shape)             # uncoalesced flag, like the reference's tensors
+    a_csr = a_coo.coalesce().to_sparse_csr()
+    ours = time_kernel(lambda: ops.spmm(graphs[0].fwd, [x], [y]), flush)
+    out["spmm_ui"] = {"ours_ms": round(ours, 5),
+                      "torch_sparse_mm_coo_ms": round(time_kernel(lambda: torch.sparse.mm(a_coo, x), flush, reps=5), 5),
+                      "cusparse_csr_ms": round(time_kernel(lambda: torch.mm(a_csr, x), flush, reps=5), 5)}
+    fs = feats[0]
+    if fs.fp32 is not None:
+        w, b = P["image_trans.weight"], P["image_trans.bias"]
+        I, d = fs.n_items, ds.embed_size
+        w_hi, w_lo = ops.split_bf16(w)
+        floats, sk = ops.gemm_bf16x3_plan(I, d, fs.dim)
+        part = torch.empty(floats, dtype=torch.float32, device=dev)
+        yp = torch.empty(I, d, device=dev)
+
+        def ours_proj():
+            ops.split_bf16(w)
+            ops.gemm_bf16x3(fs.hi, fs.lo, w_hi, w_lo, I, d, fs.dim, sk, part)
+            ops.proj_epilogue(part, sk, I, d, b, None, yp)
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        out["projection"] = {"ours_ms (split W + tcgen05 GEMM + bias epilogue)": round(time_kernel(ours_proj, flush), 5),
+                             "cublas_fp32_linear_ms": round(time_kernel(lambda: F.linear(fs.fp32, w, b), flush, reps=5), 5)}
+        torch.backends.cuda.matmul.allow_tf32 = tf32
     return out
 
 
@@ -320,14 +354,14 @@ def cpu_baseline(name, seed, steps, batch, threads=0):
             "cpu_model": model, "os_cpu_count": os.cpu_count(), "s_per_step": round(med, 4)}
 
 
-def stock_gpu_baseline(name, seed, steps, warmup, batch, device):
+def stock_gpu_baseline(name, seed, steps, warmup, batch, device, problem=None):
     """SURVEY 8d's second comparator: what the unmodified reference's hot path costs on the same B200 through stock PyTorch
     (cuSPARSE / cuBLAS / ATen element-wise kernels, autograd, torch.optim.AdamW, one float(loss) sync per step like
     main.py:431) -- the restatement in oracle/mmssl_oracle.py run on CUDA tensors.  A comparator, not the product and not the
     target; timed with CUDA events around `steps` steps after `warmup`."""
     from oracle import mmssl_oracle as O
     from mmssl_b200.synthetic import TripleSampler
-    ds, P, feats_cpu, _, _ = build_problem(name, seed, None)
+    ds, P, feats_cpu = problem if problem is not None else build_problem(name, seed, None)[:3]
     cfg = O.HotPathConfig(embed_size=ds.embed_size, n_layers=ds.n_layers, batch_size=batch)
     ui, iu = O.to_torch_coo(ds.ui_norm).to(device), O.to_torch_coo(ds.iu_norm).to(device)
     step = O.CpuHotStep({k: v.to(device) for k, v in P.items()}, feats_cpu[0].to(device), feats_cpu[1].to(device),
@@ -382,6 +416,44 @@ def cpu_full_step_baseline(name, seed, steps, batch, d_state, threads=0):
     med = statistics.median(times)
     return {"value": round(batch / med, 1), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{steps} full iterations (oracle/gan_oracle.py:FullStep) of config '{name}' (B={batch}), median", "s_per_step": round(med, 4)}
+
+
+def extra_config(name, a, dev, hbm_peak, peak_src):
+    """SURVEY 8d / VERDICT r1 #5: the other BASELINE configs on this GPU, lighter than the headline run: device-resident hot
+    step (captured graph), the stock-torch hot step on the same GPU, isolated SpMM / projection with their library twins."""
+    from mmssl_b200.hotstep import HotStepConfig
+    from mmssl_b200.synthetic import CONFIGS, TripleSampler
+    U, I, nnz, d, K, dv, dt = CONFIGS[name]
+    t0 = time.perf_counter()
+    ds, P, feats, graphs, _ = build_problem(name, a.seed, dev)
+    cpu_problem = build_problem.last_cpu
+    cfg = HotStepConfig(embed_size=d, n_layers=K, batch_size=BATCH, proj_impl=a.proj)
+    trainer = HotStepTrainer(P, feats, graphs, cfg, BATCH, world=1)
+    smp = TripleSampler(ds.train, seed=a.seed)
+    steps, warm = (200, 10) if nnz < 2_000_000 else (30, 5)
+    dev_batches = torch.from_numpy(np.stack([np.stack(smp.sample(BATCH)) for _ in range(16)])).to(dev)
+    for w in range(warm):
+        trainer.step_device(dev_batches[w % 16])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+        trainer.step_device(dev_batches[s % 16])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    roofs = roofline_objects(ds, P, feats, graphs, hbm_peak, peak_src, dev)
+    out = {"workload": f"{name}: {U}x{I}, {nnz} edges, d={d}, {K}-layer GCN, V{dv}/T{dt}, B={BATCH}", "ms_per_step": round(ms, 4),
+           "value": round(BATCH / ms * 1e3, 1), "unit": UNIT, "steps": steps, "roofline_spmm": roofs["spmm"],
+           "roofline_projection": roofs["projection"], "library_kernels": roofs["library"]}
+    del trainer
+    try:
+        sg = stock_gpu_baseline(name, a.seed, 20 if nnz < 2_000_000 else 5, 3, BATCH, str(dev), problem=cpu_problem)
+        out["stock_gpu"] = {"ms_per_step": sg["ms_per_step"], "value": sg["value"], "kind": sg["kind"], "speedup_ours": round(sg["ms_per_step"] / ms, 2)}
+    except Exception as e:                      # the comparator must never take the bench line down (e.g. cuSPARSE out of memory)
+        out["stock_gpu"] = {"unavailable": str(e)[:200]}
+    out["build_s"] = round(time.perf_counter() - t0, 1)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -513,7 +585,14 @@ def main():
                 "e2e": {"value": round(total_triples / (ms_e2e * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": 3 * BATCH * 8,
                         "d2h_bytes_per_step": 5 * 4, "ms_per_step": round(ms_e2e / a.steps, 4), "last_loss": round(last_loss, 6)},
                 "roofline": roof, "roofline_spmm": roofs["spmm"], "roofline_projection": roofs["projection"],
-                "launches_per_step": launches_per_step}
+                "library_kernels": roofs["library"], "launches_per_step": launches_per_step}
+        if world == 1:      # the reference's own ops through stock torch on THIS GPU (comparator, not the product)
+            try:
+                sg = stock_gpu_baseline(a.config, a.seed, 30, 5, BATCH, str(dev), problem=build_problem.last_cpu)
+                line["stock_gpu"] = {"ms_per_step": sg["ms_per_step"], "value": sg["value"], "kind": sg["kind"], "sample": sg["sample"],
+                                     "speedup_ours": round(sg["ms_per_step"] / (ms_total / a.steps), 2)}
+            except Exception as e:
+                line["stock_gpu"] = {"unavailable": str(e)[:200]}
         if world == 1:      # batches drawn on the device (no host sampler, no H2D)
             from mmssl_b200.sampler import DeviceTripleSampler
             P2 = {k: v.clone() for k, v in P.items()}
@@ -530,6 +609,16 @@ def main():
             ms = g0.elapsed_time(g1)
             line["device_sampler_e2e"] = {"value": round(BATCH * a.steps / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms / a.steps, 4),
                                           "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 20}
+        if world == 1 and a.extra_configs != "none":
+            del trainer
+            line["configs"] = {}
+            for name in a.extra_configs.split(","):
+                if name and name != a.config:
+                    torch.cuda.empty_cache()
+                    try:
+                        line["configs"][name] = extra_config(name, a, dev, hbm_peak, peak_src)
+                    except Exception as e:
+                        line["configs"][name] = {"failed": repr(e)[:300]}
         if not a.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(a.config, a.seed, a.cpu_steps, BATCH, a.cpu_threads)
         print(json.dumps(line))

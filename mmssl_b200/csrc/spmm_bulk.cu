@@ -22,6 +22,16 @@
 //
 // Shared memory per warp: ring of NST stages x 16 slots x (nrhs * d * 4) bytes + 2 x 8 rows per staged epilogue operand.
 // No tensor cores: the contraction is a sparse gather.
+//
+// Two copy engines, same pipeline (template parameter TMA):
+//   TMA    one cp.async.bulk per neighbour row, issued by the lane that owns the position.  MEASURED (B200, round 2,
+//          profiles/r02_probe_bulk_tma.txt): the TMA unit retires about one bulk copy per 44 cycles per SM whatever its size --
+//          6.5 G copies/s chip-wide -- so 256-512 B rows reach 6-12 B/cycle/SM, a quarter of what L2 can deliver:
+//          3.06 ms at 1M x 200k (LDG kernel 1.04 ms), 20 us at Baby (LDG 9.4 us).  Kept for 1-2 KB slots and as the measured
+//          record of why the per-neighbour TMA ring north_star sketches is not the product path at d <= 128.
+//   LDGSTS the whole warp issues 16-byte cp.async.cg copies (512 B per instruction: one d=128 row, two d=64 rows), completion
+//          through the same per-stage mbarriers (cp.async.mbarrier.arrive.noinc, 32 arrivals).  Still no register holds a row in
+//          flight, and the issue rate is the LSU's (8 cycles per 512 B), above what L2 delivers.
 #include "spmm_common.cuh"
 
 namespace mmssl {
@@ -41,7 +51,13 @@ struct BulkParams {
 };
 
 __device__ __forceinline__ uint32_t bsm(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bk_mbar_init(uint64_t* bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bsm(bar))); }
+__device__ __forceinline__ void bk_mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bsm(bar)), "r"(count)); }
+__device__ __forceinline__ void bk_cp16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bsm(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void bk_cp_arrive(uint64_t* bar) {      // this lane's earlier cp.async copies arrive on `bar` when they land
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bsm(bar)) : "memory");
+}
 __device__ __forceinline__ void bk_expect(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bsm(bar)), "r"(bytes) : "memory");
 }
@@ -101,9 +117,22 @@ template <> __device__ __forceinline__ void mcstv<4>(float* dst, const float (&v
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
 }
 
-// V floats per lane (d = 32 V), R right-hand sides, NST ring stages of kSL slots.
-template <int V, int R, int NST>
-__global__ void __launch_bounds__(128) spmm_bulk_kernel(const BulkParams bp) {
+// Warp-cooperative copy of one D-float row (16 bytes per lane per instruction): rows of 64 floats take a half warp, so two rows
+// travel per instruction (`half` selects which one a lane serves); 128 floats one instruction; 256 floats two.
+template <int D>
+__device__ __forceinline__ void bk_row_ldgsts(float* dst, const float* src, int lane, bool on) {
+    if (D == 64) {
+        if (on) bk_cp16(dst + (lane & 15) * 4, src + (lane & 15) * 4);
+    } else {
+#pragma unroll
+        for (int o = 0; o < D; o += 128)
+            if (on) bk_cp16(dst + o + lane * 4, src + o + lane * 4);
+    }
+}
+
+// V floats per lane (d = 32 V), R right-hand sides, NST ring stages of kSL slots, TMA: copy engine (see the file header).
+template <int V, int R, int NST, bool TMA>
+__global__ void __launch_bounds__(256) spmm_bulk_kernel(const BulkParams bp) {
     using L = Lay<V>;
     constexpr int CW = L::CW, NCH = L::NCH;
     constexpr int D = 32 * V;
@@ -118,7 +147,7 @@ __global__ void __launch_bounds__(128) spmm_bulk_kernel(const BulkParams bp) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(stg + (size_t)bp.n_ops * 2 * kEG * RD);   // [NST] ring + [2] operand groups
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < NST + 2; ++s) bk_mbar_init(&bars[s]);
+        for (int s = 0; s < NST + 2; ++s) bk_mbar_init(&bars[s], TMA ? 1u : 32u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -168,16 +197,28 @@ __global__ void __launch_bounds__(128) spmm_bulk_kernel(const BulkParams bp) {
             const int lo = max(q_lo, ch * kSL), hi = min(q_hi, ch * kSL + kSL);
             if (hi <= lo) return;
             uint64_t* bar = &bars[ch % NST];
-            const int q = (ch * kSL & 31) + (lane & (kSL - 1));    // this lane's position in the chunk, if it is one of its 16 lanes
-            const bool mine = ((lane >> 4) == ((ch * kSL >> 4) & 1));
-            if (lane == ((ch * kSL) & 31)) bk_expect(bar, (uint32_t)(hi - lo) * ROWB);
-            __syncwarp();
-            const int qq = (ch * kSL & ~31) + q;               // q of this lane within [0, 64)
-            if (mine && qq >= lo && qq < hi) {
-                const int col = (ch * kSL < kBk) ? my_c0 : my_c1;
-                float* dst = ring + (size_t)((ch % NST) * kSL + (qq & (kSL - 1))) * RD;
+            const int creg = (ch * kSL < kBk) ? my_c0 : my_c1;       // a chunk never straddles the two position registers
+            float* stage = ring + (size_t)((ch % NST) * kSL) * RD;
+            if (TMA) {
+                const bool mine = ((lane >> 4) == (ch & 1));           // chunk ch lives in lanes 16 (ch & 1) .. +15
+                if (lane == ((ch * kSL) & 31)) bk_expect(bar, (uint32_t)(hi - lo) * ROWB);
+                __syncwarp();
+                const int qq = ch * kSL + (lane & (kSL - 1));          // this lane's position within [0, 64)
+                if (mine && qq >= lo && qq < hi) {
+                    float* dst = stage + (size_t)(qq & (kSL - 1)) * RD;
 #pragma unroll
-                for (int r = 0; r < R; ++r) bk_copy(dst + r * D, p.x[r] + (int64_t)col * p.ldx[r], D * 4, bar);
+                    for (int r = 0; r < R; ++r) bk_copy(dst + r * D, p.x[r] + (int64_t)creg * p.ldx[r], D * 4, bar);
+                }
+            } else {
+                constexpr int RPI = (D == 64) ? 2 : 1;                 // rows per instruction
+                for (int qq = lo; qq < hi; qq += RPI) {
+                    const int myq = qq + (RPI == 2 ? (lane >> 4) : 0);
+                    const int col = __shfl_sync(0xffffffffu, creg, myq & 31);
+                    float* dst = stage + (size_t)(myq & (kSL - 1)) * RD;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) bk_row_ldgsts<D>(dst + r * D, p.x[r] + (int64_t)col * p.ldx[r], lane, myq < hi);
+                }
+                bk_cp_arrive(bar);
             }
         };
         __syncwarp();                                         // every lane is done with the ring contents of the previous task
@@ -186,30 +227,37 @@ __global__ void __launch_bounds__(128) spmm_bulk_kernel(const BulkParams bp) {
         // ---- issue: row-indexed epilogue operands of rows [row0, row0 + n_rows), groups of kEG rows, two buffers
         int groups_issued = 0, groups_waited = 0;
         const int n_groups = bp.n_ops > 0 ? (n_rows + kEG - 1) / kEG : 0;
+        auto operand_src = [&](int o, int r, int64_t row) -> const float* {   // o: 0 = A (alpha * C) when present, else B
+            if (o == 0 && has_a) return p.c[r] + row * p.ldc[r];
+            return (p.epilogue == MMSSL_EPI_SOFTMAX_BWD) ? p.ys[r] + row * p.ldys[r]
+                   : (p.s_mode == 2)                     ? p.sb[r] + row * p.ldsb[r]
+                                                         : p.s[r] + row * p.lds[r];
+        };
         auto issue_group = [&](int g) {
             uint64_t* bar = &bars[NST + (g & 1)];
             const int r_lo = g * kEG, r_n = min(kEG, n_rows - r_lo);
-            if (lane == 0) bk_expect(bar, (uint32_t)(r_n * bp.n_ops) * ROWB);
-            __syncwarp();
-            if (lane < r_n) {
-                const int64_t row = row0 + r_lo + lane;
-                int o = 0;
-                if (has_a) {
-                    float* dst = stg + (size_t)((o * 2 + (g & 1)) * kEG + lane) * RD;
+            if (TMA) {
+                if (lane == 0) bk_expect(bar, (uint32_t)(r_n * bp.n_ops) * ROWB);
+                __syncwarp();
+                if (lane < r_n) {
+                    const int64_t row = row0 + r_lo + lane;
+                    for (int o = 0; o < bp.n_ops; ++o) {
+                        float* dst = stg + (size_t)((o * 2 + (g & 1)) * kEG + lane) * RD;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) bk_copy(dst + r * D, p.c[r] + row * p.ldc[r], D * 4, bar);
-                    ++o;
-                }
-                if (has_b) {
-                    float* dst = stg + (size_t)((o * 2 + (g & 1)) * kEG + lane) * RD;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const float* src = (p.epilogue == MMSSL_EPI_SOFTMAX_BWD) ? p.ys[r] + row * p.ldys[r]
-                                           : (p.s_mode == 2)                     ? p.sb[r] + row * p.ldsb[r]
-                                                                                 : p.s[r] + row * p.lds[r];
-                        bk_copy(dst + r * D, src, D * 4, bar);
+                        for (int r = 0; r < R; ++r) bk_copy(dst + r * D, operand_src(o, r, row), D * 4, bar);
                     }
                 }
+            } else {
+                constexpr int RPI = (D == 64) ? 2 : 1;
+                for (int o = 0; o < bp.n_ops; ++o)
+                    for (int i = 0; i < r_n; i += RPI) {
+                        const int mi = i + (RPI == 2 ? (lane >> 4) : 0);
+                        const int64_t row = row0 + r_lo + min(mi, r_n - 1);
+                        float* dst = stg + (size_t)((o * 2 + (g & 1)) * kEG + mi) * RD;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) bk_row_ldgsts<D>(dst + r * D, operand_src(o, r, row), lane, mi < r_n);
+                    }
+                bk_cp_arrive(bar);
             }
         };
         for (; groups_issued < n_groups && groups_issued < 2; ++groups_issued) issue_group(groups_issued);
@@ -433,7 +481,7 @@ __global__ void __launch_bounds__(128) spmm_bulk_kernel(const BulkParams bp) {
     }
 }
 
-template <int V, int R, int NST>
+template <int V, int R, int NST, bool TMA>
 static int launch_bulk(const BulkParams& bp_in, cudaStream_t stream, int wpb, int tpw) {
     constexpr int D = 32 * V, RD = R * D;
     BulkParams bp = bp_in;
@@ -445,14 +493,14 @@ static int launch_bulk(const BulkParams& bp_in, cudaStream_t stream, int wpb, in
     if (smem > 227 * 1024) return fail("mmssl_spmm_bulk_f32", "one warp's ring does not fit shared memory (use 2 ring stages)");
     static int attr_smem = 0;
     if (smem > attr_smem) {
-        MMSSL_CUDA(cudaFuncSetAttribute(spmm_bulk_kernel<V, R, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MMSSL_CUDA(cudaFuncSetAttribute(spmm_bulk_kernel<V, R, NST, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
     const int64_t warps = (bp.n_buckets + tpw - 1) / tpw;
     const int64_t blocks = (warps + wpb - 1) / wpb;
     if (blocks == 0) return 0;
     if (blocks > 0x7fffffffll) return fail("mmssl_spmm_bulk_f32", "grid too large");
-    MMSSL_CUDA_LAUNCH((spmm_bulk_kernel<V, R, NST>), dim3((unsigned)blocks), dim3(32 * wpb), (size_t)smem, stream, bp);
+    MMSSL_CUDA_LAUNCH((spmm_bulk_kernel<V, R, NST, TMA>), dim3((unsigned)blocks), dim3(32 * wpb), (size_t)smem, stream, bp);
     MMSSL_LAUNCH_OK();
     return 0;
 }
@@ -462,7 +510,7 @@ static int launch_bulk(const BulkParams& bp_in, cudaStream_t stream, int wpb, in
 using namespace mmssl;
 
 // variant: bits 0-3 ring stages (0 = automatic: 4 when a slot is <= 512 B, else 2), bits 4-7 warps per block (0 = 4),
-// bits 8-15 buckets per warp (0 = automatic: 1 under 2M edges, 4 above).
+// bits 8-15 buckets per warp (0 = automatic: 1 under 2M edges, 4 above), bit 16: TMA bulk copies instead of LDGSTS.
 extern "C" int mmssl_spmm_bulk_f32(const mmssl_csr_t* a, const int32_t* buckets8, int64_t n_buckets, int d, int nrhs,
                                    const mmssl_spmm_rhs_t* rhs, int epilogue, float alpha, int s_mode, float* partials,
                                    int64_t partials_floats, int variant, void* stream_) {
@@ -483,14 +531,16 @@ extern "C" int mmssl_spmm_bulk_f32(const mmssl_csr_t* a, const int32_t* buckets8
     bp.n_ops = (bp.p.has_c ? 1 : 0) + (has_b ? 1 : 0);
     const int slot_bytes = nrhs * d * 4;
     int nst = variant & 15, wpb = (variant >> 4) & 15, tpw = (variant >> 8) & 255;
+    const bool tma = (variant >> 16) & 1;
     if (nst == 0) nst = slot_bytes <= 512 ? 4 : 2;
     if (wpb == 0) wpb = 4;
     if (tpw == 0) tpw = a->nnz >= (1ll << 21) ? 4 : 1;
     MMSSL_REQUIRE(nst == 2 || nst == 4, "ring stages must be 2 or 4");
-    MMSSL_REQUIRE(wpb >= 1 && wpb <= 4, "warps per block must be 1..4");
-#define MMSSL_BULK_CASE(V)                                                                      \
-    if (nrhs == 1) return nst == 4 ? launch_bulk<V, 1, 4>(bp, stream, wpb, tpw) : launch_bulk<V, 1, 2>(bp, stream, wpb, tpw); \
-    return nst == 4 ? launch_bulk<V, 2, 4>(bp, stream, wpb, tpw) : launch_bulk<V, 2, 2>(bp, stream, wpb, tpw);
+    MMSSL_REQUIRE(wpb >= 1 && wpb <= 8, "warps per block must be 1..8");
+#define MMSSL_BULK_CASE2(V, RR, NN) return tma ? launch_bulk<V, RR, NN, true>(bp, stream, wpb, tpw) : launch_bulk<V, RR, NN, false>(bp, stream, wpb, tpw);
+#define MMSSL_BULK_CASE(V)                                                       \
+    if (nrhs == 1) { if (nst == 4) { MMSSL_BULK_CASE2(V, 1, 4) } MMSSL_BULK_CASE2(V, 1, 2) } \
+    if (nst == 4) { MMSSL_BULK_CASE2(V, 2, 4) } MMSSL_BULK_CASE2(V, 2, 2)
     if (d == 64) { MMSSL_BULK_CASE(2) }
     if (d == 128) { MMSSL_BULK_CASE(4) }
     MMSSL_BULK_CASE(8)

@@ -14,7 +14,8 @@ from .graph import SparseOperand
 
 EPI_NONE, EPI_SOFTMAX, EPI_SOFTMAX_BWD = 0, 1, 2
 SPMM_IMPL_LDG, SPMM_IMPL_TMA = 0, 1     # TMA = shared-memory hot rows staged by cp.async.bulk (large graphs)
-SPMM_IMPL_BULK = 0x1000                 # bulk-copy gather pipeline (csrc/spmm_bulk.cu); low 12 bits = its variant word
+SPMM_IMPL_BULK = 0x100000               # staged gather pipeline (csrc/spmm_bulk.cu); low 20 bits = its variant word
+SPMM_BULK_TMA = 0x10000                 # ... with one TMA bulk copy per neighbour row instead of warp-wide 16-byte cp.async
 _default_spmm_impl = SPMM_IMPL_LDG
 
 
@@ -84,7 +85,7 @@ def spmm(a: SparseOperand, xs: Sequence[torch.Tensor], ys: Optional[Sequence[tor
         desc = type(b["desc"]).from_buffer_copy(b["desc"])
         desc.counters = counters.data_ptr()
         _lib.check(lib.mmssl_spmm_bulk_f32(C.byref(desc), ptr(b["buckets"]), b["n_buckets"], d, nrhs, rhs, epilogue, float(alpha),
-                                           s_mode, ptr(part), part.numel(), impl & 0xfff, stream()))
+                                           s_mode, ptr(part), part.numel(), impl & 0xfffff, stream()))
         return list(ys)
     if impl & SPMM_IMPL_BULK:
         impl = 0

@@ -156,6 +156,15 @@ void ptx_op(const char* text, void** outs, const int* out_sizes, int n_out, cons
         if (!done) yield_blocked();
         return;
     }
+    if (has("cp.async.cg.shared.global")) {                 // Ampere-style 16-byte asynchronous copy: executed at once in this model
+        if ((in[0] % 16) || (in[1] % 16)) fail("cp.async.cg 16: addresses must be multiples of 16 bytes");
+        memcpy(smem_at(in[0], 16), reinterpret_cast<const void*>((uintptr_t)in[1]), 16);
+        return;
+    }
+    if (has("cp.async.mbarrier.arrive.noinc")) {            // the lane's earlier copies have landed (model: they always have)
+        bar_arrive(bar_at(in[0]));
+        return;
+    }
     if (has("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes")) {      // 1-D bulk copy: dst, src, bytes, barrier
         const uint64_t dst = in[0], bytes = in[2];
         if ((dst % 16) || (in[1] % 16) || (bytes % 16)) fail("cp.async.bulk: addresses and size must be multiples of 16 bytes");

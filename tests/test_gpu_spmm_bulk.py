@@ -13,9 +13,9 @@ from tests.golden_util import rel_err  # noqa: E402
 from tests.test_gpu_ops import _graph  # noqa: E402
 
 
-def _bulk(nst=0, wpb=0, tpw=0):
+def _bulk(nst=0, wpb=0, tpw=0, tma=0):
     from mmssl_b200 import ops
-    return ops.SPMM_IMPL_BULK | nst | (wpb << 4) | (tpw << 8)
+    return ops.SPMM_IMPL_BULK | nst | (wpb << 4) | (tpw << 8) | (ops.SPMM_BULK_TMA if tma else 0)
 
 
 def test_bulk_plan_covers_every_nonzero_once():
@@ -53,7 +53,7 @@ def test_bulk_plan_covers_every_nonzero_once():
 
 @pytest.mark.parametrize("d", [64, 128, 256])
 @pytest.mark.parametrize("nrhs", [1, 2])
-@pytest.mark.parametrize("variant", [(0, 0, 0), (2, 2, 3), (4, 4, 1)])
+@pytest.mark.parametrize("variant", [(0, 0, 0, 0), (2, 2, 3, 0), (4, 4, 1, 1), (2, 8, 1, 0), (0, 0, 0, 1)])
 def test_spmm_bulk_plain(d, nrhs, variant):
     from mmssl_b200 import ops
     g, ref = _graph(700, 500, 30000, seed=d + nrhs, heavy_rows=2)
@@ -77,9 +77,10 @@ def test_spmm_bulk_plain(d, nrhs, variant):
 
 @pytest.mark.parametrize("d", [64, 128, 256])
 @pytest.mark.parametrize("nst", [2, 4])
-def test_spmm_bulk_epilogues(d, nst):
+@pytest.mark.parametrize("tma", [0, 1])
+def test_spmm_bulk_epilogues(d, nst, tma):
     from mmssl_b200 import ops
-    impl = _bulk(nst)
+    impl = _bulk(nst, tma=tma)
     g, ref = _graph(300, 260, 9000, seed=7 + d, heavy_rows=1)
     torch.manual_seed(1)
     x = torch.randn(260, d, device="cuda")
@@ -127,9 +128,9 @@ def test_spmm_bulk_many_short_and_empty_rows():
     cc = torch.randn(n_rows, 64, device="cuda")
     s = torch.randn(n_rows, 64, device="cuda")
     s0 = s.clone()
-    for nst in (2, 4):
+    for nst, tma in ((2, 0), (4, 0), (2, 1), (4, 1)):
         s.copy_(s0)
-        y = ops.spmm(g.fwd, [x], cs=[cc], alpha=-1.5, ss=[s], s_mode=1, impl=_bulk(nst))[0]
+        y = ops.spmm(g.fwd, [x], cs=[cc], alpha=-1.5, ss=[s], s_mode=1, impl=_bulk(nst, tma=tma))[0]
         want = torch.from_numpy(ref @ x.double().cpu().numpy()) - 1.5 * cc.double().cpu()
         assert rel_err(y, want) < 2e-6
         assert rel_err(s, s0.double().cpu() + want) < 2e-6
@@ -163,7 +164,7 @@ def test_spmm_bulk_heavy_rows_and_zipf_columns():
         x = torch.randn(n_cols, d, device="cuda")
         cs = torch.randn(n_rows, d, device="cuda")
         for _ in range(2):
-            y = ops.spmm(g.fwd, [x], cs=[cs], alpha=0.5, epilogue=ops.EPI_SOFTMAX, impl=_bulk())[0]
+            y = ops.spmm(g.fwd, [x], cs=[cs], alpha=0.5, epilogue=ops.EPI_SOFTMAX, impl=_bulk(tma=_))[0]
             want = torch.softmax(torch.from_numpy(ref @ x.double().cpu().numpy()) + 0.5 * cs.double().cpu(), -1)
             assert rel_err(y, want) < 1e-5
         yt = ops.spmm(g.bwd, [torch.ones(n_rows, d, device="cuda")], impl=_bulk())[0]

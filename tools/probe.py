@@ -71,11 +71,11 @@ def small(name):
                                                                           ysaved=[ysv], impl=impl), inner=20), 2)
     # bulk-copy gather pipeline (csrc/spmm_bulk.cu): ring stages x warps per block x buckets per warp
     B = ops.SPMM_IMPL_BULK
-    for nst in (2, 4):
-        for wpb in (1, 2, 4):
-            for tpw in (1, 2):
-                v = B | nst | (wpb << 4) | (tpw << 8)
-                tag = f"bulk_n{nst}w{wpb}t{tpw}"
+    for nst, wpb, tpw, tma in ((2, 2, 1, 0), (2, 4, 1, 0), (2, 8, 1, 0), (4, 2, 1, 0), (4, 4, 1, 0), (4, 8, 1, 0), (2, 4, 2, 0), (4, 4, 2, 0), (2, 4, 1, 1)):
+        for _ in (0,):
+            for _ in (0,):
+                v = B | nst | (wpb << 4) | (tpw << 8) | (ops.SPMM_BULK_TMA if tma else 0)
+                tag = f"bulk_n{nst}w{wpb}t{tpw}" + ("_tma" if tma else "")
                 out[f"ui_{tag}_us"] = round(graph_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu], impl=v), inner=20), 2)
                 out[f"iu_{tag}_us"] = round(graph_time(lambda: ops.spmm(g_iu.fwd, [yu], [yi], impl=v), inner=20), 2)
                 out[f"ui2_{tag}_us"] = round(graph_time(lambda: ops.spmm(g_ui.fwd, [x2[:, :d], x2[:, d:]], [y2[:, :d], y2[:, d:]], impl=v), inner=20), 2)
@@ -119,8 +119,8 @@ def large(U, I, nnz, d, tag):
     B = ops.SPMM_IMPL_BULK
     if os.environ.get("PROBE_BULK", "1") == "1":
         for nst in (2, 4):
-            for wpb in (2, 4):
-                for tpw in (1, 4, 16):
+            for wpb in (2, 4, 8):
+                for tpw in (1, 4):
                     v = B | nst | (wpb << 4) | (tpw << 8)
                     r = {}
                     for nm, g, x, y in (("ui", g_ui.fwd, xi, yu), ("iu", g_iu.fwd, yu, yi)):
