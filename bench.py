@@ -61,6 +61,10 @@ def parse():
                          "NVSwitch multicast, falls back to nccl when multicast is unavailable); 'nccl' = all-reduce + replicated AdamW")
     ap.add_argument("--extra-configs", default="sports,syn1m",
                     help="N = 1: also time these configs (hot step, stock-torch comparator, isolated kernels); 'none' to skip")
+    ap.add_argument("--row-shard", default="sports,syn1m",
+                    help="N > 1: also run the row-sharded whole hot step (north_star's scheme) on these configs; 'none' to skip")
+    ap.add_argument("--row-exchange", default="multicast", choices=["multicast", "nccl"])
+    ap.add_argument("--row-graph", type=int, default=1, help="capture the row-sharded step in a CUDA graph (multicast exchange only)")
     ap.add_argument("--graph-comm", action="store_true",
                     help="EXPERIMENTAL (hung in round 1): capture the DP all-reduce + AdamW inside the CUDA graph")
     return ap.parse_args()
@@ -456,6 +460,205 @@ def extra_config(name, a, dev, hbm_peak, peak_src):
     return out
 
 
+def _fixed_masks(I, d, drop, seed, dev):
+    g = torch.Generator().manual_seed(seed)
+    return tuple(((torch.rand(I, d, generator=g) >= drop) / (1 - drop)).float().to(dev) for _ in range(2))
+
+
+def dp_parity_vs_1gpu(trainer, P0, feats, graphs, cfg, my_batch, rank, world, dev):
+    """VERDICT r1 #1b: the N-GPU data-parallel step against 1-GPU HotSteps ON RANK 0, same fixed global batch (the N replica
+    batches) and the same injected dropout masks: mean loss and every live gradient after the cross-GPU reduction.
+    The N-GPU side runs the product's own path eagerly (its kernels, then the reduction primitive the optimiser uses:
+    multimem.ld_reduce over the symmetric gradient bucket, or the NCCL all-reduce of --dp nccl)."""
+    import torch.distributed as dist
+    from mmssl_b200 import _lib
+    from mmssl_b200._lib import ptr, stream
+    from mmssl_b200.engine import LIVE
+    from mmssl_b200.hotstep import HotStep
+    hs = trainer.hs
+    I, d = graphs[0].shape[1], cfg.embed_size
+    # restore the initial parameters on every replica so that both sides start from the same point
+    for k in LIVE:
+        hs.P[k].copy_(P0[k])
+    hs.masks = _fixed_masks(I, d, cfg.drop_rate, 1000 + rank, dev)
+    hs.idx.copy_(my_batch)
+    saved = hs.optimizer_step
+    hs.optimizer_step = False
+    out5 = hs.run().clone()
+    hs.optimizer_step = saved
+    hs.masks = None
+    torch.cuda.synchronize()
+    dist.barrier()
+    keys = list(LIVE)
+    if trainer.dp_opt is not None:          # the switch-reduced sum of the replicas' gradient buckets
+        opt = trainer.dp_opt
+        red = torch.empty_like(opt.gflat)
+        lib = _lib.load(require_device=True)
+        opt.hg.barrier()
+        import ctypes as C
+        _lib.check(lib.mmssl_mc_allreduce_sum(C.c_void_p(opt.g_mc), ptr(red), red.numel(), stream()))
+        opt.hg.barrier()
+        red.mul_(1.0 / world)
+        got = {k: red[(opt.grads[k].data_ptr() - opt.gflat.data_ptr()) // 4:][:opt.grads[k].numel()].view_as(opt.grads[k]) for k in keys}
+        how = "multimem.ld_reduce over the symmetric gradient bucket (the fused optimiser's reduction)"
+    else:
+        flat = trainer.bucket.flat.clone()
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.mul_(1.0 / world)
+        got = {k: flat[(trainer.bucket.views[k].data_ptr() - trainer.bucket.flat.data_ptr()) // 4:][:trainer.bucket.views[k].numel()].view_as(trainer.bucket.views[k]) for k in keys}
+        how = "NCCL all-reduce of the flat gradient bucket"
+    loss = out5[:1].clone()
+    dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+    all_batches = [torch.empty_like(my_batch) for _ in range(world)]
+    dist.all_gather(all_batches, my_batch.contiguous())
+    res = None
+    if rank == 0:
+        ref = HotStep({k: P0[k].clone() for k in P0}, feats, graphs, cfg, batch=my_batch.shape[1], optimizer_step=False)
+        acc = {k: torch.zeros_like(P0[k]) for k in keys}
+        ref_loss = 0.0
+        for r in range(world):
+            ref.masks = _fixed_masks(I, d, cfg.drop_rate, 1000 + r, dev)
+            ref.idx.copy_(all_batches[r])
+            ref_loss += float(ref.run()[0])
+            for k in keys:
+                acc[k] += ref.grads[k]
+        errs = {}
+        for k in keys:
+            want = acc[k] / world
+            errs[k] = float((got[k] - want).abs().max() / want.abs().max().clamp_min(1e-30))
+        lerr = abs(float(loss) / world - ref_loss / world) / max(abs(ref_loss / world), 1e-30)
+        res = {"loss_rel_err": lerr, "max_grad_rel_err": max(errs.values()), "worst_grad": max(errs, key=errs.get),
+               "n_gpu_reduction": how, "reference": f"{world} single-GPU HotStep evaluations on rank 0 (one per replica batch), averaged",
+               "tolerance": 1e-4, "ok": bool(lerr < 1e-4 and max(errs.values()) < 1e-4)}
+    for k in LIVE:                              # leave the replicas in sync for whatever runs next
+        hs.P[k].copy_(P0[k])
+    torch.cuda.synchronize()
+    dist.barrier()
+    return res
+
+
+def row_shard_report(name, a, rank, world, dev):
+    """north_star / SURVEY 8e / VERDICT r1 #2: the WHOLE hot step with embedding tables, features, graphs and optimiser state
+    row-sharded over the N GPUs (mmssl_b200/rowshard_step.py), same global batch B as the 1-GPU step: ms/step, speed-up over
+    the 1-GPU fused step on the same problem (timed on rank 0 of this run), exchanges and bytes per step, achieved NVLink
+    rate, and parity of one step (losses + all gradients, same injected dropout masks) against the 1-GPU step."""
+    import torch.distributed as dist
+    from mmssl_b200.engine import LIVE, P_EI, P_EU
+    from mmssl_b200.hotstep import HotStep, HotStepConfig
+    from mmssl_b200.rowshard_step import RowShardedHotStep, shard_problem
+    from mmssl_b200.synthetic import CONFIGS, TripleSampler
+    U, I, nnz, d, K, dv, dt = CONFIGS[name]
+    t0 = time.perf_counter()
+    ds, P_cpu, feats_cpu, _, _ = build_problem(name, a.seed, None)            # the same seeded problem on every rank (host)
+    cfg = HotStepConfig(embed_size=d, n_layers=K, batch_size=BATCH, proj_impl=a.proj)
+    Pl, fl, gl, pu, pi = shard_problem(P_cpu, feats_cpu, ds.ui_norm, ds.iu_norm, rank, world, dev)
+    mode = a.row_exchange
+    try:
+        sh = RowShardedHotStep(Pl, fl, gl, cfg, BATCH, pu, pi, rank, exchange=mode)
+    except (RuntimeError, ImportError, AttributeError) as e:
+        if rank == 0:
+            print(f"[bench] multicast exchange unavailable ({e}); NCCL all-gathers", file=sys.stderr)
+        mode = "nccl"
+        sh = RowShardedHotStep(Pl, fl, gl, cfg, BATCH, pu, pi, rank, exchange=mode)
+    smp = TripleSampler(ds.train, seed=a.seed)
+    batches = [tuple(torch.from_numpy(x).to(dev) for x in smp.sample(BATCH)) for _ in range(8)]
+    g = torch.Generator().manual_seed(7)
+    full_masks = tuple(((torch.rand(I, d, generator=g) >= cfg.drop_rate) / (1 - cfg.drop_rate)).float() for _ in range(2))
+    out = {"workload": f"{name}: {U}x{I}, {nnz} edges, d={d}, {K}-layer GCN, V{dv}/T{dt}, global B={BATCH}", "n_gpus": world,
+           "exchange": mode}
+
+    # ---- parity of one step (no optimiser) against the 1-GPU fused step on rank 0
+    sh.masks = tuple(pi.local(m, rank).to(dev) for m in full_masks)
+    sh.optimizer_step = False
+    sh.set_indices(*batches[0])
+    got5 = sh.run().clone()
+    tab = {}
+    for k, part in ((P_EU, pu), (P_EI, pi)):
+        full = [torch.empty_like(sh.grads[k]) for _ in range(world)]
+        dist.all_gather(full, sh.grads[k].contiguous())
+        tab[k] = torch.cat(full)[:part.n]
+    hs = None
+    ms_1gpu = None
+    if rank == 0:
+        _, Pd, feats, graphs, _ = build_problem(name, a.seed, dev)
+        hs = HotStep(Pd, feats, graphs, cfg, batch=BATCH, optimizer_step=False)
+        hs.masks = tuple(m.to(dev) for m in full_masks)
+        hs.set_indices(*batches[0])
+        want5 = hs.run().clone()
+        errs = {"losses": float(((got5 - want5).abs() / want5.abs().clamp_min(1e-12)).max())}
+        for k in LIVE:
+            gk = tab[k] if k in tab else sh.grads[k]
+            errs[k] = float((gk - hs.grads[k]).abs().max() / hs.grads[k].abs().max().clamp_min(1e-30))
+        worst = max(errs, key=errs.get)
+        out["parity_vs_1gpu"] = {"max_rel_err": errs[worst], "worst": worst, "loss_rel_err": errs["losses"], "tolerance": 1e-4,
+                                 "ok": bool(errs[worst] < 1e-4)}
+        # the 1-GPU step of the same problem, same batch size: the denominator of the speed-up
+        hs.masks = None
+        hs.optimizer_step = True
+        hs.capture(warmup=2)
+        n1 = 100 if nnz < 2_000_000 else 20
+        for s in range(3):
+            hs.set_indices(*batches[s % 8]); hs.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(n1):
+            hs.set_indices(*batches[s % 8]); hs.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_1gpu = e0.elapsed_time(e1) / n1
+        del hs, Pd, feats, graphs
+        torch.cuda.empty_cache()
+    dist.barrier()
+
+    # ---- timing (optimiser on, torch-RNG dropout): CUDA graph when every exchange is a kernel + signal-pad barrier
+    sh.masks = None
+    sh.optimizer_step = True
+    captured = False
+    if mode == "multicast" and a.row_graph:
+        try:
+            sh.set_indices(*batches[0])
+            sh.capture()
+            captured = True
+        except RuntimeError as e:
+            if rank == 0:
+                print(f"[bench] row-sharded step not captured ({e}); eager launches", file=sys.stderr)
+    step = sh.replay if captured else sh.run
+    steps = 100 if nnz < 2_000_000 else 20
+    for s in range(3):
+        sh.set_indices(*batches[s % 8]); step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sh.n_gathers = sh.gathered_bytes = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+        sh.set_indices(*batches[s % 8]); step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    if not captured:
+        gath, gbytes = sh.n_gathers // steps, sh.gathered_bytes / steps
+    else:                                       # counted once at capture time: run one eager step to count
+        sh.n_gathers = sh.gathered_bytes = 0
+        sh.run()
+        torch.cuda.synchronize()
+        gath, gbytes = sh.n_gathers, float(sh.gathered_bytes)
+    out.update({"ms_per_step": round(ms, 4), "value": round(BATCH / ms * 1e3, 1), "unit": UNIT, "steps": steps, "cuda_graph": captured,
+                "exchanges_per_step": int(gath), "bytes_received_per_rank_per_step": int(gbytes),
+                "nvlink_GBps_per_rank_if_serial": round(gbytes / (ms * 1e-3) / 1e9, 1),
+                "build_s": round(time.perf_counter() - t0, 1)})
+    if rank == 0 and ms_1gpu is not None:
+        out["ms_per_step_1gpu"] = round(ms_1gpu, 4)
+        out["speedup_vs_1gpu"] = round(ms_1gpu / ms, 3)
+    del sh
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 def main():
     global BATCH
@@ -509,6 +712,7 @@ def main():
 
     ds, P, feats, graphs, _ = build_problem(a.config, a.seed, dev)
     cfg = HotStepConfig(embed_size=d, n_layers=K, batch_size=BATCH, proj_impl=a.proj)
+    P0 = {k: v.clone() for k, v in P.items()} if world > 1 else None
     trainer = HotStepTrainer(P, feats, graphs, cfg, BATCH, world=world, graph_comm=a.graph_comm, dp=a.dp)
     if world > 1 and trainer.dp_mode == "fused":
         config["parallelism"] = (f"dp{world} (replicated graph; optimiser step = one multimem kernel after the graph replay: "
@@ -561,10 +765,23 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
     clk = clocks.stop() if rank == 0 else None
 
+    parity = row_shard = None
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_e2e = float(t[0]), float(t[1])
+        parity = dp_parity_vs_1gpu(trainer, P0, feats, graphs, cfg, dev_batches[0], rank, world, dev)
+        if a.row_shard != "none":
+            del trainer
+            torch.cuda.empty_cache()
+            row_shard = {}
+            for name in a.row_shard.split(","):
+                if name:
+                    try:
+                        row_shard[name] = row_shard_report(name, a, rank, world, dev)
+                    except Exception as e:          # keep the headline line alive; the failure is reported in place
+                        import traceback
+                        row_shard[name] = {"failed": repr(e)[:300], "where": traceback.format_exc()[-400:]}
 
     if rank == 0:
         hbm_peak, peak_src = peaks()
@@ -586,6 +803,10 @@ def main():
                         "d2h_bytes_per_step": 5 * 4, "ms_per_step": round(ms_e2e / a.steps, 4), "last_loss": round(last_loss, 6)},
                 "roofline": roof, "roofline_spmm": roofs["spmm"], "roofline_projection": roofs["projection"],
                 "library_kernels": roofs["library"], "launches_per_step": launches_per_step}
+        if parity is not None:
+            line["parity_vs_1gpu"] = parity
+        if row_shard is not None:
+            line["row_shard"] = row_shard
         if world == 1:      # the reference's own ops through stock torch on THIS GPU (comparator, not the product)
             try:
                 sg = stock_gpu_baseline(a.config, a.seed, 30, 5, BATCH, str(dev), problem=build_problem.last_cpu)
@@ -622,6 +843,9 @@ def main():
         if not a.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(a.config, a.seed, a.cpu_steps, BATCH, a.cpu_threads)
         print(json.dumps(line))
+        if parity is not None and not parity["ok"]:
+            print("[bench] N-GPU vs 1-GPU parity FAILED: " + json.dumps(parity), file=sys.stderr)
+            sys.exit(3)
     if world > 1:
         dist.destroy_process_group()
 

@@ -63,6 +63,55 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// ---- L2 / L1 residency hints (large graphs: what streams must not evict what is gathered) ----
+// 64-bit L2 cache-policy words (createpolicy encodings, the ones the TMA kernels already use on hardware)
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ int ldg_i32_stream(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(kL2EvictFirst));
+    return v;
+}
+__device__ __forceinline__ float ldg_f32_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(kL2EvictFirst));
+    return v;
+}
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(kL2EvictFirst));
+    return v;
+}
+__device__ __forceinline__ float4 ld4_stream(const float* p) {      // coherent (the buffer may be written by this kernel elsewhere)
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(kL2EvictFirst) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st4_stream(float* p, const float4& v) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(kL2EvictFirst) : "memory");
+}
+// gathered row: keep it in L2 (policy word chosen by the caller: evict-last when the gathered table fits L2, else normal)
+__device__ __forceinline__ float4 ldg4_l2(const float* p, uint64_t policy) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
+// gathered row with an L1 priority: hot columns (the head of the degree distribution) are pinned (evict_last), the cold ones
+// do not allocate -- two predicated loads into the same registers, no branch
+__device__ __forceinline__ float4 ldg4_l1_hot_cold(const float* p, int hot, uint64_t policy) {
+    float4 v;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q ld.global.nc.L1::evict_last.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %6;\n\t"
+        "@!q ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %6;\n\t}"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "r"(hot), "l"(policy));
+    return v;
+}
 __device__ __forceinline__ void fma4(float4& a, float s, const float4& x) {
     a.x = fmaf(s, x.x, a.x); a.y = fmaf(s, x.y, a.y); a.z = fmaf(s, x.z, a.z); a.w = fmaf(s, x.w, a.w);
 }

@@ -33,7 +33,12 @@ namespace mmssl {
 // PRE (impl bit 6, candidate awaiting measurement): the row-indexed epilogue operands -- alpha*C[row], the saved softmax
 // output, the running-sum base -- are requested as soon as the work item is known, so that they travel while the
 // index -> gather chain runs instead of adding one more dependent round trip after it.  Only for R*C <= 2 (register cost).
-template <int G, int C, int R, int UMUL, int MINB, bool PRE = false>
+// HINT (large graphs, impl bits 7 / 8): 1 = the streams (col, val, outputs, row-indexed operands) are marked L2 evict-first and
+// bypass L1 so that they do not push the gathered table out of L2 (measured round 1: DRAM traffic 2.18x the compulsory bytes
+// at 1M x 200k because a 102 MB table shares the L2 with 670 MB of streams); 2 = additionally the column indices carry a
+// "hot" flag in the sign bit (the head of the column-degree distribution, graph.py:hot_flag_plan) and hot rows are loaded
+// with L1::evict_last, cold ones with L1::no_allocate, so that the ~200 KB of L1 serve the popular rows.
+template <int G, int C, int R, int UMUL, int MINB, bool PRE = false, int HINT = 0>
 __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p) {
     pdl_wait();
     constexpr int RC = R * C;
@@ -72,13 +77,19 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
 
     int c_nxt = 0;
     float v_nxt = 0.f;
-    if (begin + lane < end) { c_nxt = __ldg(p.colidx + begin + lane); v_nxt = __ldg(p.vals + begin + lane); }
+    if (begin + lane < end) {
+        c_nxt = HINT ? ldg_i32_stream(p.colidx + begin + lane) : __ldg(p.colidx + begin + lane);
+        v_nxt = HINT ? ldg_f32_stream(p.vals + begin + lane) : __ldg(p.vals + begin + lane);
+    }
     for (int base = begin; base < end; base += G) {
         const int c_l = c_nxt;
         const float v_l = v_nxt;
         const int e2 = base + G + lane;
         c_nxt = 0; v_nxt = 0.f;
-        if (e2 < end) { c_nxt = __ldg(p.colidx + e2); v_nxt = __ldg(p.vals + e2); }   // prefetch the next chunk
+        if (e2 < end) {                                                                // prefetch the next chunk
+            c_nxt = HINT ? ldg_i32_stream(p.colidx + e2) : __ldg(p.colidx + e2);
+            v_nxt = HINT ? ldg_f32_stream(p.vals + e2) : __ldg(p.vals + e2);
+        }
         const int cnt = min(G, end - base);
         for (int j = 0; j < cnt; j += UNR) {
             int cc[UNR];
@@ -94,9 +105,14 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
                 const bool on = (j + k) < cnt;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const float* xr = p.x[r] + (int64_t)cc[k] * p.ldx[r] + lane * 4;
+                    const int col = (HINT == 2) ? (cc[k] & 0x7fffffff) : cc[k];
+                    const float* xr = p.x[r] + (int64_t)col * p.ldx[r] + lane * 4;
 #pragma unroll
-                    for (int c = 0; c < C; ++c) xv[k][r][c] = on ? ldg4(xr + c * (4 * G)) : f4zero();
+                    for (int c = 0; c < C; ++c) {
+                        if (HINT == 0) xv[k][r][c] = on ? ldg4(xr + c * (4 * G)) : f4zero();
+                        else if (HINT == 1) xv[k][r][c] = on ? ldg4_l2(xr + c * (4 * G), p.x_policy) : f4zero();
+                        else xv[k][r][c] = on ? ldg4_l1_hot_cold(xr + c * (4 * G), cc[k] < 0, p.x_policy) : f4zero();
+                    }
                 }
             }
 #pragma unroll
@@ -185,7 +201,8 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
         if (p.has_c && p.c[r] != nullptr) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const float4 cv = PRE_ON ? pre_c[r][c] : ld4(p.c[r] + (int64_t)row * p.ldc[r] + col0 + c * (4 * G));   // may alias Y
+                const float* cp_ = p.c[r] + (int64_t)row * p.ldc[r] + col0 + c * (4 * G);
+                const float4 cv = PRE_ON ? pre_c[r][c] : HINT ? ld4_stream(cp_) : ld4(cp_);   // may alias Y (read before the row is written, by the same lanes)
                 fma4(acc[r][c], p.alpha, cv);
             }
         }
@@ -227,7 +244,7 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
                 asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.y[r] + off), "f"(acc[r][c].x),
                              "f"(acc[r][c].y), "f"(acc[r][c].z), "f"(acc[r][c].w) : "memory");
             } else {
-                st4(p.y[r] + off, acc[r][c]);
+                if (HINT) st4_stream(p.y[r] + off, acc[r][c]); else st4(p.y[r] + off, acc[r][c]);
                 if (p.y_mode[r] == 2)         // peer-mapped tables over NVLink
                     for (int q = 0; q < p.n_peers[r]; ++q) st4(p.y_peers[r][q] + off, acc[r][c]);
             }
@@ -244,13 +261,13 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
     }
 }
 
-template <int G, int C, int R, int UMUL, int MINB, bool PRE = false>
+template <int G, int C, int R, int UMUL, int MINB, bool PRE = false, int HINT = 0>
 static int launch_spmm_v(const SpmmParams& p, cudaStream_t stream, int T) {
     const int64_t groups_per_block = T / G;
     const int64_t blocks = (p.n_items + groups_per_block - 1) / groups_per_block;
     if (blocks == 0) return 0;
     if (blocks > 0x7fffffffll) return fail("mmssl_spmm_csr_f32", "grid too large");
-    MMSSL_CUDA_LAUNCH((spmm_csr_kernel<G, C, R, UMUL, MINB, PRE>), dim3((unsigned)blocks), dim3(T), 0, stream, p);
+    MMSSL_CUDA_LAUNCH((spmm_csr_kernel<G, C, R, UMUL, MINB, PRE, HINT>), dim3((unsigned)blocks), dim3(T), 0, stream, p);
     MMSSL_LAUNCH_OK();
     return 0;
 }
@@ -259,6 +276,8 @@ static int launch_spmm_v(const SpmmParams& p, cudaStream_t stream, int T) {
 // bit 6 (64): early epilogue-operand prefetch (only with the two policy defaults, i.e. bit 3 clear)
 template <int G, int C, int R>
 static int launch_spmm(const SpmmParams& p, cudaStream_t stream, int T, int impl) {
+    if (impl & 256) return launch_spmm_v<G, C, R, 1, 6, false, 2>(p, stream, T);       // L2 streams + L1 hot / cold rows
+    if (impl & 128) return launch_spmm_v<G, C, R, 1, 6, false, 1>(p, stream, T);       // L2 streams
     if ((impl & 64) && R * C <= 2 && !(impl & 8))
         return (impl & 16) ? launch_spmm_v<G, C, R, 1, 6, true>(p, stream, T) : launch_spmm_v<G, C, R, 1, 1, true>(p, stream, T);
     switch ((impl >> 3) & 3) {
@@ -322,6 +341,8 @@ extern "C" int mmssl_spmm_csr_f32(const mmssl_csr_t* a, int d, int nrhs, const m
     cudaStream_t stream = (cudaStream_t)stream_;
     SpmmParams p;
     if (int rc = fill_spmm_params(p, a, d, nrhs, rhs, epilogue, alpha, s_mode, partials, partials_floats)) return rc;
+    // gathered rows: evict-last in L2 when every right-hand side table fits it with room to spare, else no preference
+    p.x_policy = ((int64_t)a->n_cols * d * nrhs * 4 <= (96ll << 20)) ? kL2EvictLast : 0x1000000000000000ull;
     // impl 0 = automatic policy from measurements (tools/probe.py): small graphs are launch/latency
     // bound and prefer 128-thread blocks; large graphs are bound by the number of resident row walks
     // and prefer the register-capped variant (6 blocks/SM).

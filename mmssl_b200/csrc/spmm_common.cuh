@@ -29,6 +29,7 @@ struct SpmmParams {
     int y_mode[kMaxRhs];            // 0 local, 1 multicast (multimem.st), 2 local + peers
     int n_peers[kMaxRhs];
     float* y_peers[kMaxRhs][8];
+    unsigned long long x_policy;    // L2 policy word of the gathered rows (hinted variants of the LDG kernel)
 };
 
 // G lanes per group, C float4 chunks per lane per rhs (d = 4*G*C), R right-hand sides.

@@ -122,6 +122,24 @@ class SparseOperand:
             b["work"][width] = w
         return w
 
+    def hot_flag_colidx(self, n_hot: int):
+        """Copy of the column index array with the sign bit set on the `n_hot` highest-degree columns (LDG kernel, impl bit 8:
+        hot rows are pinned in L1, cold rows bypass it).  One-time graph preparation, device side."""
+        key = ("hotflag", n_hot)
+        if key not in self._work:
+            col = self.colidx[:self.nnz].long()
+            deg = torch.bincount(col, minlength=self.n_cols)
+            h = int(min(n_hot, self.n_cols))
+            flag = torch.zeros(self.n_cols, dtype=torch.bool, device=self.device)
+            if h > 0 and self.nnz > 0:
+                flag[torch.topk(deg, h).indices] = True
+            buf = self.colidx.clone()
+            if self.nnz > 0:
+                buf[:self.nnz] = torch.where(flag[col], self.colidx[:self.nnz] | -2147483648, self.colidx[:self.nnz])
+                self.hot_flag_fraction = float(flag[col].float().mean())
+            self._work[key] = buf
+        return self._work[key]
+
     def hot_plan(self, max_slots: int = 2048):
         """(colidx_hot, hot_ids, n_hot) for the TMA-staged SpMM: the `max_slots` highest-degree columns
         get shared-memory slots (ordered by decreasing degree) and are encoded as -(slot+1) in a copy of

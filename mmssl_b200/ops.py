@@ -92,6 +92,8 @@ def spmm(a: SparseOperand, xs: Sequence[torch.Tensor], ys: Optional[Sequence[tor
     part, counters = a.work_area(nrhs * d)
     desc = type(a.desc).from_buffer_copy(a.desc)
     desc.counters = counters.data_ptr()
+    if impl & 256:       # L1 hot / cold rows: the column indices carry the hot flag (about 192 KB of rows per SM)
+        desc.colidx = a.hot_flag_colidx(max(1, (192 * 1024) // (nrhs * d * 4))).data_ptr()
     if impl == SPMM_IMPL_TMA:
         colidx_hot, hot_ids, n_hot = a.hot_plan()
         _lib.check(lib.mmssl_spmm_hot_f32(C.byref(desc), ptr(colidx_hot), ptr(hot_ids), n_hot, d, nrhs, rhs, epilogue,

@@ -27,7 +27,6 @@ def test_projection_gemm_kernel_through_the_ptx_model(emu, m, n, k):
 
 @pytest.mark.parametrize("m,n,k", [(64, 24, 96), (300, 200, 96), (130, 257, 70), (5, 1, 8), (260, 600, 200)])
 def test_wide_gemm_kernel_through_the_ptx_model(emu, monkeypatch, m, n, k):
-    monkeypatch.setenv("MMSSL_RUN_UNVALIDATED", "1")
     from tests import test_gpu_zzz_gemm_wide as W
     W.test_gemm_wide_vs_fp64(m, n, k)
 

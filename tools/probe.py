@@ -116,8 +116,19 @@ def large(U, I, nnz, d, tag):
         gat = 8 * nnz + 4 * (M + 1) + 4 * d * nnz + 4 * d * M
         res[nm] = {"us": round(us, 1), "alg_MB": round(alg / 1e6, 1), "GBs": round(alg / us / 1e3, 1),
                    "frac": round(alg / us / 1e3 / PEAK, 3), "gather_GBs": round(gat / us / 1e3, 1)}
+    # LDG kernel with residency hints: 16 = register-capped policy variant (the default here), +128 L2 streams, +256 L1 hot / cold rows
+    for v in (16, 16 | 128, 16 | 128 | 256):
+        r = {}
+        for nm, g, x, y in (("ui", g_ui.fwd, xi, yu), ("iu", g_iu.fwd, yu, yi), ("uiT", g_ui.bwd, yu, yi), ("iuT", g_iu.bwd, yi, yu)):
+            ops.spmm(g, [x], [y], impl=v); torch.cuda.synchronize()
+            r[nm] = round(cold_time(lambda: ops.spmm(g, [x], [y], impl=v), flush, reps=5), 1)
+        res[f"ldg_impl{v}_us"] = r
+    ya = ops.spmm(g_ui.fwd, [xi], impl=16)[0]
+    for v in (16 | 128, 16 | 128 | 256):
+        res[f"impl{v}_max_abs_diff"] = float((ya - ops.spmm(g_ui.fwd, [xi], impl=v)[0]).abs().max())
+    res["hot_flag_fraction_ui"] = getattr(g_ui.fwd, "hot_flag_fraction", None)
     B = ops.SPMM_IMPL_BULK
-    if os.environ.get("PROBE_BULK", "1") == "1":
+    if os.environ.get("PROBE_BULK", "0") == "1":
         for nst in (2, 4):
             for wpb in (2, 4, 8):
                 for tpw in (1, 4):
