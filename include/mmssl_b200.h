@@ -100,21 +100,23 @@ int mmssl_spmm_hot_f32(const mmssl_csr_t* a /*host*/, const int32_t* colidx_hot,
                        int nrhs, const mmssl_spmm_rhs_t* rhs /*host*/, int epilogue, float alpha, int s_mode,
                        float* partials, int64_t partials_floats, void* stream);
 
-/* Bulk-copy gather pipeline (spmm_bulk.cu; north_star: "stages neighbour embeddings through TMA into shared memory with
- * warp-shuffle partial sums"): one warp per bucket of 32 non-zeros, neighbour rows and the row-indexed epilogue operands
- * travel as cp.async.bulk copies completed on mbarriers, no register holds a row in flight.  Same contract / epilogues as
- * mmssl_spmm_csr_f32 for nrhs <= 2 (not: softmax-backward together with a running sum).  `a` carries the BULK plan
- * (items / split_table / counters from mmssl_spmm_bulk_plan; split_table[.][2] = first bucket of the row), `partials`
- * >= a->segs_cap * nrhs * d zeroed floats.  variant: bits 0-3 ring stages (0 auto, 2 or 4), bits 4-7 warps per block
- * (0 = 4), bits 8-15 buckets per warp (0 auto). */
-int64_t mmssl_spmm_bulk_plan_items_cap(int64_t n_rows, int64_t nnz);
+/* Staged-gather pipeline (spmm_bulk.cu; north_star: "stages neighbour embeddings through TMA into shared memory with
+ * warp-shuffle partial sums"): one warp per BUCKET of <= 32 consecutive non-zeros / <= 8 whole rows (or one 32-chunk of a longer
+ * row); every neighbour row of the bucket and the row-indexed epilogue operands travel as asynchronous copies into the warp's
+ * shared-memory slots (warp-wide 16-byte cp.async, or one cp.async.bulk per row completed on an mbarrier: variant bit 16), no
+ * register holds a row in flight.  Same contract / epilogues as mmssl_spmm_csr_f32 for nrhs <= 2 (not: softmax-backward
+ * together with a running sum).  `a` carries the operand's CSR arrays and the BUCKET plan's split_table / counters / segs_cap
+ * (`items` is not used), `partials` >= a->segs_cap * nrhs * d zeroed floats.
+ * variant: bits 4-7 warps per block (0 = 4), bits 8-15 buckets per warp (0 auto), bit 16 TMA copy engine. */
 int64_t mmssl_spmm_bulk_plan_splits_cap(int64_t nnz);
 int64_t mmssl_spmm_bulk_plan_segs_cap(int64_t nnz);
-int64_t mmssl_spmm_bulk_plan_buckets(int64_t nnz);
-/* workspace: mmssl_spmm_plan_workspace_bytes(n_rows) */
-int mmssl_spmm_bulk_plan(const int32_t* rowptr, int64_t n_rows, int64_t nnz, int32_t* items4, int64_t items_cap,
-                         int32_t* split_table4, int32_t* counters, int64_t splits_cap, int32_t* buckets8 /*[n_buckets][8]*/,
-                         int64_t n_buckets, int32_t* totals3, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t mmssl_spmm_bulk_plan_buckets_cap(int64_t n_rows, int64_t nnz);
+int64_t mmssl_spmm_bulk_plan_workspace_bytes(int64_t n_rows);
+/* buckets8[k] = {first row, #rows, first position, #positions, split-row index or -1, chunk index, 0, 0}; entries beyond
+ * totals3[0] stay zero (0 rows: skipped by the kernel).  totals3 = {#buckets, #split rows, #partial slots}. */
+int mmssl_spmm_bulk_plan(const int32_t* rowptr, int64_t n_rows, int64_t nnz, int32_t* split_table4, int32_t* counters,
+                         int64_t splits_cap, int32_t* buckets8 /*[buckets_cap][8]*/, int64_t buckets_cap, int32_t* totals3,
+                         void* workspace, int64_t workspace_bytes, void* stream);
 int mmssl_spmm_bulk_f32(const mmssl_csr_t* a /*host*/, const int32_t* buckets8, int64_t n_buckets, int d, int nrhs,
                         const mmssl_spmm_rhs_t* rhs /*host*/, int epilogue, float alpha, int s_mode, float* partials,
                         int64_t partials_floats, int variant, void* stream);

@@ -48,11 +48,11 @@ _SIGS = {
                                      c_i64, c_i32, c_vp]),
     "mmssl_spmm_hot_f32": (C.c_int, [C.POINTER(CsrDesc), c_vp, c_vp, c_i32, c_i32, c_i32, C.POINTER(SpmmRhs), c_i32, c_f32, c_i32,
                                      c_vp, c_i64, c_vp]),
-    "mmssl_spmm_bulk_plan_items_cap": (c_i64, [c_i64, c_i64]),
     "mmssl_spmm_bulk_plan_splits_cap": (c_i64, [c_i64]),
     "mmssl_spmm_bulk_plan_segs_cap": (c_i64, [c_i64]),
-    "mmssl_spmm_bulk_plan_buckets": (c_i64, [c_i64]),
-    "mmssl_spmm_bulk_plan": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "mmssl_spmm_bulk_plan_buckets_cap": (c_i64, [c_i64, c_i64]),
+    "mmssl_spmm_bulk_plan_workspace_bytes": (c_i64, [c_i64]),
+    "mmssl_spmm_bulk_plan": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "mmssl_spmm_bulk_f32": (C.c_int, [C.POINTER(CsrDesc), c_vp, c_i64, c_i32, c_i32, C.POINTER(SpmmRhs), c_i32, c_f32, c_i32, c_vp,
                                       c_i64, c_i32, c_vp]),
     "mmssl_sgemm": (C.c_int, [c_i32, c_i32, c_i64, c_i64, c_i64, c_f32, c_vp, c_i64, c_vp, c_i64, c_f32, c_vp, c_i64,

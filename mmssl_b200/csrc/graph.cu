@@ -137,77 +137,92 @@ __global__ void plan_fill_kernel(const int32_t* __restrict__ rowptr, int64_t n_r
 }
 
 
-// ---------------------------------------------------------------- work plan of the bulk-copy SpMM (spmm_bulk.cu)
-// The non-zeros are cut into buckets of 32 consecutive positions (one per lane of the warp that owns the bucket).
-//   item = {row, begin, end, split}: a row of <= 32 non-zeros is one item, owned by the bucket its first position falls
-//   in (it may run up to 31 positions into the next bucket; an empty row belongs to the bucket of its row pointer);
-//   a longer row is cut AT the bucket boundaries: one item per bucket it touches, split = index into the split-row table
-//   {first partial slot, #segments, first bucket, heavy}: heavy (> 32 segments) rows accumulate with vector reductions.
-//   bucket = {first item, #items, first row, #rows}, {first position, end of the last item, 0, 0}; rows of a bucket are
-//   consecutive, so the row-indexed epilogue operands of a bucket are a contiguous block.
+// ---------------------------------------------------------------- work plan of the staged-gather SpMM (spmm_bulk.cu)
+// BUCKETS of at most 32 consecutive non-zeros (one per lane of the warp that owns the bucket) and at most 8 rows, that never cut
+// a row of <= 32 non-zeros:
+//   * rows of <= 32 non-zeros ("short", empty rows included) are grouped by the 32-aligned window their first position falls
+//     in; the rows of one window form a run (a longer row in between ends it).  A run spans at most 63 positions and only its
+//     last row can end more than 32 positions after the run's first one: that row gets a bucket of its own, the others share
+//     buckets of up to 8 rows;
+//   * a row of more than 32 non-zeros is cut into chunks of 32 from its start, one bucket each; split-row table entry
+//     {first partial slot, #chunks, 0, heavy}: heavy (> 32 chunks) rows accumulate with vector reductions.
+//   bucket = {first row, #rows, first position, #positions}, {split-row index or -1, chunk index, 0, 0}, in row order.
 constexpr int kBulkBucket = 32;
+constexpr int kBulkRows = 8;
 constexpr int kBulkHeavySegs = 32;
 
-__global__ void bulk_count_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, int32_t* __restrict__ n_items,
-                                  int32_t* __restrict__ is_split, int32_t* __restrict__ n_segs) {
+__global__ void bulk_runflag_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, int32_t* __restrict__ run_flag) {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     const int b = rowptr[r], e = rowptr[r + 1];
-    const bool split = (e - b) > kBulkBucket;
-    const int segs = split ? ((e - 1) / kBulkBucket - b / kBulkBucket + 1) : 0;
-    n_items[r] = split ? segs : 1;
-    is_split[r] = split ? 1 : 0;
-    n_segs[r] = segs;
+    bool start = (r == 0) || (e - b) > kBulkBucket;
+    if (!start) {
+        const int pb = rowptr[r - 1];
+        start = (b - pb) > kBulkBucket || (b / kBulkBucket) != (pb / kBulkBucket);
+    }
+    run_flag[r] = start ? 1 : 0;
 }
 
-__global__ void bulk_fill_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, const int32_t* __restrict__ item_off,
-                                 const int32_t* __restrict__ split_off, const int32_t* __restrict__ seg_off,
-                                 const int32_t* __restrict__ is_split, int4* __restrict__ items, int4* __restrict__ split_table,
-                                 int32_t* __restrict__ totals) {
+__global__ void bulk_runfirst_kernel(const int32_t* __restrict__ run_flag, const int32_t* __restrict__ run_excl, int64_t n_rows,
+                                     int32_t* __restrict__ run_first) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r < n_rows && run_flag[r]) run_first[run_excl[r]] = (int32_t)r;
+}
+
+__global__ void bulk_count_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, const int32_t* __restrict__ run_flag,
+                                  const int32_t* __restrict__ run_excl, const int32_t* __restrict__ run_first,
+                                  int32_t* __restrict__ n_bk, int32_t* __restrict__ is_split, int32_t* __restrict__ n_segs) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int b = rowptr[r], e = rowptr[r + 1];
+    if (e - b > kBulkBucket) {
+        const int chunks = (e - b + kBulkBucket - 1) / kBulkBucket;
+        n_bk[r] = chunks; is_split[r] = 1; n_segs[r] = chunks;
+        return;
+    }
+    const int rs = run_first[run_excl[r] + run_flag[r] - 1];      // first row of this row's run
+    const bool straddler = (e - rowptr[rs]) > kBulkBucket;
+    n_bk[r] = (r == rs || straddler || ((r - rs) % kBulkRows) == 0) ? 1 : 0;
+    is_split[r] = 0; n_segs[r] = 0;
+}
+
+__global__ void bulk_fill_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, const int32_t* __restrict__ n_bk,
+                                 const int32_t* __restrict__ bk_off, const int32_t* __restrict__ split_off,
+                                 const int32_t* __restrict__ seg_off, const int32_t* __restrict__ is_split, int4* __restrict__ buckets,
+                                 int4* __restrict__ split_table, int32_t* __restrict__ totals) {
     const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= n_rows) return;
     const int b = rowptr[r], e = rowptr[r + 1];
-    int segs = 0;
-    if (!is_split[r]) {
-        if (lane == 0) items[item_off[r]] = make_int4((int)r, b, e, -1);
-    } else {
-        const int fb = b / kBulkBucket;
-        segs = (e - 1) / kBulkBucket - fb + 1;
+    const int nb = n_bk[r], o = bk_off[r];
+    if (is_split[r]) {
         const int s = split_off[r];
-        for (int k = lane; k < segs; k += 32)
-            items[item_off[r] + k] = make_int4((int)r, max(b, (fb + k) * kBulkBucket), min(e, (fb + k + 1) * kBulkBucket), s);
-        if (lane == 0) split_table[s] = make_int4(seg_off[r], segs, fb, segs > kBulkHeavySegs ? 1 : 0);
+        for (int k = lane; k < nb; k += 32) {
+            buckets[2 * (o + k)] = make_int4((int)r, 1, b + k * kBulkBucket, min(kBulkBucket, e - (b + k * kBulkBucket)));
+            buckets[2 * (o + k) + 1] = make_int4(s, k, 0, 0);
+        }
+        if (lane == 0) split_table[s] = make_int4(seg_off[r], nb, 0, nb > kBulkHeavySegs ? 1 : 0);
+    } else if (nb == 1 && lane == 0) {
+        buckets[2 * o] = make_int4((int)r, 0, b, 0);          // #rows / #positions: bulk_extent_kernel (needs the next bucket's first row)
+        buckets[2 * o + 1] = make_int4(-1, 0, 0, 0);
     }
     if (r == n_rows - 1 && lane == 0) {
-        totals[0] = item_off[r] + (is_split[r] ? segs : 1);
-        totals[1] = split_off[r] + is_split[r];
-        totals[2] = seg_off[r] + segs;
+        totals[0] = o + nb;                                    // buckets
+        totals[1] = split_off[r] + is_split[r];                // split rows
+        totals[2] = seg_off[r] + (is_split[r] ? nb : 0);       // partial-sum slots
     }
 }
 
-__global__ void bulk_bucket_kernel(const int4* __restrict__ items, const int32_t* __restrict__ totals, int64_t n_buckets,
-                                   int4* __restrict__ buckets) {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n_buckets) return;
-    const int n = totals[0];
-    auto lower = [&](int64_t target) {          // first item whose begin >= target (begins are non-decreasing in row order)
-        int lo = 0, hi = n;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((int64_t)items[mid].y < target) lo = mid + 1; else hi = mid;
-        }
-        return lo;
-    };
-    const int lo = lower(t * kBulkBucket), hi = lower((t + 1) * kBulkBucket);
-    if (hi <= lo) {
-        buckets[2 * t] = make_int4(lo, 0, 0, 0);
-        buckets[2 * t + 1] = make_int4(0, 0, 0, 0);
-        return;
-    }
-    const int4 first = items[lo], last = items[hi - 1];
-    buckets[2 * t] = make_int4(lo, hi - lo, first.x, last.x - first.x + 1);
-    buckets[2 * t + 1] = make_int4(first.y, last.z, 0, 0);
+__global__ void bulk_extent_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, const int32_t* __restrict__ totals,
+                                   int32_t* __restrict__ buckets) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int total = totals[0];
+    if (k >= total) return;
+    if (buckets[8 * k + 4] >= 0) return;                       // chunk of a long row: complete
+    const int row0 = buckets[8 * k];
+    const int r1 = (k + 1 < total) ? buckets[8 * (k + 1)] : (int)n_rows;
+    buckets[8 * k + 1] = r1 - row0;
+    buckets[8 * k + 3] = rowptr[r1] - rowptr[row0];
 }
 
 __global__ void row_normalize_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows, float* __restrict__ vals) {
@@ -316,45 +331,58 @@ extern "C" int mmssl_spmm_plan(const int32_t* rowptr, int64_t n_rows, int64_t nn
 
 
 extern "C" int64_t mmssl_spmm_bulk_plan_splits_cap(int64_t nnz) { return nnz / (kBulkBucket + 1) + 2; }
-extern "C" int64_t mmssl_spmm_bulk_plan_segs_cap(int64_t nnz) { return nnz / kBulkBucket + 2 * mmssl_spmm_bulk_plan_splits_cap(nnz) + 2; }
-extern "C" int64_t mmssl_spmm_bulk_plan_items_cap(int64_t n_rows, int64_t nnz) { return n_rows + mmssl_spmm_bulk_plan_segs_cap(nnz); }
-extern "C" int64_t mmssl_spmm_bulk_plan_buckets(int64_t nnz) { return nnz / kBulkBucket + 1; }
+extern "C" int64_t mmssl_spmm_bulk_plan_segs_cap(int64_t nnz) { return nnz / kBulkBucket + mmssl_spmm_bulk_plan_splits_cap(nnz) + 2; }
+extern "C" int64_t mmssl_spmm_bulk_plan_buckets_cap(int64_t n_rows, int64_t nnz) { return n_rows / kBulkRows + nnz / 8 + 16; }
+extern "C" int64_t mmssl_spmm_bulk_plan_workspace_bytes(int64_t n_rows) {
+    size_t cub_bytes = 0;
+    if (n_rows <= 0) return 256;
+    if (cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_rows) != cudaSuccess)
+        return -1;
+    return (int64_t)(9 * ((sizeof(int32_t) * n_rows + 255) & ~(size_t)255) + cub_bytes + 512);
+}
 
-extern "C" int mmssl_spmm_bulk_plan(const int32_t* rowptr, int64_t n_rows, int64_t nnz, int32_t* items4, int64_t items_cap,
-                                    int32_t* split_table4, int32_t* counters, int64_t splits_cap, int32_t* buckets8,
-                                    int64_t n_buckets, int32_t* totals3, void* workspace, int64_t workspace_bytes, void* stream_) {
+extern "C" int mmssl_spmm_bulk_plan(const int32_t* rowptr, int64_t n_rows, int64_t nnz, int32_t* split_table4, int32_t* counters,
+                                    int64_t splits_cap, int32_t* buckets8, int64_t buckets_cap, int32_t* totals3, void* workspace,
+                                    int64_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    MMSSL_REQUIRE(items_cap >= mmssl_spmm_bulk_plan_items_cap(n_rows, nnz), "items_cap too small");
     MMSSL_REQUIRE(splits_cap >= mmssl_spmm_bulk_plan_splits_cap(nnz), "splits_cap too small");
-    MMSSL_REQUIRE(n_buckets == mmssl_spmm_bulk_plan_buckets(nnz), "n_buckets must be mmssl_spmm_bulk_plan_buckets(nnz)");
+    MMSSL_REQUIRE(buckets_cap >= mmssl_spmm_bulk_plan_buckets_cap(n_rows, nnz), "buckets_cap too small");
     const int T = 256;
-    MMSSL_CUDA(cudaMemsetAsync(items4, 0xff, sizeof(int4) * items_cap, stream));
     MMSSL_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * splits_cap, stream));
     MMSSL_CUDA(cudaMemsetAsync(totals3, 0, sizeof(int32_t) * 3, stream));
-    MMSSL_CUDA(cudaMemsetAsync(buckets8, 0, sizeof(int4) * 2 * n_buckets, stream));
+    MMSSL_CUDA(cudaMemsetAsync(buckets8, 0, sizeof(int4) * 2 * buckets_cap, stream));      // unused entries: 0 rows -> skipped
     if (n_rows == 0) return 0;
     size_t cub_bytes = 0;
     MMSSL_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_rows));
     const size_t arr = (sizeof(int32_t) * n_rows + 255) & ~(size_t)255;
-    MMSSL_REQUIRE((int64_t)(6 * arr + cub_bytes + 256) <= workspace_bytes, "workspace too small (mmssl_spmm_plan_workspace_bytes)");
+    MMSSL_REQUIRE((int64_t)(9 * arr + cub_bytes + 256) <= workspace_bytes, "workspace too small (mmssl_spmm_bulk_plan_workspace_bytes)");
     char* b = (char*)workspace;
-    int32_t* n_items = (int32_t*)(b);
-    int32_t* is_split = (int32_t*)(b + arr);
-    int32_t* n_segs = (int32_t*)(b + 2 * arr);
-    int32_t* item_off = (int32_t*)(b + 3 * arr);
-    int32_t* split_off = (int32_t*)(b + 4 * arr);
-    int32_t* seg_off = (int32_t*)(b + 5 * arr);
-    void* cub_tmp = (void*)(b + 6 * arr);
-    bulk_count_kernel<<<(unsigned)((n_rows + T - 1) / T), T, 0, stream>>>(rowptr, n_rows, n_items, is_split, n_segs);
+    int32_t* run_flag = (int32_t*)(b);
+    int32_t* run_excl = (int32_t*)(b + arr);
+    int32_t* run_first = (int32_t*)(b + 2 * arr);
+    int32_t* n_bk = (int32_t*)(b + 3 * arr);
+    int32_t* is_split = (int32_t*)(b + 4 * arr);
+    int32_t* n_segs = (int32_t*)(b + 5 * arr);
+    int32_t* bk_off = (int32_t*)(b + 6 * arr);
+    int32_t* split_off = (int32_t*)(b + 7 * arr);
+    int32_t* seg_off = (int32_t*)(b + 8 * arr);
+    void* cub_tmp = (void*)(b + 9 * arr);
+    const unsigned gr = (unsigned)((n_rows + T - 1) / T);
+    bulk_runflag_kernel<<<gr, T, 0, stream>>>(rowptr, n_rows, run_flag);
     MMSSL_LAUNCH_OK();
-    MMSSL_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, n_items, item_off, (int)n_rows, stream));
+    MMSSL_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, run_flag, run_excl, (int)n_rows, stream));
+    bulk_runfirst_kernel<<<gr, T, 0, stream>>>(run_flag, run_excl, n_rows, run_first);
+    MMSSL_LAUNCH_OK();
+    bulk_count_kernel<<<gr, T, 0, stream>>>(rowptr, n_rows, run_flag, run_excl, run_first, n_bk, is_split, n_segs);
+    MMSSL_LAUNCH_OK();
+    MMSSL_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, n_bk, bk_off, (int)n_rows, stream));
     MMSSL_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, is_split, split_off, (int)n_rows, stream));
     MMSSL_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, n_segs, seg_off, (int)n_rows, stream));
     const int64_t threads = n_rows * 32;
-    bulk_fill_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, stream>>>(rowptr, n_rows, item_off, split_off, seg_off, is_split,
-                                                                         (int4*)items4, (int4*)split_table4, totals3);
+    bulk_fill_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, stream>>>(rowptr, n_rows, n_bk, bk_off, split_off, seg_off, is_split,
+                                                                         (int4*)buckets8, (int4*)split_table4, totals3);
     MMSSL_LAUNCH_OK();
-    bulk_bucket_kernel<<<(unsigned)((n_buckets + T - 1) / T), T, 0, stream>>>((const int4*)items4, totals3, n_buckets, (int4*)buckets8);
+    bulk_extent_kernel<<<(unsigned)((buckets_cap + T - 1) / T), T, 0, stream>>>(rowptr, n_rows, totals3, buckets8);
     MMSSL_LAUNCH_OK();
     return 0;
 }

@@ -86,29 +86,28 @@ class SparseOperand:
         return w
 
     def bulk_plan(self):
-        """Work plan of the bulk-copy SpMM (csrc/spmm_bulk.cu): buckets of 32 non-zeros, rows over 32 non-zeros cut at the
-        bucket boundaries.  Built once per operand on first use; returns (CsrDesc with the bulk items, buckets, n_buckets)."""
+        """Bucket plan of the staged-gather SpMM (csrc/spmm_bulk.cu): buckets of <= 32 non-zeros / <= 8 whole rows, rows over 32
+        non-zeros cut into 32-chunks.  Built once per operand on first use (one host read of the bucket count)."""
         if self._bulk is None:
             lib = _lib.load(require_device=True)
             i32 = dict(dtype=torch.int32, device=self.device)
-            items_cap = lib.mmssl_spmm_bulk_plan_items_cap(self.n_rows, self.nnz)
             splits_cap = lib.mmssl_spmm_bulk_plan_splits_cap(self.nnz)
             segs_cap = lib.mmssl_spmm_bulk_plan_segs_cap(self.nnz)
-            n_buckets = lib.mmssl_spmm_bulk_plan_buckets(self.nnz)
-            items = torch.empty(items_cap * 4, **i32)
+            buckets_cap = lib.mmssl_spmm_bulk_plan_buckets_cap(self.n_rows, self.nnz)
             split_table = torch.empty(splits_cap * 4, **i32)
             counters = torch.empty(splits_cap, **i32)
-            buckets = torch.empty(n_buckets * 8, **i32)
+            buckets = torch.empty(buckets_cap * 8, **i32)
             totals = torch.empty(3, **i32)
-            pws_bytes = lib.mmssl_spmm_plan_workspace_bytes(self.n_rows)
+            pws_bytes = lib.mmssl_spmm_bulk_plan_workspace_bytes(self.n_rows)
             pws = torch.empty(pws_bytes, dtype=torch.uint8, device=self.device)
-            _lib.check(lib.mmssl_spmm_bulk_plan(ptr(self.rowptr), self.n_rows, self.nnz, ptr(items), items_cap, ptr(split_table),
-                                                ptr(counters), splits_cap, ptr(buckets), n_buckets, ptr(totals), ptr(pws), pws_bytes,
-                                                stream()))
-            desc = CsrDesc(ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), self.n_rows, self.n_cols, self.nnz, ptr(items),
-                           items_cap, ptr(split_table), ptr(counters), segs_cap)
-            self._bulk = dict(desc=desc, buckets=buckets, n_buckets=n_buckets, items=items, split_table=split_table, counters=counters,
-                              totals=totals, segs_cap=segs_cap, splits_cap=splits_cap, work={}, keep=pws)
+            _lib.check(lib.mmssl_spmm_bulk_plan(ptr(self.rowptr), self.n_rows, self.nnz, ptr(split_table), ptr(counters), splits_cap,
+                                                ptr(buckets), buckets_cap, ptr(totals), ptr(pws), pws_bytes, stream()))
+            n_buckets, n_split, n_segs = (int(x) for x in totals.cpu())
+            buckets = buckets[:max(n_buckets, 1) * 8].clone()             # exact size (the capacity bound is generous)
+            desc = CsrDesc(ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), self.n_rows, self.n_cols, self.nnz, ptr(self.rowptr),
+                           0, ptr(split_table), ptr(counters), max(n_segs, 0))
+            self._bulk = dict(desc=desc, buckets=buckets, n_buckets=n_buckets, split_table=split_table, counters=counters,
+                              totals=totals, segs_cap=max(n_segs, 0), splits_cap=splits_cap, n_split=n_split, work={})
         return self._bulk
 
     def bulk_work_area(self, width: int):

@@ -161,6 +161,7 @@ void ptx_op(const char* text, void** outs, const int* out_sizes, int n_out, cons
         memcpy(smem_at(in[0], 16), reinterpret_cast<const void*>((uintptr_t)in[1]), 16);
         return;
     }
+    if (has("cp.async.commit_group") || has("cp.async.wait_group")) return;      // copies execute at once in this model
     if (has("cp.async.mbarrier.arrive.noinc")) {            // the lane's earlier copies have landed (model: they always have)
         bar_arrive(bar_at(in[0]));
         return;

@@ -1,7 +1,7 @@
-"""Bulk-copy gather SpMM (csrc/spmm_bulk.cu, plan: mmssl_spmm_bulk_plan) against scipy fp64 and against the LDG kernel:
-plain products, both ring sizes, several buckets per warp, all epilogues, row-indexed operands (alpha*C, running sums, saved
-softmax output), rows cut at bucket boundaries (deterministic reduction) and heavy rows (vector reductions), empty rows, empty
-graphs, strided operands, repeated launches (self-resetting counters / slots)."""
+"""Staged-gather SpMM (csrc/spmm_bulk.cu, plan: mmssl_spmm_bulk_plan) against scipy fp64: the bucket plan's invariants, plain
+products with both copy engines (warp-wide cp.async / one TMA bulk copy per row), several buckets per warp, all epilogues,
+row-indexed operands (alpha*C, running sums, saved softmax output), long rows cut into chunks (deterministic reduction) and
+heavy rows (vector reductions), empty rows, empty graphs, strided operands, repeated launches (self-resetting counters / slots)."""
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -18,42 +18,55 @@ def _bulk(nst=0, wpb=0, tpw=0, tma=0):
     return ops.SPMM_IMPL_BULK | nst | (wpb << 4) | (tpw << 8) | (ops.SPMM_BULK_TMA if tma else 0)
 
 
-def test_bulk_plan_covers_every_nonzero_once():
-    """Every position belongs to exactly one item, items of a bucket start inside it, long rows are cut at the boundaries."""
-    g, ref = _graph(700, 500, 30000, seed=5, heavy_rows=2)
-    b = g.fwd.bulk_plan()
-    torch.cuda.synchronize()
-    n_items, n_split, n_segs = b["totals"].cpu().tolist()
-    items = b["items"].cpu().numpy().reshape(-1, 4)[:n_items]
-    rowptr = g.fwd.rowptr.cpu().numpy()
-    cover = np.zeros(g.fwd.nnz, np.int32)
-    for row, lo, hi, split in items:
-        cover[lo:hi] += 1
-        assert rowptr[row] <= lo <= hi <= rowptr[row + 1]
+def _check_plan(op):
+    """Every position belongs to exactly one bucket, buckets hold <= 32 positions and <= 8 whole rows (or one chunk of a long row),
+    rows of <= 32 non-zeros are never cut, every row is covered, buckets come in row order."""
+    b = op.bulk_plan()
+    n = b["n_buckets"]
+    bk = b["buckets"].cpu().numpy().reshape(-1, 8)[:n]
+    rowptr = op.rowptr.cpu().numpy()
+    n_rows = op.n_rows
+    cover = np.zeros(max(op.nnz, 1), np.int32)
+    row_seen = np.zeros(n_rows, np.int32)
+    st = b["split_table"].cpu().numpy().reshape(-1, 4)
+    last_row = -1
+    for row0, nr, nz0, cnt, split, seg, _, _ in bk:
+        assert 1 <= nr <= 8 and 0 <= cnt <= 32
+        cover[nz0:nz0 + cnt] += 1
         if split < 0:
-            assert (lo, hi) == (rowptr[row], rowptr[row + 1]) and hi - lo <= 32
+            assert row0 > last_row
+            assert nz0 == rowptr[row0] and nz0 + cnt == rowptr[row0 + nr]
+            assert (np.diff(rowptr[row0:row0 + nr + 1]) <= 32).all()
+            row_seen[row0:row0 + nr] += 1
+            last_row = row0 + nr - 1
         else:
-            assert hi - lo <= 32 and lo // 32 == (hi - 1) // 32
-    assert (cover == 1).all()
-    assert (np.diff(items[:, 1]) >= 0).all() and n_split > 0
-    bk = b["buckets"].cpu().numpy().reshape(-1, 8)
-    assert bk.shape[0] == g.fwd.nnz // 32 + 1
-    seen = 0
-    for t, (i0, n, row0, n_rows, nz0, nz1, _, _) in enumerate(bk):
-        if n == 0:
-            continue
-        assert i0 == seen
-        seen += n
-        its = items[i0:i0 + n]
-        assert (its[:, 1] // 32 == t).all() or (its[:, 1] == its[:, 2]).all() or ((its[:, 1] >= 32 * t) & (its[:, 1] < 32 * t + 32)).all()
-        assert nz0 == its[0, 1] and nz1 == its[-1, 2] and nz1 - 32 * t <= 64
-        assert row0 == its[0, 0] and n_rows == its[-1, 0] - row0 + 1
-    assert seen == n_items
+            assert nr == 1 and rowptr[row0 + 1] - rowptr[row0] > 32
+            chunks = -(-(rowptr[row0 + 1] - rowptr[row0]) // 32)
+            assert st[split, 1] == chunks and 0 <= seg < chunks and nz0 == rowptr[row0] + 32 * seg
+            assert st[split, 3] == (1 if chunks > 32 else 0)
+            if seg == 0:
+                row_seen[row0] += 1
+                assert row0 > last_row
+                last_row = row0
+    if op.nnz:
+        assert (cover[:op.nnz] == 1).all()
+    assert (row_seen == 1).all()
+    return bk
+
+
+def test_bulk_plan_covers_every_nonzero_once():
+    g, ref = _graph(700, 500, 30000, seed=5, heavy_rows=2)
+    bk = _check_plan(g.fwd)
+    assert (bk[:, 4] >= 0).any()                                      # the heavy rows are cut into chunks
+    _check_plan(g.bwd)
+    g2, _ = _graph(5000, 40, 3000, seed=6)                            # mostly empty rows: buckets of 8 rows without positions
+    _check_plan(g2.fwd)
+    _check_plan(g2.bwd)
 
 
 @pytest.mark.parametrize("d", [64, 128, 256])
 @pytest.mark.parametrize("nrhs", [1, 2])
-@pytest.mark.parametrize("variant", [(0, 0, 0, 0), (2, 2, 3, 0), (4, 4, 1, 1), (2, 8, 1, 0), (0, 0, 0, 1)])
+@pytest.mark.parametrize("variant", [(0, 0, 0, 0), (0, 2, 3, 0), (0, 4, 1, 1), (0, 8, 1, 0), (0, 1, 2, 1)])
 def test_spmm_bulk_plain(d, nrhs, variant):
     from mmssl_b200 import ops
     g, ref = _graph(700, 500, 30000, seed=d + nrhs, heavy_rows=2)
@@ -76,11 +89,10 @@ def test_spmm_bulk_plain(d, nrhs, variant):
 
 
 @pytest.mark.parametrize("d", [64, 128, 256])
-@pytest.mark.parametrize("nst", [2, 4])
 @pytest.mark.parametrize("tma", [0, 1])
-def test_spmm_bulk_epilogues(d, nst, tma):
+def test_spmm_bulk_epilogues(d, tma):
     from mmssl_b200 import ops
-    impl = _bulk(nst, tma=tma)
+    impl = _bulk(tma=tma)
     g, ref = _graph(300, 260, 9000, seed=7 + d, heavy_rows=1)
     torch.manual_seed(1)
     x = torch.randn(260, d, device="cuda")
@@ -91,8 +103,10 @@ def test_spmm_bulk_epilogues(d, nst, tma):
     s = torch.empty(300, d, device="cuda")
     y = ops.spmm(g.fwd, [x], cs=[c], alpha=0.25, epilogue=ops.EPI_SOFTMAX, ss=[s], s_mode=2, sbases=[sb], impl=impl)[0]
     want = torch.softmax(v, dim=-1)
-    assert rel_err(y, want) < 5e-6
-    assert rel_err(s, sb.double().cpu() + want) < 5e-6
+    # row 0 is a heavy row (3000 non-zeros, vector reductions in arrival order): its fp32 sum moves by ~1e-6 of its magnitude
+    # (~50) from run to run, which the softmax turns into ~1e-5 -- hence 3e-5 here, 5e-6 where no exponential follows
+    assert rel_err(y, want) < 3e-5
+    assert rel_err(s, sb.double().cpu() + want) < 3e-5
     ops.spmm(g.fwd, [x], cs=[c], alpha=0.25, epilogue=ops.EPI_NONE, ss=[s], s_mode=1, impl=impl)
     assert rel_err(s, sb.double().cpu() + want + v) < 5e-6
     ysv = torch.softmax(torch.randn(300, d, device="cuda"), -1)
@@ -128,9 +142,10 @@ def test_spmm_bulk_many_short_and_empty_rows():
     cc = torch.randn(n_rows, 64, device="cuda")
     s = torch.randn(n_rows, 64, device="cuda")
     s0 = s.clone()
-    for nst, tma in ((2, 0), (4, 0), (2, 1), (4, 1)):
+    _check_plan(g.fwd)
+    for tma in (0, 1):
         s.copy_(s0)
-        y = ops.spmm(g.fwd, [x], cs=[cc], alpha=-1.5, ss=[s], s_mode=1, impl=_bulk(nst, tma=tma))[0]
+        y = ops.spmm(g.fwd, [x], cs=[cc], alpha=-1.5, ss=[s], s_mode=1, impl=_bulk(tma=tma))[0]
         want = torch.from_numpy(ref @ x.double().cpu().numpy()) - 1.5 * cc.double().cpu()
         assert rel_err(y, want) < 2e-6
         assert rel_err(s, s0.double().cpu() + want) < 2e-6
