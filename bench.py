@@ -64,6 +64,8 @@ def parse():
     ap.add_argument("--row-shard", default="sports,syn1m",
                     help="N > 1: also run the row-sharded whole hot step (north_star's scheme) on these configs; 'none' to skip")
     ap.add_argument("--row-exchange", default="multicast", choices=["multicast", "nccl"])
+    ap.add_argument("--row-schedule", default="reduce_scatter", choices=["reduce_scatter", "allgather"],
+                    help="products with a user-sized operand: partial products + reduce-scatter of the item-sized result, or all-gather of the operand")
     ap.add_argument("--row-graph", type=int, default=1, help="capture the row-sharded step in a CUDA graph (multicast exchange only)")
     ap.add_argument("--graph-comm", action="store_true",
                     help="EXPERIMENTAL (hung in round 1): capture the DP all-reduce + AdamW inside the CUDA graph")
@@ -554,18 +556,18 @@ def row_shard_report(name, a, rank, world, dev):
     Pl, fl, gl, pu, pi = shard_problem(P_cpu, feats_cpu, ds.ui_norm, ds.iu_norm, rank, world, dev)
     mode = a.row_exchange
     try:
-        sh = RowShardedHotStep(Pl, fl, gl, cfg, BATCH, pu, pi, rank, exchange=mode)
+        sh = RowShardedHotStep(Pl, fl, gl, cfg, BATCH, pu, pi, rank, exchange=mode, schedule=a.row_schedule)
     except (RuntimeError, ImportError, AttributeError) as e:
         if rank == 0:
             print(f"[bench] multicast exchange unavailable ({e}); NCCL all-gathers", file=sys.stderr)
         mode = "nccl"
-        sh = RowShardedHotStep(Pl, fl, gl, cfg, BATCH, pu, pi, rank, exchange=mode)
+        sh = RowShardedHotStep(Pl, fl, gl, cfg, BATCH, pu, pi, rank, exchange=mode, schedule=a.row_schedule)
     smp = TripleSampler(ds.train, seed=a.seed)
     batches = [tuple(torch.from_numpy(x).to(dev) for x in smp.sample(BATCH)) for _ in range(8)]
     g = torch.Generator().manual_seed(7)
     full_masks = tuple(((torch.rand(I, d, generator=g) >= cfg.drop_rate) / (1 - cfg.drop_rate)).float() for _ in range(2))
     out = {"workload": f"{name}: {U}x{I}, {nnz} edges, d={d}, {K}-layer GCN, V{dv}/T{dt}, global B={BATCH}", "n_gpus": world,
-           "exchange": mode}
+           "exchange": mode, "schedule": sh.schedule}
 
     # ---- parity of one step (no optimiser) against the 1-GPU fused step on rank 0
     sh.masks = tuple(pi.local(m, rank).to(dev) for m in full_masks)
@@ -629,7 +631,7 @@ def row_shard_report(name, a, rank, world, dev):
         sh.set_indices(*batches[s % 8]); step()
     torch.cuda.synchronize()
     dist.barrier()
-    sh.n_gathers = sh.gathered_bytes = 0
+    sh.n_gathers = sh.gathered_bytes = sh.n_reduce_scatters = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(steps):
@@ -640,14 +642,14 @@ def row_shard_report(name, a, rank, world, dev):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     if not captured:
-        gath, gbytes = sh.n_gathers // steps, sh.gathered_bytes / steps
+        gath, rsc, gbytes = sh.n_gathers // steps, sh.n_reduce_scatters // steps, sh.gathered_bytes / steps
     else:                                       # counted once at capture time: run one eager step to count
-        sh.n_gathers = sh.gathered_bytes = 0
+        sh.n_gathers = sh.gathered_bytes = sh.n_reduce_scatters = 0
         sh.run()
         torch.cuda.synchronize()
-        gath, gbytes = sh.n_gathers, float(sh.gathered_bytes)
+        gath, rsc, gbytes = sh.n_gathers, sh.n_reduce_scatters, float(sh.gathered_bytes)
     out.update({"ms_per_step": round(ms, 4), "value": round(BATCH / ms * 1e3, 1), "unit": UNIT, "steps": steps, "cuda_graph": captured,
-                "exchanges_per_step": int(gath), "bytes_received_per_rank_per_step": int(gbytes),
+                "all_gathers_per_step": int(gath), "reduce_scatters_per_step": int(rsc), "bytes_received_per_rank_per_step": int(gbytes),
                 "nvlink_GBps_per_rank_if_serial": round(gbytes / (ms * 1e-3) / 1e9, 1),
                 "build_s": round(time.perf_counter() - t0, 1)})
     if rank == 0 and ms_1gpu is not None:

@@ -121,6 +121,13 @@ int mmssl_spmm_bulk_f32(const mmssl_csr_t* a /*host*/, const int32_t* buckets8, 
                         const mmssl_spmm_rhs_t* rhs /*host*/, int epilogue, float alpha, int s_mode, float* partials,
                         int64_t partials_floats, int variant, void* stream);
 
+/* Second half of a row-sharded product computed as partial products (rowshard_step.py, schedule "reduce_scatter"): the rank's
+ * rows of the SUM over all ranks' partial tables -- rhs[r].x = multicast address of the rank's first row (multicast != 0:
+ * multimem.ld_reduce, the NVSwitch adds the replicas) or a local pointer to reduced rows (multicast == 0) -- followed by the
+ * SpMM epilogue of mmssl_spmm_csr_f32 (+ alpha*C, softmax / softmax backward, store, running sum; same rhs fields). */
+int mmssl_reduce_rows_epilogue(int64_t n_rows, int d, int nrhs, const mmssl_spmm_rhs_t* rhs /*host*/, int epilogue, float alpha,
+                               int s_mode, int multicast, void* stream);
+
 /* ------------------------------------------------------------------ dense fp32 GEMM (CUDA-core path)
  * C = alpha * op(A) * op(B) + beta * C, row-major.  Used for the d x d "attention" mixing
  * (Models.py:139-169 == v * sum_h Wcat[h]) and as the verification path of the

@@ -55,6 +55,7 @@ _SIGS = {
     "mmssl_spmm_bulk_plan": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "mmssl_spmm_bulk_f32": (C.c_int, [C.POINTER(CsrDesc), c_vp, c_i64, c_i32, c_i32, C.POINTER(SpmmRhs), c_i32, c_f32, c_i32, c_vp,
                                       c_i64, c_i32, c_vp]),
+    "mmssl_reduce_rows_epilogue": (C.c_int, [c_i64, c_i32, c_i32, C.POINTER(SpmmRhs), c_i32, c_f32, c_i32, c_i32, c_vp]),
     "mmssl_sgemm": (C.c_int, [c_i32, c_i32, c_i64, c_i64, c_i64, c_f32, c_vp, c_i64, c_vp, c_i64, c_f32, c_vp, c_i64,
                               c_i32, c_vp]),
     "mmssl_id_fuse_fwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -133,7 +134,7 @@ _lib = None
 
 # kernels launched by one call of each entry point (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
-    "mmssl_csr_from_coo": 6, "mmssl_csr_row_normalize": 1, "mmssl_spmm_plan": 8, "mmssl_spmm_csr_f32": 1, "mmssl_spmm_hot_f32": 1, "mmssl_spmm_bulk_plan": 9, "mmssl_spmm_bulk_f32": 1, "mmssl_sgemm": 1,
+    "mmssl_csr_from_coo": 6, "mmssl_csr_row_normalize": 1, "mmssl_spmm_plan": 8, "mmssl_spmm_csr_f32": 1, "mmssl_spmm_hot_f32": 1, "mmssl_spmm_bulk_plan": 9, "mmssl_spmm_bulk_f32": 1, "mmssl_reduce_rows_epilogue": 1, "mmssl_sgemm": 1,
     "mmssl_id_fuse_fwd": 1, "mmssl_id_fuse_bwd": 1, "mmssl_wsum": 1, "mmssl_id_fuse2_fwd": 1, "mmssl_id_fuse2_bwd": 1,
     "mmssl_dwcat_reduce": 1, "mmssl_combine_fwd": 1, "mmssl_combine_bwd": 1, "mmssl_softmax_bwd": 1,
     "mmssl_axpby": 1, "mmssl_mul_mask": 1, "mmssl_sumsq": 1, "mmssl_bpr": 1, "mmssl_infonce_prepare": 1,

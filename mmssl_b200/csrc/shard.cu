@@ -5,8 +5,7 @@
 //   scatter_add_owned table[idx[j] - lo] += src[j] for the owned j only           -> the loss kernels' gradient rows
 //                     return to the rank that owns the row; duplicates (the same item drawn twice) accumulate atomically
 // One thread per float4 of a row (d % 4 == 0, rows 16-byte aligned like every table of the library).
-#include "common.cuh"
-#include "../../include/mmssl_b200.h"
+#include "spmm_common.cuh"
 
 namespace mmssl {
 
@@ -121,4 +120,63 @@ extern "C" int mmssl_mc_allreduce_sum(const float* src_mc, float* dst, int64_t n
     mc_allreduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(src_mc, dst, n / 4);
     MMSSL_LAUNCH_OK();
     return 0;
+}
+
+// ---- reduce-scatter + SpMM epilogue of the row-sharded step's "partial product" schedule (rowshard_step.py): for a product
+// whose dense operand lives in the LARGE (user) row space, every rank multiplies the column block of A it owns,
+// A[:, U_r] * X[U_r], into its copy of a full-height partial table (symmetric memory).  After a barrier this kernel gives a rank
+// the rows it owns of the SUM over the ranks' copies -- one multimem.ld_reduce per 16 bytes through the table's multicast
+// address (the switch adds the replicas), or a plain load when `reduced` rows are handed in (NCCL / gloo reduce-scatter) -- and
+// applies what the SpMM would have applied to a finished row: + alpha*C, row softmax / softmax backward, the store, the running
+// layer sum.  Only the item-sized table crosses NVLink; the user-sized operand never moves.
+namespace mmssl {
+template <int G, int C, int R>
+__global__ void __launch_bounds__(256) reduce_rows_epilogue_kernel(const SpmmParams p, int64_t n_rows, int multicast) {
+    const unsigned gmask = group_mask<G>();
+    const int lane = threadIdx.x & (G - 1);
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    if (row >= n_rows) return;            // whole group exits together
+    float4 acc[R][C];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float* src = p.x[r] + row * p.ldx[r] + lane * 4 + c * (4 * G);
+            if (multicast) {
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(acc[r][c].x), "=f"(acc[r][c].y), "=f"(acc[r][c].z), "=f"(acc[r][c].w) : "l"(src) : "memory");
+            } else {
+                acc[r][c] = ld4(src);
+            }
+        }
+    spmm_epilogue<G, C, R>(p, acc, (int)row, lane, gmask);
+}
+
+template <int G, int C>
+static int launch_reduce_rows(const SpmmParams& p, int nrhs, int64_t n_rows, int multicast, cudaStream_t st) {
+    const int T = 256;
+    const int64_t blocks = (n_rows * G + T - 1) / T;
+    if (blocks == 0) return 0;
+    if (nrhs == 1) reduce_rows_epilogue_kernel<G, C, 1><<<(unsigned)blocks, T, 0, st>>>(p, n_rows, multicast);
+    else if (nrhs == 2) reduce_rows_epilogue_kernel<G, C, 2><<<(unsigned)blocks, T, 0, st>>>(p, n_rows, multicast);
+    else reduce_rows_epilogue_kernel<G, C, 3><<<(unsigned)blocks, T, 0, st>>>(p, n_rows, multicast);
+    MMSSL_LAUNCH_OK();
+    return 0;
+}
+}  // namespace mmssl
+
+// rhs[r].x = the rank's row block inside the partial table: the MULTICAST address of its first row (multicast != 0) or a local
+// pointer to already reduced rows (multicast == 0); every other field as for mmssl_spmm_csr_f32 (y, c, ysaved, s, sbase: local rows).
+extern "C" int mmssl_reduce_rows_epilogue(int64_t n_rows, int d, int nrhs, const mmssl_spmm_rhs_t* rhs, int epilogue, float alpha,
+                                          int s_mode, int multicast, void* stream_) {
+    MMSSL_REQUIRE(n_rows >= 0 && n_rows < (1ll << 31), "row count");
+    mmssl_csr_t a;
+    memset(&a, 0, sizeof(a));
+    a.items = reinterpret_cast<const int32_t*>(rhs);      // unused by the epilogue; fill_spmm_params only checks presence
+    SpmmParams p;
+    if (int rc = fill_spmm_params(p, &a, d, nrhs, rhs, epilogue, alpha, s_mode, nullptr, 0)) return rc;
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (d == 64) return launch_reduce_rows<16, 1>(p, nrhs, n_rows, multicast, st);
+    if (d == 128) return launch_reduce_rows<32, 1>(p, nrhs, n_rows, multicast, st);
+    return launch_reduce_rows<32, 2>(p, nrhs, n_rows, multicast, st);
 }

@@ -80,9 +80,19 @@ class Engine:
         # global column ids, and each SpMM needs its dense operand from all ranks.  ``exchange(list_of_local, space)``
         # ('u' = user rows, 'i' = item rows) returns the gathered operands; None = single GPU, operands pass through.
         self.exchange = None
+        self.sharded_spmm = None            # callable(g, which, xs, space, ys, **spmm_kwargs) -> list of local outputs
 
     def _full(self, xs, space: str):
         return xs if self.exchange is None else self.exchange(xs, space)
+
+    def _spmm(self, g, which: str, xs, space: str, ys=None, **kw):
+        """One propagation product  Y = epi(op(g) @ X):  which = 'fwd' (A) or 'bwd' (A^T); `space` names the row space the dense
+        operand lives in ('u' users / 'i' items).  Single GPU: the operand passes through.  Row-sharded: `sharded_spmm`
+        (rowshard_step.py) decides how the operand / the result crosses the GPUs (all-gather of the operand, or partial products
+        + reduce-scatter of the result, whichever moves the item-sized table)."""
+        if self.sharded_spmm is not None:
+            return self.sharded_spmm(g, which, xs, space, ys, **kw)
+        return ops.spmm(getattr(g, which), self._full(xs, space), ys, **kw)
 
     def _pair(self, dev, fn_a, fn_b):
         """Run two independent kernel groups concurrently (user side on the current stream, item side
@@ -180,8 +190,8 @@ class Engine:
             resolved[0] = m
             self._project(P[P_WV], P[P_BV], feats[0], m[0] if m else None, xv)             # Models.py:173
             self._project(P[P_WT], P[P_BT], feats[1], m[1] if m else None, xt)             # Models.py:174
-            ops.spmm(g_ui.fwd, self._full([xv, xt], "i"), [uv, ut])                        # :177,182
-            ops.spmm(g_iu.fwd, self._full([uv, ut], "u"), [iv, it])                        # :178,183
+            self._spmm(g_ui, "fwd", [xv, xt], "i", [uv, ut])                        # :177,182
+            self._spmm(g_iu, "fwd", [uv, ut], "u", [iv, it])                        # :178,183
 
         if side is not main:
             side.wait_stream(main)
@@ -191,13 +201,10 @@ class Engine:
             modal_branch()
 
         def id_prop(ga, gb, e, rows, space):                                           # :179-180,185-186
-            if ga.nnz > 0 or gb.nnz > 0:
-                e = self._full([e], space)[0]
-
             def one(g):
                 if g.nnz == 0:
                     return torch.zeros(rows, d, dtype=torch.float32, device=dev)
-                return ops.spmm(g.fwd, [e])[0]
+                return self._spmm(g, "fwd", [e], space)[0]
             ya = one(ga)
             return (ya, ya) if ga is gb else (ya, one(gb))
 
@@ -237,8 +244,8 @@ class Engine:
             last = k == K - 1
             epi = ops.EPI_SOFTMAX if last else ops.EPI_NONE
             mode = 2 if k == 0 else 1
-            u_n = ops.spmm(g_ui.fwd, self._full([cur_i], "i"), epilogue=epi, ss=[s_u], s_mode=mode, sbases=[u0] if k == 0 else None)[0]
-            i_n = ops.spmm(g_iu.fwd, self._full([u_n], "u"), epilogue=epi, ss=[s_i], s_mode=mode, sbases=[i0] if k == 0 else None)[0]
+            u_n = self._spmm(g_ui, "fwd", [cur_i], "i", epilogue=epi, ss=[s_u], s_mode=mode, sbases=[u0] if k == 0 else None)[0]
+            i_n = self._spmm(g_iu, "fwd", [u_n], "u", epilogue=epi, ss=[s_i], s_mode=mode, sbases=[i0] if k == 0 else None)[0]
             if last:
                 st.u_last, st.i_last = u_n, i_n
             cur_i = i_n
@@ -300,9 +307,9 @@ class Engine:
         def modal_backward():
             # modality propagation backward (Models.py:177-178,182-183), image|text batched, then the
             # projection backward (dropout mask folded into the operand split)
-            ops.spmm(g_iu.bwd, self._full([gI2[:, :d], gI2[:, d:]], "i"), [gU2[:, :d], gU2[:, d:]], cs=[gU2[:, :d], gU2[:, d:]], alpha=1.0)
+            self._spmm(g_iu, "bwd", [gI2[:, :d], gI2[:, d:]], "i", [gU2[:, :d], gU2[:, d:]], cs=[gU2[:, :d], gU2[:, d:]], alpha=1.0)
             gX2 = self._new(I, 2 * d, dev=dev)
-            ops.spmm(g_ui.bwd, self._full([gU2[:, :d], gU2[:, d:]], "u"), [gX2[:, :d], gX2[:, d:]])
+            self._spmm(g_ui, "bwd", [gU2[:, :d], gU2[:, d:]], "u", [gX2[:, :d], gX2[:, d:]])
             m = st.masks
             self._project_bwd(gX2[:, :d], m[0] if m else None, feats[0], w_slots[0], w_slots[1])
             self._project_bwd(gX2[:, d:], m[1] if m else None, feats[1], w_slots[2], w_slots[3])
@@ -319,10 +326,10 @@ class Engine:
             t = ops.softmax_bwd(st.i_last, g_if, inv, self._new(I, d, dev=dev))
             for k in range(K - 1, -1, -1):
                 last = k == K - 1
-                tu = ops.spmm(g_iu.bwd, self._full([t], "i"), cs=[g_uf], alpha=inv,
+                tu = self._spmm(g_iu, "bwd", [t], "i", cs=[g_uf], alpha=inv,
                               epilogue=ops.EPI_SOFTMAX_BWD if last else ops.EPI_NONE,
                               ysaved=[st.u_last] if last else None)[0]
-                t = ops.spmm(g_ui.bwd, self._full([tu], "u"), cs=[g_if], alpha=inv)[0]
+                t = self._spmm(g_ui, "bwd", [tu], "u", cs=[g_if], alpha=inv)[0]
             g_i0 = t                                            # d loss / d i_0
         else:
             g_i0 = ops.axpby(g_if, inv, 0.0, self._new(I, d, dev=dev))
@@ -387,15 +394,15 @@ class Engine:
                 if ga.nnz == 0:
                     return
                 if same_out and gya is not None:
-                    ops.spmm(ga.bwd, self._full([gya], space), [g_e], cs=[g_e], alpha=1.0)
+                    self._spmm(ga, "bwd", [gya], space, [g_e], cs=[g_e], alpha=1.0)
                     return
                 for g in (gya, gyb):
                     if g is not None:
-                        ops.spmm(ga.bwd, self._full([g], space), [g_e], cs=[g_e], alpha=1.0)
+                        self._spmm(ga, "bwd", [g], space, [g_e], cs=[g_e], alpha=1.0)
                 return
             for gr, g in ((ga, gya), (gb, gyb)):
                 if g is not None and gr.nnz > 0:
-                    ops.spmm(gr.bwd, self._full([g], space), [g_e], cs=[g_e], alpha=1.0)
+                    self._spmm(gr, "bwd", [g], space, [g_e], cs=[g_e], alpha=1.0)
 
         # Uvid = A_vui E_i, Utid = A_tui E_i -> gradient flows to E_i; Ivid/Itid -> E_u.  The head reduction
         # of dWcat does not feed them, so it rides along on the pair stream.

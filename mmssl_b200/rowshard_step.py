@@ -41,8 +41,12 @@ class RowBlockGraph:
     SpMM operands (global column ids), ``shape`` = the LOCAL (padded) row counts of the two row spaces, ``nnz`` = the
     global edge count (only compared with 0)."""
 
-    def __init__(self, fwd: SparseOperand, bwd: SparseOperand, shape: Tuple[int, int], nnz: int):
+    def __init__(self, fwd: SparseOperand, bwd: SparseOperand, shape: Tuple[int, int], nnz: int,
+                 fwd_part: Optional[SparseOperand] = None, bwd_part: Optional[SparseOperand] = None):
         self.fwd, self.bwd, self.shape, self.nnz = fwd, bwd, shape, int(nnz)
+        # partial-product schedule: fwd_part = A[:, cols_r] (every row of A, the rank's columns, LOCAL column ids) so that
+        # A @ X = sum over ranks of fwd_part_r @ X[cols_r];  bwd_part = (A^T)[:, rows_r] likewise for A^T @ dY
+        self.fwd_part, self.bwd_part = fwd_part, bwd_part
 
     @classmethod
     def from_scipy(cls, mat, part_rows: RowPartition, part_cols: RowPartition, rank: int, device) -> "RowBlockGraph":
@@ -52,21 +56,42 @@ class RowBlockGraph:
             o = SparseOperand(t(blk.row, "int64"), t(blk.col, "int64"), t(blk.data, "float32"), blk.shape[0], blk.shape[1])
             o.tighten()
             return o
+        def col_block(m, part_r, part_c):
+            """m[:, cols_r] with rows padded to world * block (the partial table's height) and local column ids."""
+            lo, hi = part_c.bounds(rank)
+            blk = m.tocsc()[:, lo:hi].tocoo()
+            t = lambda a, dt: torch.from_numpy(np.asarray(a).astype(dt)).to(device)
+            o = SparseOperand(t(blk.row, "int64"), t(blk.col, "int64"), t(blk.data, "float32"), part_r.world * part_r.block, part_c.block)
+            o.tighten()
+            return o
         mat = mat.tocsr()
-        return cls(op(mat, part_rows), op(mat.T.tocsr(), part_cols), (part_rows.block, part_cols.block), mat.nnz)
+        mt = mat.T.tocsr()
+        return cls(op(mat, part_rows), op(mt, part_cols), (part_rows.block, part_cols.block), mat.nnz,
+                   fwd_part=col_block(mat, part_rows, part_cols), bwd_part=col_block(mt, part_cols, part_rows))
 
 
     @classmethod
-    def from_csr_blocks(cls, fwd_blk, bwd_blk, nnz: int, device) -> "RowBlockGraph":
+    def from_csr_blocks(cls, fwd_blk, bwd_blk, nnz: int, device, heights=None) -> "RowBlockGraph":
         """From two ``dataset.CsrBlock``s (the rank's rows of A and of A^T as ``ShardedDataset.operand`` maps them from disk:
-        indptr rebased to 0, global column ids): a rank never sees the rest of the graph."""
+        indptr rebased to 0, global column ids): a rank never sees the rest of the graph.  heights = (world * block of A's row
+        space, world * block of its column space): padded heights of the two partial tables (default: the unpadded sizes)."""
         def op(blk):
             rows = np.repeat(np.arange(blk.shape[0], dtype=np.int64), np.diff(blk.indptr))
             t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).astype(dt)).to(device)
             o = SparseOperand(t(rows, "int64"), t(blk.indices, "int64"), t(blk.values, "float32"), blk.shape[0], blk.shape[1])
             o.tighten()
             return o
-        return cls(op(fwd_blk), op(bwd_blk), (fwd_blk.shape[0], bwd_blk.shape[0]), nnz)
+
+        def transposed(blk, height):
+            """(blk)^T with `height` (padded) rows: the column block of the other operand, local column ids."""
+            rows = np.repeat(np.arange(blk.shape[0], dtype=np.int64), np.diff(blk.indptr))
+            t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).astype(dt)).to(device)
+            o = SparseOperand(t(rows, "int64"), t(blk.indices, "int64"), t(blk.values, "float32"), blk.shape[0], height, transpose=True)
+            o.tighten()
+            return o
+        h_rows, h_cols = heights if heights is not None else (bwd_blk.shape[1], fwd_blk.shape[1])
+        return cls(op(fwd_blk), op(bwd_blk), (fwd_blk.shape[0], bwd_blk.shape[0]), nnz,
+                   fwd_part=transposed(bwd_blk, h_rows), bwd_part=transposed(fwd_blk, h_cols))
 
 
 def gather_owned(table: torch.Tensor, idx: torch.Tensor, lo: int, hi: int, out: torch.Tensor) -> torch.Tensor:
@@ -156,6 +181,60 @@ class MulticastAllReduce:
         return out
 
 
+class PartialTables:
+    """Full-height partial-product tables of the "reduce_scatter" schedule, in CUDA symmetric memory: every rank writes
+    A[:, cols_r] @ X[cols_r] into its own copy, one signal-pad barrier, then each rank reads the rows it owns of the SUM over the
+    copies through the multicast address (mmssl_reduce_rows_epilogue: multimem.ld_reduce + the SpMM epilogue).  Two tables per
+    width are used alternately: a table is rewritten only two exchanges later, after a barrier every rank can only have
+    reached once it had read the older contents.  Created lazily, in the (identical) order the ranks first need them."""
+
+    def __init__(self, part: RowPartition, rank: int, device, group=None):
+        self.part, self.rank, self.device, self.group = part, rank, device, group
+        self.tabs: Dict[int, list] = {}
+        self.turn: Dict[int, int] = {}
+
+    def next(self, width: int):
+        import torch.distributed._symmetric_memory as symm
+        if width not in self.tabs:
+            g = self.group if self.group is not None else dist.group.WORLD
+            pair = []
+            for _ in range(2):
+                t = symm.empty(self.part.world * self.part.block, width, dtype=torch.float32, device=self.device)
+                t.zero_()
+                h = symm.rendezvous(t, g.group_name)
+                mc = int(h.multicast_ptr)
+                if mc == 0:
+                    raise RuntimeError("NVSwitch multicast is not available for symmetric memory on this system")
+                pair.append((t, h, mc))
+            torch.cuda.synchronize(self.device)
+            pair[0][1].barrier()
+            self.tabs[width], self.turn[width] = pair, 0
+        t = self.tabs[width][self.turn[width]]
+        self.turn[width] ^= 1
+        return t
+
+
+def reduce_rows_epilogue(srcs, n_rows: int, d: int, ys, *, multicast: bool, epilogue=0, alpha=1.0, cs=None, ysaved=None, ss=None,
+                         s_mode=0, sbases=None):
+    """mmssl_reduce_rows_epilogue: srcs[r] = raw address (multicast) or tensor (reduced rows) of the rank's rows, right-hand side r."""
+    import ctypes as C
+    from ._lib import SpmmRhs
+    lib = _lib.load(require_device=True)
+    nrhs = len(ys)
+    rhs = (SpmmRhs * nrhs)()
+    ld_ = lambda t: 0 if t is None else int(t.stride(0))
+    for r in range(nrhs):
+        c = cs[r] if cs is not None else None
+        yv = ysaved[r] if ysaved is not None else None
+        sr = ss[r] if ss is not None else None
+        sb = sbases[r] if sbases is not None else None
+        src, lds_ = srcs[r]
+        rhs[r] = SpmmRhs(C.c_void_p(int(src)), int(lds_), ptr(ys[r]), ld_(ys[r]), ptr(c), ld_(c), ptr(yv), ld_(yv), ptr(sr), ld_(sr),
+                         ptr(sb), ld_(sb))
+    _lib.check(lib.mmssl_reduce_rows_epilogue(n_rows, d, nrhs, rhs, epilogue, float(alpha), s_mode, 1 if multicast else 0, stream()))
+    return list(ys)
+
+
 class RowShardedHotStep:
     """One rank of the row-sharded hot step.  ``params``: the rank's padded row blocks of the two embedding tables
     (``RowPartition.local``) and full copies of the five small parameters; ``feats``: FeatureStores of the rank's item rows;
@@ -163,19 +242,29 @@ class RowShardedHotStep:
 
     def __init__(self, params: Dict[str, torch.Tensor], feats: Sequence[FeatureStore], graphs: Sequence[RowBlockGraph],
                  cfg: HotStepConfig, batch: int, part_u: RowPartition, part_i: RowPartition, rank: int, group=None,
-                 optimizer_step: bool = True, exchange: str = "nccl"):
+                 optimizer_step: bool = True, exchange: str = "nccl", schedule: str = "reduce_scatter"):
         self.cfg, self.batch, self.pu, self.pi, self.rank, self.group = cfg, batch, part_u, part_i, rank, group
         self.P = {k: params[k] for k in LIVE}
         self.feats, self.graphs = tuple(feats), tuple(graphs)
         self.engine = Engine(cfg.embed_size, cfg.n_layers, cfg.head_num, cfg.id_cat_rate, cfg.model_cat_rate, cfg.proj_impl)
         self.engine.two_streams = False                     # the collectives order the work on one stream
         self.engine.exchange = self._exchange
+        # schedule of the products whose dense operand lives in the user space (A_iu @ u, A_ui^T @ du, ...):
+        #   "allgather"      all-gather the user-sized operand, multiply the rank's rows (round 1)
+        #   "reduce_scatter" multiply the rank's COLUMN block, reduce-scatter the item-sized result (only the smaller, item-side
+        #                    table ever crosses NVLink: syn1m 0.1 GB instead of 0.5 GB per exchange)
+        if schedule not in ("allgather", "reduce_scatter"):
+            raise ValueError("schedule must be 'allgather' or 'reduce_scatter'")
+        self.schedule = schedule if part_u.world > 1 and all(g.fwd_part is not None for g in graphs) else "allgather"
+        self.engine.sharded_spmm = self._sharded_spmm
+        self.partials = None
         # "nccl": all_gather_into_tensor (gloo in the CPU tests); "multicast": MulticastExchange (symmetric memory, no NCCL)
         self.mc = MulticastExchange(part_u, part_i, rank, self.P[P_EU].device, group) if exchange == "multicast" and part_u.world > 1 else None
         if exchange not in ("nccl", "multicast"):
             raise ValueError("exchange must be 'nccl' or 'multicast'")
         self.optimizer_step = optimizer_step
         self.n_gathers, self.gathered_bytes = 0, 0
+        self.n_reduce_scatters = 0
         dev = self.P[P_EU].device
         d, B = cfg.embed_size, batch
         f = dict(dtype=torch.float32, device=dev)
@@ -236,6 +325,43 @@ class RowShardedHotStep:
             self.gathered_bytes += x.numel() * x.element_size() * (part.world - 1)
             out.append(self.mc.gather(x.contiguous(), space) if self.mc is not None else all_gather_rows(x, part, self.group))
         return out
+
+    def _sharded_spmm(self, g, which: str, xs, space: str, ys=None, **kw):
+        """Engine hook: Y = epi(op(g) @ X) with X a row block of a table that lives in `space`."""
+        if space == "i" or self.schedule == "allgather":
+            return ops.spmm(getattr(g, which), self._exchange(list(xs), space), ys, **kw)
+        # the operand is user-sized: partial product over the rank's columns into full-height item-space tables, then the
+        # rank's rows of the sum over ranks + the epilogue the SpMM would have applied
+        op = g.fwd_part if which == "fwd" else g.bwd_part
+        d = xs[0].shape[1]
+        nrhs = len(xs)
+        part = self.pi
+        lo = self.rank * part.block
+        if ys is None:
+            ys = [torch.empty(part.block, d, dtype=torch.float32, device=xs[0].device) for _ in range(nrhs)]
+        self.n_reduce_scatters += 1
+        self.gathered_bytes += part.block * d * nrhs * 4 * (part.world - 1)
+        if self.mc is not None:
+            if self.partials is None:
+                self.partials = PartialTables(part, self.rank, xs[0].device, self.group)
+            tab, h, mc = self.partials.next(nrhs * d)
+            outs = [tab[:, r * d:(r + 1) * d] for r in range(nrhs)]
+            ops.spmm(op, [x if x.stride(1) == 1 else x.contiguous() for x in xs], outs)
+            h.barrier()                                             # every rank's partial table is complete
+            srcs = [(mc + (lo * nrhs * d + r * d) * 4, nrhs * d) for r in range(nrhs)]
+            return reduce_rows_epilogue(srcs, part.block, d, ys, multicast=True, **kw)
+        full = torch.empty(part.world * part.block, nrhs * d, dtype=torch.float32, device=xs[0].device)
+        outs = [full[:, r * d:(r + 1) * d] for r in range(nrhs)]
+        ops.spmm(op, [x if x.stride(1) == 1 else x.contiguous() for x in xs], outs)
+        if dist.get_backend(self.group) == "gloo":                  # CPU tests: gloo has no reduce-scatter
+            dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)
+            mine = full[lo:lo + part.block]
+        else:
+            mine = torch.empty(part.block, nrhs * d, dtype=torch.float32, device=xs[0].device)
+            dist.reduce_scatter_tensor(mine, full, op=dist.ReduceOp.SUM, group=self.group)
+        srcs = [(mine[:, r * d:(r + 1) * d].data_ptr(), nrhs * d) for r in range(nrhs)]
+        self._keep = mine
+        return reduce_rows_epilogue(srcs, part.block, d, ys, multicast=False, **kw)
 
     def _masks(self):
         if not self.training or self.cfg.drop_rate <= 0:
@@ -382,6 +508,7 @@ def shard_problem_from_disk(root: str, P_full: Dict[str, torch.Tensor], rank: in
         f[:rows.shape[0]] = torch.from_numpy(np.ascontiguousarray(rows))
         feats.append(FeatureStore(f.to(device), keep_fp32=True))
     nnz = sh.meta["operands"]["ui"]["nnz"]
-    g_ui = RowBlockGraph.from_csr_blocks(sh.operand("ui"), sh.operand("uiT"), nnz, device)
-    g_iu = RowBlockGraph.from_csr_blocks(sh.operand("iu"), sh.operand("iuT"), nnz, device)
+    hu, hi_ = pu.world * pu.block, pi.world * pi.block
+    g_ui = RowBlockGraph.from_csr_blocks(sh.operand("ui"), sh.operand("uiT"), nnz, device, heights=(hu, hi_))
+    g_iu = RowBlockGraph.from_csr_blocks(sh.operand("iu"), sh.operand("iuT"), nnz, device, heights=(hi_, hu))
     return P, tuple(feats), (g_ui, g_iu, g_ui, g_iu, g_ui, g_iu), pu, pi

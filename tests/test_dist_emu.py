@@ -45,7 +45,7 @@ def _problem(modal):
     return U, I, d, B, csr_norm(r), csr_norm(r.T.tocsr()), P, feats, masks, (users, pos, neg), mods
 
 
-def _worker(rank, port, modal, ret):
+def _worker(rank, port, modal, schedule, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=WORLD)
     try:
@@ -76,7 +76,7 @@ def _worker(rank, port, modal, ret):
         if mods is not None:
             for j, (m_ui, m_iu) in zip((2, 4), mods):
                 gl[j], gl[j + 1] = RowBlockGraph.from_scipy(m_ui, pu, pi, rank, "cpu"), RowBlockGraph.from_scipy(m_iu, pi, pu, rank, "cpu")
-        sh = RowShardedHotStep(Pl, fl, gl, cfg, B, pu, pi, rank)
+        sh = RowShardedHotStep(Pl, fl, gl, cfg, B, pu, pi, rank, schedule=schedule)
         sh.masks = tuple(pi.local(m, rank) for m in masks)
         sh.set_indices(users, pos, neg)
         errs = {}
@@ -102,23 +102,26 @@ def _worker(rank, port, modal, ret):
             else:
                 errs["p/" + k] = rel_err(sh.P[k], hs.P[k])
         errs["gathers_per_step"] = sh.n_gathers / 2
+        errs["reduce_scatters_per_step"] = sh.n_reduce_scatters / 2
         ret[rank] = errs
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("modal", ["alias", "random"])
-def test_row_sharded_hot_step_matches_single_process(modal):
+@pytest.mark.parametrize("modal,schedule", [("alias", "reduce_scatter"), ("random", "reduce_scatter"), ("alias", "allgather"), ("random", "allgather")])
+def test_row_sharded_hot_step_matches_single_process(modal, schedule):
+    """schedule 'allgather': every product all-gathers its dense operand; 'reduce_scatter': products whose operand is user-sized
+    multiply the rank's column block and reduce-scatter the item-sized result (mmssl_reduce_rows_epilogue applies the epilogue)."""
     port = _free_port()
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(port, modal, ret), nprocs=WORLD, join=True)
+    mp.spawn(_worker, args=(port, modal, schedule, ret), nprocs=WORLD, join=True)
     assert len(ret) == WORLD
     for rank in range(WORLD):
         e = dict(ret[rank])
-        gathers = e.pop("gathers_per_step")
+        gathers, rs = e.pop("gathers_per_step"), e.pop("reduce_scatters_per_step")
         bad = {k: v for k, v in e.items() if not v < 2e-5}
         assert not bad, (rank, bad)
-        assert gathers > 0
+        assert gathers > 0 and (rs > 0) == (schedule == "reduce_scatter")
 
 
 def _disk_worker(rank, port, shard_dir, ret):

@@ -20,7 +20,8 @@ from mmssl_b200.rowshard_step import RowShardedHotStep, shard_problem  # noqa: E
 from mmssl_b200.synthetic import TripleSampler  # noqa: E402
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
-name = args[0] if args and args[0] not in ("check", "mc", "graph") else "tiktok"
+name = args[0] if args and args[0] not in ("check", "mc", "graph", "allgather") else "tiktok"
+schedule = "allgather" if "allgather" in args else "reduce_scatter"
 check = "check" in args
 steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 20
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -33,13 +34,13 @@ ds, P_cpu, feats_cpu, _, _ = bench.build_problem(name, 2022, None)           # t
 cfg = HotStepConfig(embed_size=ds.embed_size, n_layers=ds.n_layers, batch_size=B)
 Pl, fl, gl, pu, pi = shard_problem(P_cpu, feats_cpu, ds.ui_norm, ds.iu_norm, rank, world, dev)
 mode = "multicast" if "mc" in args and world > 1 else "nccl"
-sh = RowShardedHotStep(Pl, fl, gl, cfg, B, pu, pi, rank, exchange=mode)
+sh = RowShardedHotStep(Pl, fl, gl, cfg, B, pu, pi, rank, exchange=mode, schedule=schedule)
 smp = TripleSampler(ds.train, seed=2022)
 batches = [tuple(torch.from_numpy(x).to(dev) for x in smp.sample(B)) for _ in range(4)]
 g = torch.Generator().manual_seed(7)
 full_masks = tuple(((torch.rand(ds.n_items, ds.embed_size, generator=g) >= cfg.drop_rate) / (1 - cfg.drop_rate)).float() for _ in range(2))
 sh.masks = tuple(pi.local(m, rank).to(dev) for m in full_masks)
-res = {"config": name, "n_gpus": world, "scheme": "row-sharded whole hot step", "exchange": ("publish kernel over NVSwitch multicast / peer stores + signal-pad barrier (no NCCL)" if mode == "multicast" else "NCCL all-gather per SpMM operand"), "batch": B}
+res = {"config": name, "n_gpus": world, "scheme": "row-sharded whole hot step", "schedule": sh.schedule, "exchange": ("publish kernel over NVSwitch multicast / peer stores + signal-pad barrier (no NCCL)" if mode == "multicast" else "NCCL all-gather per SpMM operand"), "batch": B}
 
 if check:
     _, Pd, feats, graphs, _ = bench.build_problem(name, 2022, dev)
@@ -70,7 +71,7 @@ for s in range(3):
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
-sh.n_gathers = sh.gathered_bytes = 0
+sh.n_gathers = sh.gathered_bytes = sh.n_reduce_scatters = 0
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
 for s in range(steps):
@@ -80,7 +81,7 @@ torch.cuda.synchronize()
 ms = torch.tensor([a.elapsed_time(b) / steps], device=dev)
 if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-res.update(ms_per_step=round(float(ms), 4), triples_per_s=round(B / float(ms) * 1e3, 1), gathers_per_step=sh.n_gathers // steps,
+res.update(ms_per_step=round(float(ms), 4), triples_per_s=round(B / float(ms) * 1e3, 1), gathers_per_step=sh.n_gathers // steps, reduce_scatters_per_step=sh.n_reduce_scatters // steps,
            gathered_MB_per_rank_per_step=round(sh.gathered_bytes / steps / 1e6, 2), graph_capture=use_graph)
 if rank == 0:
     print(json.dumps(res))
