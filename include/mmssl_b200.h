@@ -362,6 +362,9 @@ int mmssl_split_bf16(const float* x, int64_t ldx, int64_t rows, int64_t cols, ui
 /* transposed split: hi/lo [cols][ldo] from x [rows][cols] (optionally multiplied by mask [rows][cols]) */
 int mmssl_split_bf16_t(const float* x, int64_t ldx, const float* mask, int64_t ldm, int64_t rows, int64_t cols,
                        uint16_t* hi, uint16_t* lo, int64_t ldo, void* stream);
+/* the same + colsum[c] = sum_r (x * mask)[r][c]   (db of the projection's backward, Models.py:173-174, from the tile pass) */
+int mmssl_split_bf16_t_colsum(const float* x, int64_t ldx, const float* mask, int64_t ldm, int64_t rows, int64_t cols,
+                              uint16_t* hi, uint16_t* lo, int64_t ldo, float* colsum, void* stream);
 int64_t mmssl_gemm_bf16x3_workspace_floats(int64_t m, int64_t n, int64_t k, int* split_k_out);
 /* partial[s][m][n] (fp32) = sum over the s-th K slice of (Ahi+Alo)[m,k] * (Bhi+Blo)[n,k]  (lo*lo dropped).
  * A: [m][lda] bf16 K-major, B: [n][ldb] bf16 K-major; n in {64,128,256}. */

@@ -121,6 +121,7 @@ _SIGS = {
     "mmssl_degree_values": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "mmssl_split_bf16": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "mmssl_split_bf16_t": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "mmssl_split_bf16_t_colsum": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "mmssl_gemm_bf16x3_workspace_floats": (c_i64, [c_i64, c_i64, c_i64, C.POINTER(c_i32)]),
     "mmssl_gemm_bf16x3": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp]),
     "mmssl_gemm_bf16x3_wide": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_i32, c_vp, c_i64, c_vp]),
@@ -139,7 +140,7 @@ KERNELS_PER_CALL = {
     "mmssl_dwcat_reduce": 1, "mmssl_combine_fwd": 1, "mmssl_combine_bwd": 1, "mmssl_softmax_bwd": 1,
     "mmssl_axpby": 1, "mmssl_mul_mask": 1, "mmssl_sumsq": 1, "mmssl_bpr": 1, "mmssl_infonce_prepare": 1,
     "mmssl_infonce_stats": 2, "mmssl_infonce_grad": 1, "mmssl_infonce_scatter": 1, "mmssl_loss_assemble": 1,
-    "mmssl_step_tick": 1, "mmssl_dp_fused_adamw": 1, "mmssl_sampler_init": 1, "mmssl_sample_triples": 1, "mmssl_adamw": 1, "mmssl_split_bf16": 1, "mmssl_split_bf16_t": 1, "mmssl_gemm_bf16x3": 1, "mmssl_gemm_bf16x3_wide": 1,
+    "mmssl_step_tick": 1, "mmssl_dp_fused_adamw": 1, "mmssl_sampler_init": 1, "mmssl_sample_triples": 1, "mmssl_adamw": 1, "mmssl_split_bf16": 1, "mmssl_split_bf16_t": 1, "mmssl_split_bf16_t_colsum": 1, "mmssl_gemm_bf16x3": 1, "mmssl_gemm_bf16x3_wide": 1,
     "mmssl_proj_epilogue": 1, "mmssl_wgrad_epilogue": 1, "mmssl_colsum": 1,
     "mmssl_eval_rank": 1, "mmssl_eval_reduce": 1,
     "mmssl_gan_bn_fwd": 1, "mmssl_gan_bn_bwd": 1, "mmssl_gan_gp_rev_bn": 1, "mmssl_gan_bn_fwd_rev": 1, "mmssl_gan_colsum": 1,

@@ -29,10 +29,12 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int64_t ldx, int6
     lo[i] = l;
 }
 
-// hi/lo [cols][ldo] <- (x * mask)[rows][cols] transposed, through a 32x32 smem tile
+// hi/lo [cols][ldo] <- (x * mask)[rows][cols] transposed, through a 32x32 smem tile.  colsum != NULL: additionally
+// colsum[c] += sum over the tile's rows of (x * mask)[r][c]  (the bias gradient db = colsum(dX * mask) of the projection's
+// backward rides along: the tile is in shared memory anyway; one float reduction per column per 32-row tile).
 __global__ void split_bf16_t_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ mask,
                                     int64_t ldm, int64_t rows, int64_t cols, uint16_t* __restrict__ hi,
-                                    uint16_t* __restrict__ lo, int64_t ldo) {
+                                    uint16_t* __restrict__ lo, int64_t ldo, float* __restrict__ colsum) {
     __shared__ float tile[32][33];
     const int64_t r0 = blockIdx.x * 32ll, c0 = blockIdx.y * 32ll;
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {
@@ -45,6 +47,12 @@ __global__ void split_bf16_t_kernel(const float* __restrict__ x, int64_t ldx, co
         tile[k][threadIdx.x] = v;
     }
     __syncthreads();
+    if (colsum != nullptr && threadIdx.y == 0 && c0 + threadIdx.x < cols) {
+        float sacc = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) sacc += tile[k][threadIdx.x];      // rows beyond `rows` hold zeros
+        atomicAdd(colsum + c0 + threadIdx.x, sacc);
+    }
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {
         const int64_t c = c0 + k, r = r0 + threadIdx.x;   // output row = input column
         if (c < cols && r < ldo) {
@@ -128,15 +136,26 @@ extern "C" int mmssl_split_bf16(const float* x, int64_t ldx, int64_t rows, int64
     return 0;
 }
 
-extern "C" int mmssl_split_bf16_t(const float* x, int64_t ldx, const float* mask, int64_t ldm, int64_t rows,
-                                  int64_t cols, uint16_t* hi, uint16_t* lo, int64_t ldo, void* stream_) {
-    cudaStream_t st = (cudaStream_t)stream_;
+static int split_t_launch(const float* x, int64_t ldx, const float* mask, int64_t ldm, int64_t rows, int64_t cols, uint16_t* hi,
+                          uint16_t* lo, int64_t ldo, float* colsum, cudaStream_t st) {
     MMSSL_REQUIRE(ldo >= rows, "ldo < rows");
+    if (colsum != nullptr) MMSSL_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * cols, st));
     if (cols == 0 || ldo == 0) return 0;
     dim3 grid((unsigned)((ldo + 31) / 32), (unsigned)((cols + 31) / 32));
-    split_bf16_t_kernel<<<grid, dim3(32, 8), 0, st>>>(x, ldx, mask, ldm, rows, cols, hi, lo, ldo);
+    split_bf16_t_kernel<<<grid, dim3(32, 8), 0, st>>>(x, ldx, mask, ldm, rows, cols, hi, lo, ldo, colsum);
     MMSSL_LAUNCH_OK();
     return 0;
+}
+
+extern "C" int mmssl_split_bf16_t(const float* x, int64_t ldx, const float* mask, int64_t ldm, int64_t rows,
+                                  int64_t cols, uint16_t* hi, uint16_t* lo, int64_t ldo, void* stream_) {
+    return split_t_launch(x, ldx, mask, ldm, rows, cols, hi, lo, ldo, nullptr, (cudaStream_t)stream_);
+}
+
+extern "C" int mmssl_split_bf16_t_colsum(const float* x, int64_t ldx, const float* mask, int64_t ldm, int64_t rows,
+                                         int64_t cols, uint16_t* hi, uint16_t* lo, int64_t ldo, float* colsum, void* stream_) {
+    MMSSL_REQUIRE(colsum != nullptr, "colsum output missing");
+    return split_t_launch(x, ldx, mask, ldm, rows, cols, hi, lo, ldo, colsum, (cudaStream_t)stream_);
 }
 
 extern "C" int mmssl_proj_epilogue(const float* partial, int split_k, int64_t m, int64_t n, const float* bias,

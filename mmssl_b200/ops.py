@@ -330,8 +330,9 @@ def split_bf16(x, ldo=None):
     return hi, lo
 
 
-def split_bf16_t(x, mask=None, ldo=None, out=None):
-    """fp32 [rows, cols] (optionally * mask) -> transposed (hi, lo) bf16 [cols, ldo], zero padded."""
+def split_bf16_t(x, mask=None, ldo=None, out=None, colsum=None):
+    """fp32 [rows, cols] (optionally * mask) -> transposed (hi, lo) bf16 [cols, ldo], zero padded.
+    colsum: optional fp32 [cols] that receives the column sums of (x * mask) from the same pass."""
     lib = _lib_()
     rows, cols = x.shape
     if ldo is None:
@@ -341,7 +342,12 @@ def split_bf16_t(x, mask=None, ldo=None, out=None):
         lo = torch.empty(cols, ldo, dtype=torch.bfloat16, device=x.device)
     else:
         hi, lo = out
-    _lib.check(lib.mmssl_split_bf16_t(ptr(x), x.stride(0), ptr(mask), _ld(mask), rows, cols, ptr(hi), ptr(lo), ldo, stream()))
+    if colsum is not None:
+        assert colsum.dtype == torch.float32 and colsum.numel() == cols and colsum.is_contiguous()
+        _lib.check(lib.mmssl_split_bf16_t_colsum(ptr(x), x.stride(0), ptr(mask), _ld(mask), rows, cols, ptr(hi), ptr(lo), ldo,
+                                                 ptr(colsum), stream()))
+    else:
+        _lib.check(lib.mmssl_split_bf16_t(ptr(x), x.stride(0), ptr(mask), _ld(mask), rows, cols, ptr(hi), ptr(lo), ldo, stream()))
     return hi, lo
 
 
