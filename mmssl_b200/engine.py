@@ -102,7 +102,7 @@ class Engine:
         key = (dev.type, dev.index, "pair")
         st = self._side.get(key)
         if st is None:
-            st = torch.cuda.Stream(device=dev)
+            st = torch.cuda.Stream(device=dev, priority=-1)      # twin of the critical id / GCN chain: ahead of the projection branch
             self._side[key] = st
         main = torch.cuda.current_stream(dev)
         st.wait_stream(main)
@@ -112,13 +112,13 @@ class Engine:
         main.wait_stream(st)
         return ra, rb
 
-    def _fork2(self, dev, fn_a, fn_b):
+    def _fork2(self, dev, fn_a, fn_b, name: str = "fork2"):
         """fn_a on the current stream, fn_b on a third stream (forked from / joined into the current one); serial when
         `two_streams` is off.  Used for the image | text halves of the projection, which are independent."""
         if not self.two_streams:
             fn_a(); fn_b()
             return
-        key = (dev.type, dev.index, "fork2")
+        key = (dev.type, dev.index, name)
         st = self._side.get(key)
         if st is None:
             st = torch.cuda.Stream(device=dev)
@@ -341,23 +341,24 @@ class Engine:
         else:
             keep = modal_backward()
         # ---- GCN backward.  every u_k, i_k receives inv * g_uf / inv * g_if from the layer mean.
-        if K >= 1:
+        # d loss / d u_0 = inv * g_uf (u_0 only feeds the layer mean): needed only after the chain -> issued first, on the pair stream
+        g_eu = slot(P_EU, P[P_EU])
+        g_ei = slot(P_EI, P[P_EI])
+
+        def chain():
+            if K == 0:
+                return ops.axpby(g_if, inv, 0.0, g_ei)
             t = ops.softmax_bwd(st.i_last, g_if, inv, self._new(I, d, dev=dev))
             for k in range(K - 1, -1, -1):
                 last = k == K - 1
                 tu = self._spmm(g_iu, "bwd", [t], "i", cs=[g_uf], alpha=inv,
-                              epilogue=ops.EPI_SOFTMAX_BWD if last else ops.EPI_NONE,
-                              ysaved=[st.u_last] if last else None)[0]
-                t = self._spmm(g_ui, "bwd", [tu], "u", cs=[g_if], alpha=inv)[0]
-            g_i0 = t                                            # d loss / d i_0
-        else:
-            g_i0 = ops.axpby(g_if, inv, 0.0, self._new(I, d, dev=dev))
-        # d loss / d u_0 = inv * g_uf (u_0 only feeds the layer mean)
-        g_eu = slot(P_EU, P[P_EU])
-        g_ei = slot(P_EI, P[P_EI])
-        ops.axpby(g_uf, inv, 0.0, g_eu)
-        if g_i0.data_ptr() != g_ei.data_ptr():
-            ops.axpby(g_i0, 1.0, 0.0, g_ei)
+                                epilogue=ops.EPI_SOFTMAX_BWD if last else ops.EPI_NONE,
+                                ysaved=[st.u_last] if last else None)[0]
+                # the last product of the chain IS d loss / d i_0: it lands in the item table's gradient slot
+                t = self._spmm(g_ui, "bwd", [tu], "u", [g_ei] if k == 0 else None, cs=[g_if], alpha=inv)[0]
+            return t
+
+        self._pair(dev, chain, lambda: ops.axpby(g_uf, inv, 0.0, g_eu))
         # ---- id fusion backward (Models.py:188-197)
         uvid, utid, ivid, itid = st.id_out
         g_wcat = slot(P_WCAT, P[P_WCAT])
@@ -423,14 +424,17 @@ class Engine:
                 if g is not None and gr.nnz > 0:
                     self._spmm(gr, "bwd", [g], space, [g_e], cs=[g_e], alpha=1.0)
 
-        # Uvid = A_vui E_i, Utid = A_tui E_i -> gradient flows to E_i; Ivid/Itid -> E_u.  The head reduction
-        # of dWcat does not feed them, so it rides along on the pair stream.
-        def tail_b():
-            id_prop_bwd(g_viu, g_tiu, gt_ivid, gt_itid, g_eu, st.fused and ivid is itid, "i")
+        # Uvid = A_vui E_i, Utid = A_tui E_i -> gradient flows to E_i; Ivid/Itid -> E_u.  The head reduction of dWcat feeds
+        # nothing else of the step: it runs beside the two propagations on a third stream.
+        def props():
+            self._pair(dev, lambda: id_prop_bwd(g_vui, g_tui, gt_uvid, gt_utid, g_ei, st.fused and uvid is utid, "u"),
+                       lambda: id_prop_bwd(g_viu, g_tiu, gt_ivid, gt_itid, g_eu, st.fused and ivid is itid, "i"))
+
+        def head_reduce():
             if dwcat_args is not None:
                 ops.dwcat_reduce(dwcat_args[0], dwcat_args[1], d, self.H, g_wcat)
 
-        self._pair(dev, lambda: id_prop_bwd(g_vui, g_tui, gt_uvid, gt_utid, g_ei, st.fused and uvid is utid, "u"), tail_b)
+        self._fork2(dev, props, head_reduce, name="fork3")
         if side is not main:
             main.wait_stream(side)
         return res

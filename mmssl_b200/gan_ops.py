@@ -37,8 +37,13 @@ def _new(*shape, like):
 # ---- bf16 hi/lo operand splits of the Discriminator's weights are reused by every product of an iteration (W1 alone enters 6 of
 # them, 100 MB of traffic per split at Baby); activations are split per call.  Only tensors registered as weights are cached;
 # `adam` (the only writer of the weights on this path) drops the cache, `weights_changed()` does it for any other writer.
+# The split of a registered weight always lands in the SAME pair of buffers (`_split_bufs`): inside a CUDA graph the iteration's
+# first use of W1 reads what the previous replay's post-Adam split left there -- a Python-side cache that handed out fresh
+# buffers per split made the captured graph read the warm-up iteration's buffers for ever (round 2, first hardware run of the
+# captured full step on this route: gradient penalty 1.5e-3 off).
 _weights = {}            # data_ptr -> weak reference to the registered tensor OBJECT (an address alone could be reused)
 _split_cache = {}
+_split_bufs = {}
 
 
 def register_weights(tensors) -> None:
@@ -50,6 +55,8 @@ def weights_changed() -> None:
     _split_cache.clear()
     for k in [k for k, r in _weights.items() if r() is None]:
         del _weights[k]
+        for b in [b for b in _split_bufs if b[0] == k]:
+            del _split_bufs[b]
 
 
 def _split(t, transposed: bool):
@@ -59,7 +66,9 @@ def _split(t, transposed: bool):
     key = (t.data_ptr(), tuple(t.shape), transposed, t._version)
     hit = _split_cache.get(key)
     if hit is None:
-        hit = ops.split_bf16_t(t) if transposed else ops.split_bf16(t)
+        bufs = _split_bufs.get(key[:3])
+        hit = ops.split_bf16_t(t, out=bufs) if transposed else ops.split_bf16(t, out=bufs)
+        _split_bufs[key[:3]] = hit
         _split_cache[key] = hit
     return hit
 

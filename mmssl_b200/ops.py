@@ -318,14 +318,17 @@ def wgrad_epilogue(partial, split_k, m, n, dw, accumulate=False):
     return dw
 
 
-def split_bf16(x, ldo=None):
+def split_bf16(x, ldo=None, out=None):
     """fp32 [rows, cols] -> (hi, lo) bf16 [rows, ldo] with zero padding (ldo % 8 == 0 for TMA strides)."""
     lib = _lib_()
     rows, cols = x.shape
     if ldo is None:
         ldo = (cols + 7) // 8 * 8
-    hi = torch.empty(rows, ldo, dtype=torch.bfloat16, device=x.device)
-    lo = torch.empty(rows, ldo, dtype=torch.bfloat16, device=x.device)
+    if out is None:
+        hi = torch.empty(rows, ldo, dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty(rows, ldo, dtype=torch.bfloat16, device=x.device)
+    else:
+        hi, lo = out
     _lib.check(lib.mmssl_split_bf16(ptr(x), x.stride(0), rows, cols, ptr(hi), ptr(lo), ldo, stream()))
     return hi, lo
 

@@ -169,8 +169,10 @@ def test_spmm_epilogues(d):
     s = torch.empty(300, d, device="cuda")
     y = ops.spmm(g.fwd, [x], cs=[c], alpha=0.25, epilogue=ops.EPI_SOFTMAX, ss=[s], s_mode=2, sbases=[sb])[0]
     want = torch.softmax(v, dim=-1)
-    assert rel_err(y, want) < 5e-6
-    assert rel_err(s, sb.double().cpu() + want) < 5e-6
+    # row 0 is a heavy row (3000 non-zeros: vector reductions in arrival order); its fp32 sum moves by ~1e-6 of its magnitude
+    # (~50) from run to run and the softmax turns that into up to ~1e-5 (seen on hardware: 5e-6 .. 8e-6) -- hence 3e-5 here
+    assert rel_err(y, want) < 3e-5
+    assert rel_err(s, sb.double().cpu() + want) < 3e-5
     ops.spmm(g.fwd, [x], cs=[c], alpha=0.25, epilogue=ops.EPI_NONE, ss=[s], s_mode=1)
     assert rel_err(s, sb.double().cpu() + want + v) < 5e-6
     # softmax backward epilogue
