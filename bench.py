@@ -180,11 +180,16 @@ class HotStepTrainer:
         # the graph replay.  graph_comm=True captures them inside the graph; that variant deadlocked on the
         # box in round 1 (NCCL capture) and is kept only as an experiment.
         self.graph_comm = graph_comm or world == 1
+        self.dp_in_graph = self.dp_opt is not None and os.environ.get("MMSSL_DP_IN_GRAPH", "1") == "1"
         self.hs = HotStep(P, feats, graphs, cfg, batch=batch, optimizer_step=self.graph_comm, sampler=sampler)
         self.pin_idx = torch.empty(3, batch, dtype=torch.int64).pin_memory()
         self.pin_out = torch.empty(5, dtype=torch.float32).pin_memory()
         if self.dp_opt is not None:
             self.hs.grads.update(self.dp_opt.grads)
+            if self.dp_in_graph:      # barriers + the multimem optimiser kernel are part of the captured step
+                from mmssl_b200 import ops as _ops
+                hs, opt = self.hs, self.dp_opt
+                self.hs.grad_sync = lambda: (_ops.step_tick(hs.step_dev), opt.step_captured(hs.step_dev))
         elif world > 1:
             from mmssl_b200.parallel import GradBucket
             self.bucket = GradBucket(self.hs.grads)      # one flat all-reduce bucket for all live parameters
@@ -194,6 +199,8 @@ class HotStepTrainer:
         self.hs.capture(warmup=2)
 
     def _finish_step(self):
+        if self.dp_opt is not None and self.dp_in_graph:
+            return
         if self.dp_opt is not None:
             from mmssl_b200 import ops
             ops.step_tick(self.hs.step_dev)      # the device sampler's counter
@@ -484,10 +491,10 @@ def dp_parity_vs_1gpu(trainer, P0, feats, graphs, cfg, my_batch, rank, world, de
         hs.P[k].copy_(P0[k])
     hs.masks = _fixed_masks(I, d, cfg.drop_rate, 1000 + rank, dev)
     hs.idx.copy_(my_batch)
-    saved = hs.optimizer_step
-    hs.optimizer_step = False
+    saved, saved_sync = hs.optimizer_step, hs.grad_sync
+    hs.optimizer_step, hs.grad_sync = False, None         # gradients only: the reduction is done explicitly below
     out5 = hs.run().clone()
-    hs.optimizer_step = saved
+    hs.optimizer_step, hs.grad_sync = saved, saved_sync
     hs.masks = None
     torch.cuda.synchronize()
     dist.barrier()
@@ -717,7 +724,8 @@ def main():
     P0 = {k: v.clone() for k, v in P.items()} if world > 1 else None
     trainer = HotStepTrainer(P, feats, graphs, cfg, BATCH, world=world, graph_comm=a.graph_comm, dp=a.dp)
     if world > 1 and trainer.dp_mode == "fused":
-        config["parallelism"] = (f"dp{world} (replicated graph; optimiser step = one multimem kernel after the graph replay: "
+        where = "inside the step's CUDA graph" if trainer.dp_in_graph else "after the graph replay"
+        config["parallelism"] = (f"dp{world} (replicated graph; optimiser step = two signal-pad barriers + one multimem kernel {where}: "
                                  f"switch-reduced gradient slice, AdamW on 1/{world} of the parameters, multicast store of the new slice)")
     smp = TripleSampler(ds.train, seed=a.seed + 17 * rank)
     n_batches = a.steps + a.warmup
@@ -726,10 +734,10 @@ def main():
 
     # launches per step (our kernels only): count one eager step that leaves the optimiser state alone
     c0 = _lib.launch_count
-    saved = trainer.hs.optimizer_step
-    trainer.hs.optimizer_step = False
+    saved, saved_sync = trainer.hs.optimizer_step, trainer.hs.grad_sync
+    trainer.hs.optimizer_step, trainer.hs.grad_sync = False, None
     trainer.hs.run()
-    trainer.hs.optimizer_step = saved
+    trainer.hs.optimizer_step, trainer.hs.grad_sync = saved, saved_sync
     launches_per_step = (_lib.launch_count - c0) + 2     # + step_tick + adamw
 
     def barrier():
@@ -745,33 +753,47 @@ def main():
         trainer.step_device(dev_batches[w])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_seg = 5 if a.steps >= 10 else 1
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(n_seg - 1)]
+    seg = a.steps // n_seg
     barrier()
     e0.record()
     for s in range(a.steps):
         trainer.step_device(dev_batches[a.warmup + s])
+        if (s + 1) % seg == 0 and (s + 1) // seg <= n_seg - 1:
+            marks[(s + 1) // seg - 1].record()              # spread of the timed region (no synchronisation)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    pts = [e0] + marks + [e1]
+    seg_steps = [seg] * (n_seg - 1) + [a.steps - seg * (n_seg - 1)]
+    seg_ms = [pts[i].elapsed_time(pts[i + 1]) / seg_steps[i] for i in range(n_seg)]
 
     # ---------------- (B) end to end through the public API (pinned host -> device, loss read back)
     for w in range(min(3, a.warmup)):
         trainer.train_step(*host_batches[w])
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fmarks = [torch.cuda.Event(enable_timing=True) for _ in range(n_seg - 1)]
     f0.record()
     last_loss = 0.0
     for s in range(a.steps):
         last_loss = trainer.train_step(*host_batches[a.warmup + s])
+        if (s + 1) % seg == 0 and (s + 1) // seg <= n_seg - 1:
+            fmarks[(s + 1) // seg - 1].record()
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    fpts = [f0] + fmarks + [f1]
+    seg_ms_e2e = [fpts[i].elapsed_time(fpts[i + 1]) / seg_steps[i] for i in range(n_seg)]
     clk = clocks.stop() if rank == 0 else None
 
     parity = row_shard = None
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e], device=dev)
+        t = torch.tensor([ms_total, ms_e2e] + seg_ms + seg_ms_e2e, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_e2e = float(t[0]), float(t[1])
+        seg_ms, seg_ms_e2e = t[2:2 + n_seg].tolist(), t[2 + n_seg:].tolist()
         parity = dp_parity_vs_1gpu(trainer, P0, feats, graphs, cfg, dev_batches[0], rank, world, dev)
         if a.row_shard != "none":
             del trainer
@@ -801,6 +823,10 @@ def main():
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms_total / a.steps, 4), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "clocks": clk, "gpu_launches": launches_per_step * a.steps,
+                "ms_per_step_spread": {"segments": n_seg, "min": round(min(seg_ms), 4), "median": round(statistics.median(seg_ms), 4),
+                                       "max": round(max(seg_ms), 4), "e2e_min": round(min(seg_ms_e2e), 4),
+                                       "e2e_median": round(statistics.median(seg_ms_e2e), 4), "e2e_max": round(max(seg_ms_e2e), 4),
+                                       "note": "the timed region cut into equal consecutive segments (events, max over ranks per segment)"},
                 "e2e": {"value": round(total_triples / (ms_e2e * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": 3 * BATCH * 8,
                         "d2h_bytes_per_step": 5 * 4, "ms_per_step": round(ms_e2e / a.steps, 4), "last_loss": round(last_loss, 6)},
                 "roofline": roof, "roofline_spmm": roofs["spmm"], "roofline_projection": roofs["projection"],

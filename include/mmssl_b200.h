@@ -242,6 +242,10 @@ int mmssl_adamw(int n_tensors, float* const* p /*host array of device ptrs*/, co
 int mmssl_dp_fused_adamw(const float* p_local, float* p_mc, const float* g_mc, float* m, float* v, int64_t begin,
                          int64_t count, float inv_world, int step, float lr, float beta1, float beta2, float eps,
                          float weight_decay, void* stream);
+/* the same with the 1-based step number read from device memory (mmssl_step_tick): the launch is CUDA-graph capturable */
+int mmssl_dp_fused_adamw_dev(const float* p_local, float* p_mc, const float* g_mc, float* m, float* v, int64_t begin,
+                             int64_t count, float inv_world, const int32_t* step_dev, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, void* stream);
 
 /* ------------------------------------------------------------------ GPU triple sampler (SURVEY 8f "next" #1)
  * Semantics of Data.sample (utility/load_data.py:153-191): `batch` (<= 1024) distinct users with >= 1

@@ -69,8 +69,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamPack pk, const int
 __global__ void __launch_bounds__(256) dp_fused_adamw_kernel(const float* __restrict__ p_local, float* p_mc,
                                                              const float* g_mc, float* __restrict__ m,
                                                              float* __restrict__ v, int64_t begin, int64_t count4,
-                                                             float inv_world, int step, float lr, float b1, float b2,
-                                                             float eps, float wd) {
+                                                             float inv_world, int step_host, const int32_t* __restrict__ step_dev,
+                                                             float lr, float b1, float b2, float eps, float wd) {
+    // step_dev != NULL: the 1-based step number lives on the device (mmssl_step_tick), so the launch can sit in a CUDA graph
+    const int step = step_dev != nullptr ? *step_dev : step_host;
     const float bc1 = 1.f - powf(b1, (float)step);
     const float bc2 = 1.f - powf(b2, (float)step);
     const float step_size = lr / bc1;
@@ -100,20 +102,34 @@ __global__ void __launch_bounds__(256) dp_fused_adamw_kernel(const float* __rest
 
 using namespace mmssl;
 
-extern "C" int mmssl_dp_fused_adamw(const float* p_local, float* p_mc, const float* g_mc, float* m, float* v, int64_t begin,
-                                    int64_t count, float inv_world, int step, float lr, float beta1, float beta2, float eps,
-                                    float weight_decay, void* stream_) {
-    cudaStream_t st = (cudaStream_t)stream_;
+static int dp_fused_launch(const float* p_local, float* p_mc, const float* g_mc, float* m, float* v, int64_t begin, int64_t count,
+                           float inv_world, int step, const int32_t* step_dev, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, cudaStream_t st) {
     MMSSL_REQUIRE(begin % 4 == 0 && count % 4 == 0, "slice must be a multiple of 4 floats");
     MMSSL_REQUIRE(aligned16(p_local) && aligned16(p_mc) && aligned16(g_mc) && aligned16(m) && aligned16(v), "alignment");
-    MMSSL_REQUIRE(step >= 1, "step is 1-based");
+    MMSSL_REQUIRE(step_dev != nullptr || step >= 1, "step is 1-based");
     if (count == 0) return 0;
     int64_t blocks = (count / 4 + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    dp_fused_adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p_local, p_mc, g_mc, m, v, begin, count / 4, inv_world, step, lr,
+    dp_fused_adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p_local, p_mc, g_mc, m, v, begin, count / 4, inv_world, step, step_dev, lr,
                                                            beta1, beta2, eps, weight_decay);
     MMSSL_LAUNCH_OK();
     return 0;
+}
+
+extern "C" int mmssl_dp_fused_adamw(const float* p_local, float* p_mc, const float* g_mc, float* m, float* v, int64_t begin,
+                                    int64_t count, float inv_world, int step, float lr, float beta1, float beta2, float eps,
+                                    float weight_decay, void* stream_) {
+    return dp_fused_launch(p_local, p_mc, g_mc, m, v, begin, count, inv_world, step, nullptr, lr, beta1, beta2, eps, weight_decay,
+                           (cudaStream_t)stream_);
+}
+
+extern "C" int mmssl_dp_fused_adamw_dev(const float* p_local, float* p_mc, const float* g_mc, float* m, float* v, int64_t begin,
+                                        int64_t count, float inv_world, const int32_t* step_dev, float lr, float beta1, float beta2,
+                                        float eps, float weight_decay, void* stream_) {
+    MMSSL_REQUIRE(step_dev != nullptr, "device step counter missing");
+    return dp_fused_launch(p_local, p_mc, g_mc, m, v, begin, count, inv_world, 0, step_dev, lr, beta1, beta2, eps, weight_decay,
+                           (cudaStream_t)stream_);
 }
 
 extern "C" int mmssl_step_tick(int32_t* step_dev, void* stream_) {

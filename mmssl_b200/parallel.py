@@ -107,6 +107,19 @@ class FusedDPOptimizer:
                                             self.count, 1.0 / self.world, self.step_no, lr, b1, b2, eps, wd, stream()))
         self.hp.barrier()          # every slice of the new parameters has been published
 
+    def step_captured(self, step_dev: torch.Tensor) -> None:
+        """The same step with the step number read from the device counter `step_dev` (int32, already ticked): two signal-pad
+        barriers + one kernel, nothing host-dependent -- meant to be captured INSIDE the step's CUDA graph (the
+        eager launches after the replay were what the N >= 2 step paid over the 1-GPU step)."""
+        from . import _lib
+        from ._lib import ptr, stream
+        lib = _lib.load(require_device=True)
+        lr, b1, b2, eps, wd = self.hyper
+        self.hg.barrier()
+        _lib.check(lib.mmssl_dp_fused_adamw_dev(ptr(self.pflat), self.p_mc, self.g_mc, ptr(self.m), ptr(self.v), self.begin,
+                                                self.count, 1.0 / self.world, ptr(step_dev), lr, b1, b2, eps, wd, stream()))
+        self.hp.barrier()
+
 
 # ------------------------------------------------------------------------------------------ row sharding
 @dataclass(frozen=True)
