@@ -149,6 +149,11 @@ static int choose_split(int64_t m, int64_t n, int64_t k) {
     const int64_t m_tiles = (m + kBlockM - 1) / kBlockM;
     const int64_t slots = (int64_t)kNumSMs * (n == 64 ? 2 : 1);
     int64_t split = slots / m_tiles;
+    // accuracy: the tensor core's fp32 accumulate is not round-to-nearest and its error grows linearly with the number of MMAs
+    // chained into one TMEM accumulator (gemm_wide.cu; measured round 2: the weight gradient at 200k items, 347 k-blocks per
+    // slice, was 1e-4 off).  A slice is therefore at most kMaxChainKb k-blocks long; the slices are summed in fp32 by the epilogue.
+    const int64_t need = (total_kb + kMaxChainKb - 1) / kMaxChainKb;
+    if (split < need) split = need;
     if (split > kMaxSplit) split = kMaxSplit;
     if (split > total_kb) split = total_kb;
     if (split < 1) split = 1;

@@ -10,7 +10,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle span
 constexpr int kTileABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kThreads = 192;
-constexpr int kMaxSplit = 64;
+constexpr int kMaxSplit = 1024;
+constexpr int kMaxChainKb = 48;                  // k-blocks (64 of K each) accumulated in TMEM by one CTA of the split-K GEMM: 576 chained MMAs
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -247,7 +247,11 @@ class RowShardedHotStep:
         self.P = {k: params[k] for k in LIVE}
         self.feats, self.graphs = tuple(feats), tuple(graphs)
         self.engine = Engine(cfg.embed_size, cfg.n_layers, cfg.head_num, cfg.id_cat_rate, cfg.model_cat_rate, cfg.proj_impl)
-        self.engine.two_streams = False                     # the collectives order the work on one stream
+        # NCCL / gloo collectives order the work on one stream.  With the multicast exchange every exchange is a kernel plus a
+        # device-side signal-pad barrier on its own symmetric table, so the modality branch (tables of width 2d) and the id / GCN
+        # branch (width d) can overlap one branch's exchange with the other's SpMMs, like on one GPU (engine.two_streams).
+        import os as _os
+        self.engine.two_streams = (exchange == "multicast" and part_u.world > 1 and _os.environ.get("MMSSL_ROWSHARD_STREAMS", "1") == "1")
         self.engine.exchange = self._exchange
         # schedule of the products whose dense operand lives in the user space (A_iu @ u, A_ui^T @ du, ...):
         #   "allgather"      all-gather the user-sized operand, multiply the rank's rows (round 1)
