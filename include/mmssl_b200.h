@@ -213,6 +213,16 @@ int mmssl_infonce_stats(const float* a, const float* b, int64_t n, int d, float 
 int mmssl_infonce_grad(const float* a, const float* b, int64_t n, int d, float inv_tau, const float* coef, float* ga,
                        float* gb, void* stream);
 /* through the normalisation, then (atomic) scatter-add into the tables: g_z1[idx[i]] += ..., g_z2[idx[i]] += ... */
+/* Tensor-core InfoNCE for n <= 2048, d in {64, 128} (loss_tc.cu): the similarity tiles a a^T, a b^T on tcgen05 (bf16 hi/lo, three
+ * MMAs per product), exp / row sums / diagonal in the TMEM epilogue, the exponentials kept as bf16 hi/lo matrices in `workspace`;
+ * the backward = three split-K tcgen05 products of those matrices with [a | u.a], b, u.a + one combine kernel.  Same inputs and
+ * outputs as mmssl_infonce_stats / mmssl_infonce_grad (ga, gb are WRITTEN here, accumulated there). */
+int mmssl_infonce_tc_supported(int64_t n, int d);
+int64_t mmssl_infonce_tc_workspace_bytes(int64_t n, int d);
+int mmssl_infonce_stats_tc(const float* a, const float* b, int64_t n, int d, float inv_tau, float* stats, float* coef,
+                           const float* g_loss, float* loss_part, void* workspace, int64_t workspace_bytes, void* stream);
+int mmssl_infonce_grad_tc(const float* a, const float* b, int64_t n, int d, float inv_tau, const float* coef, const float* stats,
+                          float* ga, float* gb, void* workspace, int64_t workspace_bytes, void* stream);
 int mmssl_infonce_scatter(const float* ga, const float* gb, const float* a, const float* b, const float* na,
                           const float* nb, const int64_t* idx, int64_t n, int d, float* g_z1, int64_t ldg1, float* g_z2,
                           int64_t ldg2, void* stream);

@@ -503,6 +503,15 @@ extern "C" int mmssl_infonce_stats(const float* a, const float* b, int64_t n, in
     return 0;
 }
 
+namespace mmssl {
+// loss rows + backward coefficients from the row sums of `ntj` column tiles (used by the tensor-core path, loss_tc.cu)
+int nce_finalize_launch(int64_t n, int64_t ntj, float* stats, float* coef, const float* g_loss, float* loss_part, cudaStream_t st) {
+    MMSSL_CUDA_LAUNCH((nce_finalize_kernel), dim3((unsigned)mmssl_infonce_loss_blocks(n)), dim3(256), 0, st, n, ntj, stats, coef, g_loss, loss_part);
+    MMSSL_LAUNCH_OK();
+    return 0;
+}
+}  // namespace mmssl
+
 extern "C" int mmssl_infonce_grad(const float* a, const float* b, int64_t n, int d, float inv_tau, const float* coef,
                                   float* ga, float* gb, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;

@@ -1,0 +1,331 @@
+// InfoNCE on the tensor cores (reference: sim / batched_contrastive_loss, main.py:211-249, calls :411-412).
+//
+// For a batch of n <= 2048 rows the two similarity matrices  a a^T  and  a b^T  (a = normalised z1 rows, b = normalised z2 rows)
+// are n x n x d contractions: 0.27 GFLOP at n = 1024, d = 64 -- tensor-core work.  The fp32 contract (1e-4) is kept the way the
+// projection keeps it: operands as bf16 hi + lo pairs, three MMAs per product, fp32 accumulation in TMEM (K = d <= 256: 48
+// chained MMAs at most, far below the lengths where the accumulate error shows, gemm_wide.cu).  |s / tau| <= 2, so a 1e-5
+// error in s is 2e-5 in exp(s / tau).
+//
+//   forward  nce_stats_tc_kernel: CTA (it, jt) owns the 128 x 128 tiles  S_R = A_i A_j^T,  S_B = A_i B_j^T  and  S_T = B_i A_j^T
+//            (the transposed block of a b^T that the backward needs row-major) in three TMEM accumulators; operands by TMA
+//            (SWIZZLE_128B), single-thread tcgen05.mma issue, four epilogue warps: tcgen05.ld -> exp -> row sums, diagonal,
+//            and the exponentials themselves stored as bf16 hi / lo matrices E_R, E_B, E_T (12 MB at n = 1024: L2-resident).
+//            nce_finalize_kernel (loss.cu) turns the sums into loss rows and backward coefficients u, v as before.
+//   backward with P_ij = -(u_i + u_j) R_ij / tau (i != j), Q_ij = B_ij (-u_i + [i == j] v_i) / tau:
+//              dL/da_i = sum_j P_ij a_j + Q_ij b_j = -(1/tau) [ u_i (E_R a)_i + (E_R (u.a))_i + u_i (E_B b)_i ] + diagonal terms
+//              dL/db_j = sum_i Q_ij a_i           = -(1/tau) (E_T (u.a))_j + diagonal term
+//            i.e. three products of the stored exponentials with [a | u.a], b and u.a: nce_operands_kernel writes those operands
+//            transposed (K-major over the batch) as bf16 hi / lo, the products run on the projection's split-K tcgen05 kernel
+//            (mmssl_gemm_bf16x3), nce_combine_kernel sums the K slices and applies the coefficients.
+// Larger batches (B = 16384: the exponentials would take 3 TB) and d = 256 (operand width 512) stay on the CUDA-core kernels.
+#include <cuda_bf16.h>
+
+#include "tc_common.cuh"
+#include "../../include/mmssl_b200.h"
+
+namespace mmssl {
+
+int nce_finalize_launch(int64_t n, int64_t ntj, float* stats, float* coef, const float* g_loss, float* loss_part, cudaStream_t st);   // loss.cu
+
+constexpr int kNceTile = 128;
+constexpr int kNceMaxN = 2048;
+constexpr uint32_t kNceIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNceTile >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+constexpr int kNceStageBytes = 8 * kTileABytes;                     // Ai, Aj, Bj, Bi  x  hi, lo : 128 KB
+constexpr int kNceSmemBytes = kNceStageBytes + 1024 + 256;
+
+__device__ __forceinline__ uint32_t pack_bf16(float x, float y) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(y)) << 16);
+}
+
+// stats layout (loss.cu): [diagR n][diagB n][loss n][unused n][partR ntj*n][partB ntj*n],  ntj = gridDim.y
+__global__ void __launch_bounds__(kThreads, 1)
+nce_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, int64_t n, int nkb,
+                    float inv_tau, float* __restrict__ stats, uint16_t* __restrict__ e_hi, uint16_t* __restrict__ e_lo, int64_t lde) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kNceStageBytes);
+    uint64_t* empty_bar = full_bar + 1;
+    uint64_t* accum_bar = empty_bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int it = blockIdx.x, jt = blockIdx.y;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_lo) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(full_bar, 1); mbar_init(empty_bar, 1); mbar_init(accum_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(empty_bar, ((uint32_t)kb & 1u) ^ 1u);
+                mbar_expect_tx(full_bar, kNceStageBytes);
+                const int kx = kb * kBlockK;
+                tma_load_2d(&tm_a_hi, full_bar, smem + 0 * kTileABytes, kx, it * kNceTile, kEvictLast);   // A_i
+                tma_load_2d(&tm_a_lo, full_bar, smem + 1 * kTileABytes, kx, it * kNceTile, kEvictLast);
+                tma_load_2d(&tm_a_hi, full_bar, smem + 2 * kTileABytes, kx, jt * kNceTile, kEvictLast);   // A_j
+                tma_load_2d(&tm_a_lo, full_bar, smem + 3 * kTileABytes, kx, jt * kNceTile, kEvictLast);
+                tma_load_2d(&tm_b_hi, full_bar, smem + 4 * kTileABytes, kx, jt * kNceTile, kEvictLast);   // B_j
+                tma_load_2d(&tm_b_lo, full_bar, smem + 5 * kTileABytes, kx, jt * kNceTile, kEvictLast);
+                tma_load_2d(&tm_b_hi, full_bar, smem + 6 * kTileABytes, kx, it * kNceTile, kEvictLast);   // B_i
+                tma_load_2d(&tm_b_lo, full_bar, smem + 7 * kTileABytes, kx, it * kNceTile, kEvictLast);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full_bar, (uint32_t)kb & 1u);
+                tc_fence_after();
+                const uint32_t t0 = smem_u32(smem);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint32_t off = k * 32;
+                    uint64_t dsc[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dsc[q] = make_sw128_kmajor_desc(t0 + q * kTileABytes + off);
+                    const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                    // S_R = A_i A_j^T
+                    umma_bf16(tmem_base + 0 * kNceTile, dsc[0], dsc[2], kNceIdesc, acc);
+                    umma_bf16(tmem_base + 0 * kNceTile, dsc[0], dsc[3], kNceIdesc, 1u);
+                    umma_bf16(tmem_base + 0 * kNceTile, dsc[1], dsc[2], kNceIdesc, 1u);
+                    // S_B = A_i B_j^T
+                    umma_bf16(tmem_base + 1 * kNceTile, dsc[0], dsc[4], kNceIdesc, acc);
+                    umma_bf16(tmem_base + 1 * kNceTile, dsc[0], dsc[5], kNceIdesc, 1u);
+                    umma_bf16(tmem_base + 1 * kNceTile, dsc[1], dsc[4], kNceIdesc, 1u);
+                    // S_T = B_i A_j^T   (= the transposed block of a b^T)
+                    umma_bf16(tmem_base + 2 * kNceTile, dsc[6], dsc[2], kNceIdesc, acc);
+                    umma_bf16(tmem_base + 2 * kNceTile, dsc[6], dsc[3], kNceIdesc, 1u);
+                    umma_bf16(tmem_base + 2 * kNceTile, dsc[7], dsc[2], kNceIdesc, 1u);
+                }
+                umma_commit(empty_bar);
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int64_t i = (int64_t)it * kNceTile + q * 32 + lane;
+        const int64_t j0 = (int64_t)jt * kNceTile;
+        const int64_t ntj = gridDim.y;
+        const float scale = inv_tau * 1.4426950408889634f;          // exp(x) = exp2(x log2 e)
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        float sum_r = 0.f, sum_b = 0.f;
+#pragma unroll 1
+        for (int mat = 0; mat < 3; ++mat) {
+            uint16_t* hi = e_hi + (int64_t)mat * lde * lde + i * lde + j0;
+            uint16_t* lo = e_lo + (int64_t)mat * lde * lde + i * lde + j0;
+#pragma unroll 1
+            for (int c = 0; c < kNceTile; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mat * kNceTile + c), v);
+                uint32_t ph[16], pl[16];
+                float part = 0.f;
+#pragma unroll
+                for (int t = 0; t < 32; t += 2) {
+                    float e0 = 0.f, e1 = 0.f;
+                    if (i < n && j0 + c + t < n) e0 = exp2f(__uint_as_float(v[t]) * scale);
+                    if (i < n && j0 + c + t + 1 < n) e1 = exp2f(__uint_as_float(v[t + 1]) * scale);
+                    part += e0 + e1;
+                    if (mat < 2 && i < n) {
+                        if (i == j0 + c + t) stats[mat * n + i] = e0;
+                        if (i == j0 + c + t + 1) stats[mat * n + i] = e1;
+                    }
+                    const float h0 = __bfloat162float(__float2bfloat16_rn(e0)), h1 = __bfloat162float(__float2bfloat16_rn(e1));
+                    ph[t / 2] = pack_bf16(e0, e1);
+                    pl[t / 2] = pack_bf16(e0 - h0, e1 - h1);
+                }
+                if (mat == 0) sum_r += part; else if (mat == 1) sum_b += part;
+                if (i < lde) {      // rows up to the padded height are written (zeros beyond n): the GEMMs read them as K padding
+#pragma unroll
+                    for (int t = 0; t < 16; t += 4) {
+                        *reinterpret_cast<uint4*>(hi + c + 2 * t) = make_uint4(ph[t], ph[t + 1], ph[t + 2], ph[t + 3]);
+                        *reinterpret_cast<uint4*>(lo + c + 2 * t) = make_uint4(pl[t], pl[t + 1], pl[t + 2], pl[t + 3]);
+                    }
+                }
+            }
+        }
+        if (i < n) {
+            stats[4 * n + jt * n + i] = sum_r;
+            stats[4 * n + ntj * n + jt * n + i] = sum_b;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+// Transposed bf16 hi / lo operands of the backward products, K-major over the batch (zero beyond n):
+//   op1[c][i] = a[i][c] (c < d),  op1[d + c][i] = u_i a[i][c];    op2[c][i] = b[i][c]
+__global__ void nce_operands_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ coef, int64_t n,
+                                    int d, uint16_t* __restrict__ op1_hi, uint16_t* __restrict__ op1_lo, uint16_t* __restrict__ op2_hi,
+                                    uint16_t* __restrict__ op2_lo, int64_t ldn) {
+    __shared__ float ta[32][33], tb[32][33];
+    __shared__ float us[32];
+    const int64_t i0 = blockIdx.x * 32ll;
+    const int c0 = blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int64_t i = i0 + k;
+        const int c = c0 + threadIdx.x;
+        ta[k][threadIdx.x] = (i < n) ? a[i * d + c] : 0.f;
+        tb[k][threadIdx.x] = (i < n) ? b[i * d + c] : 0.f;
+    }
+    if (threadIdx.y == 0) us[threadIdx.x] = (i0 + threadIdx.x < n) ? coef[i0 + threadIdx.x] : 0.f;
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int c = c0 + k;
+        const int64_t i = i0 + threadIdx.x;
+        if (i >= ldn) continue;
+        const float va = ta[threadIdx.x][k], vb = tb[threadIdx.x][k], vu = va * us[threadIdx.x];
+        const __nv_bfloat16 ha = __float2bfloat16_rn(va), hb = __float2bfloat16_rn(vb), hu = __float2bfloat16_rn(vu);
+        op1_hi[(int64_t)c * ldn + i] = __bfloat16_as_ushort(ha);
+        op1_lo[(int64_t)c * ldn + i] = __bfloat16_as_ushort(__float2bfloat16_rn(va - __bfloat162float(ha)));
+        op1_hi[(int64_t)(d + c) * ldn + i] = __bfloat16_as_ushort(hu);
+        op1_lo[(int64_t)(d + c) * ldn + i] = __bfloat16_as_ushort(__float2bfloat16_rn(vu - __bfloat162float(hu)));
+        op2_hi[(int64_t)c * ldn + i] = __bfloat16_as_ushort(hb);
+        op2_lo[(int64_t)c * ldn + i] = __bfloat16_as_ushort(__float2bfloat16_rn(vb - __bfloat162float(hb)));
+    }
+}
+
+// ga[i] = -(1/tau) [ u_i (G1a_i - R_ii a_i) + (G1ua_i - R_ii u_i a_i) + u_i G2_i ] + (v_i/tau) B_ii b_i
+// gb[j] = -(1/tau) G3_j + (v_j/tau) B_jj a_j          G1 = E_R [a | u.a] (width 2d), G2 = E_B b, G3 = E_T (u.a): sums of K slices
+__global__ void __launch_bounds__(256) nce_combine_kernel(const float* __restrict__ g1, int s1, const float* __restrict__ g2, int s2,
+                                                          const float* __restrict__ g3, int s3, const float* __restrict__ a,
+                                                          const float* __restrict__ b, const float* __restrict__ coef,
+                                                          const float* __restrict__ stats, int64_t n, int d4, float inv_tau,
+                                                          float* __restrict__ ga, float* __restrict__ gb) {
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= n * d4) return;
+    const int64_t i = t / d4;
+    const int c = (int)(t - i * d4) * 4;
+    const int d = d4 * 4;
+    float4 xa = f4zero(), xua = f4zero(), x2 = f4zero(), x3 = f4zero();
+    for (int s = 0; s < s1; ++s) {
+        const float* p = g1 + ((int64_t)s * n + i) * (2 * d);
+        xa = add4(xa, ld4(p + c));
+        xua = add4(xua, ld4(p + d + c));
+    }
+    for (int s = 0; s < s2; ++s) x2 = add4(x2, ld4(g2 + ((int64_t)s * n + i) * d + c));
+    for (int s = 0; s < s3; ++s) x3 = add4(x3, ld4(g3 + ((int64_t)s * n + i) * d + c));
+    const float u = coef[i], v = coef[n + i], rii = stats[i], bii = stats[n + i];
+    const float4 av = ld4(a + i * d + c), bv = ld4(b + i * d + c);
+    float4 o, w;
+    o.x = -inv_tau * (u * (xa.x - rii * av.x) + (xua.x - rii * u * av.x) + u * x2.x) + inv_tau * v * bii * bv.x;
+    o.y = -inv_tau * (u * (xa.y - rii * av.y) + (xua.y - rii * u * av.y) + u * x2.y) + inv_tau * v * bii * bv.y;
+    o.z = -inv_tau * (u * (xa.z - rii * av.z) + (xua.z - rii * u * av.z) + u * x2.z) + inv_tau * v * bii * bv.z;
+    o.w = -inv_tau * (u * (xa.w - rii * av.w) + (xua.w - rii * u * av.w) + u * x2.w) + inv_tau * v * bii * bv.w;
+    w.x = -inv_tau * x3.x + inv_tau * v * bii * av.x;
+    w.y = -inv_tau * x3.y + inv_tau * v * bii * av.y;
+    w.z = -inv_tau * x3.z + inv_tau * v * bii * av.z;
+    w.w = -inv_tau * x3.w + inv_tau * v * bii * av.w;
+    st4(ga + i * d + c, o);
+    st4(gb + i * d + c, w);
+}
+
+struct NceWs {
+    uint16_t *a_hi, *a_lo, *b_hi, *b_lo;        // [n][d]
+    uint16_t *e_hi, *e_lo;                       // [3][lde][lde]  (E_R, E_B, E_T)
+    uint16_t *op1_hi, *op1_lo, *op2_hi, *op2_lo; // [2d][lde], [d][lde]
+    float *g1, *g2, *g3;                         // K-slice partials of the three products
+    int s1, s2, s3;
+    int64_t lde;
+    size_t total;
+};
+
+static void nce_carve(int64_t n, int d, void* base, NceWs* w) {
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const int64_t lde = (n + kNceTile - 1) / kNceTile * kNceTile;
+    size_t off = 0;
+    char* b = (char*)base;
+    auto take = [&](size_t bytes) { char* p = b + off; off += up(bytes); return p; };
+    w->lde = lde;
+    w->a_hi = (uint16_t*)take(2 * n * d); w->a_lo = (uint16_t*)take(2 * n * d);
+    w->b_hi = (uint16_t*)take(2 * n * d); w->b_lo = (uint16_t*)take(2 * n * d);
+    w->e_hi = (uint16_t*)take(2 * 3 * lde * lde); w->e_lo = (uint16_t*)take(2 * 3 * lde * lde);
+    w->op1_hi = (uint16_t*)take(2 * 2 * d * lde); w->op1_lo = (uint16_t*)take(2 * 2 * d * lde);
+    w->op2_hi = (uint16_t*)take(2 * d * lde); w->op2_lo = (uint16_t*)take(2 * d * lde);
+    const int64_t f1 = mmssl_gemm_bf16x3_workspace_floats(n, 2 * d, n, &w->s1);
+    const int64_t f2 = mmssl_gemm_bf16x3_workspace_floats(n, d, n, &w->s2);
+    w->s3 = w->s2;
+    w->g1 = (float*)take(4 * f1); w->g2 = (float*)take(4 * f2); w->g3 = (float*)take(4 * f2);
+    w->total = off + 256;
+}
+
+}  // namespace mmssl
+
+using namespace mmssl;
+
+extern "C" int mmssl_infonce_tc_supported(int64_t n, int d) { return (n >= 1 && n <= kNceMaxN && (d == 64 || d == 128)) ? 1 : 0; }
+
+extern "C" int64_t mmssl_infonce_tc_workspace_bytes(int64_t n, int d) {
+    if (!mmssl_infonce_tc_supported(n, d)) return 0;
+    NceWs w;
+    nce_carve(n, d, nullptr, &w);
+    return (int64_t)w.total;
+}
+
+// a, b: the normalised rows written by mmssl_infonce_prepare; stats / coef / loss_part as for mmssl_infonce_stats.
+extern "C" int mmssl_infonce_stats_tc(const float* a, const float* b, int64_t n, int d, float inv_tau, float* stats, float* coef,
+                                      const float* g_loss, float* loss_part, void* workspace, int64_t workspace_bytes, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    MMSSL_REQUIRE(mmssl_infonce_tc_supported(n, d), "tensor-core InfoNCE: n <= 2048 and d in {64, 128} (use mmssl_infonce_stats)");
+    MMSSL_REQUIRE(workspace != nullptr && aligned16(workspace), "workspace missing");
+    NceWs w;
+    nce_carve(n, d, workspace, &w);
+    MMSSL_REQUIRE((int64_t)w.total <= workspace_bytes, "workspace too small (mmssl_infonce_tc_workspace_bytes)");
+    if (int rc = mmssl_split_bf16(a, d, n, d, w.a_hi, w.a_lo, d, stream_)) return rc;
+    if (int rc = mmssl_split_bf16(b, d, n, d, w.b_hi, w.b_lo, d, stream_)) return rc;
+    CUtensorMap ah, al, bh, bl;
+    if (int rc = make_map(&ah, w.a_hi, n, d, kNceTile)) return rc;
+    if (int rc = make_map(&al, w.a_lo, n, d, kNceTile)) return rc;
+    if (int rc = make_map(&bh, w.b_hi, n, d, kNceTile)) return rc;
+    if (int rc = make_map(&bl, w.b_lo, n, d, kNceTile)) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MMSSL_CUDA(cudaFuncSetAttribute(nce_stats_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNceSmemBytes));
+        attr_done = true;
+    }
+    const unsigned nt = (unsigned)(w.lde / kNceTile);
+    nce_stats_tc_kernel<<<dim3(nt, nt), kThreads, kNceSmemBytes, st>>>(ah, al, bh, bl, n, d / kBlockK, inv_tau, stats, w.e_hi, w.e_lo, w.lde);
+    MMSSL_LAUNCH_OK();
+    return nce_finalize_launch(n, nt, stats, coef, g_loss, loss_part, st);
+}
+
+// ga, gb (written, not accumulated) from the exponentials mmssl_infonce_stats_tc left in `workspace`.
+extern "C" int mmssl_infonce_grad_tc(const float* a, const float* b, int64_t n, int d, float inv_tau, const float* coef,
+                                     const float* stats, float* ga, float* gb, void* workspace, int64_t workspace_bytes, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    MMSSL_REQUIRE(mmssl_infonce_tc_supported(n, d), "tensor-core InfoNCE: n <= 2048 and d in {64, 128} (use mmssl_infonce_grad)");
+    NceWs w;
+    nce_carve(n, d, workspace, &w);
+    MMSSL_REQUIRE(workspace != nullptr && (int64_t)w.total <= workspace_bytes, "workspace too small");
+    dim3 grid((unsigned)((w.lde + 31) / 32), (unsigned)(d / 32));
+    nce_operands_kernel<<<grid, dim3(32, 8), 0, st>>>(a, b, coef, n, d, w.op1_hi, w.op1_lo, w.op2_hi, w.op2_lo, w.lde);
+    MMSSL_LAUNCH_OK();
+    const int64_t ee = w.lde * w.lde;
+    if (int rc = mmssl_gemm_bf16x3(w.e_hi, w.e_lo, w.lde, w.op1_hi, w.op1_lo, w.lde, n, 2 * d, n, w.s1, w.g1, stream_)) return rc;
+    if (int rc = mmssl_gemm_bf16x3(w.e_hi + ee, w.e_lo + ee, w.lde, w.op2_hi, w.op2_lo, w.lde, n, d, n, w.s2, w.g2, stream_)) return rc;
+    if (int rc = mmssl_gemm_bf16x3(w.e_hi + 2 * ee, w.e_lo + 2 * ee, w.lde, w.op1_hi + (int64_t)d * w.lde, w.op1_lo + (int64_t)d * w.lde, w.lde,
+                                   n, d, n, w.s3, w.g3, stream_)) return rc;
+    const int64_t tot = n * (d / 4);
+    nce_combine_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w.g1, w.s1, w.g2, w.s2, w.g3, w.s3, a, b, coef, stats, n, d / 4, inv_tau, ga, gb);
+    MMSSL_LAUNCH_OK();
+    return 0;
+}

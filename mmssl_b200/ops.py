@@ -242,11 +242,19 @@ def bpr(uf, pf, nf, users, pos, neg, *, mode: int, reg_coef: float, g_mf=None, g
     return part, nb
 
 
+NCE_IMPL = "auto"       # "auto": tensor cores where mmssl_infonce_tc_supported (n <= 2048, d in {64, 128}); "simt": CUDA cores
+
+
 class InfoNCEWork:
     """Caller-owned work buffers of one InfoNCE evaluation (n rows, width d)."""
 
-    def __init__(self, n: int, d: int, device):
+    def __init__(self, n: int, d: int, device, impl: Optional[str] = None):
         lib = _lib_()
+        impl = NCE_IMPL if impl is None else impl
+        self.tc = impl != "simt" and n > 0 and bool(lib.mmssl_infonce_tc_supported(n, d))
+        self.ws = None
+        if self.tc:      # exponentials (bf16 hi/lo), transposed operands and K-slice partials of the tensor-core path
+            self.ws = torch.empty(lib.mmssl_infonce_tc_workspace_bytes(n, d), dtype=torch.uint8, device=device)
         f = dict(dtype=torch.float32, device=device)
         self.n, self.d = n, d
         self.a = torch.empty(n, d, **f); self.b = torch.empty(n, d, **f)
@@ -264,8 +272,12 @@ def infonce_forward(z1, z2, idx, inv_tau: float, work: InfoNCEWork, g_loss=None)
     n, d = work.n, work.d
     _lib.check(lib.mmssl_infonce_prepare(ptr(z1), _ld(z1), ptr(z2), _ld(z2), ptr(idx), n, d, ptr(work.a), ptr(work.b),
                                          ptr(work.na), ptr(work.nb), ptr(work.ga), ptr(work.gb), stream()))
-    _lib.check(lib.mmssl_infonce_stats(ptr(work.a), ptr(work.b), n, d, float(inv_tau), ptr(work.stats), ptr(work.coef),
-                                       ptr(g_loss), ptr(work.loss_part), stream()))
+    if work.tc:
+        _lib.check(lib.mmssl_infonce_stats_tc(ptr(work.a), ptr(work.b), n, d, float(inv_tau), ptr(work.stats), ptr(work.coef),
+                                              ptr(g_loss), ptr(work.loss_part), ptr(work.ws), work.ws.numel(), stream()))
+    else:
+        _lib.check(lib.mmssl_infonce_stats(ptr(work.a), ptr(work.b), n, d, float(inv_tau), ptr(work.stats), ptr(work.coef),
+                                           ptr(g_loss), ptr(work.loss_part), stream()))
     return work.loss_part[:work.n_loss_blocks]
 
 
@@ -273,7 +285,11 @@ def infonce_backward(idx, inv_tau: float, work: InfoNCEWork, g_z1, g_z2):
     """grad + scatter: accumulates d loss / d z1, z2 into g_z1 / g_z2 (tables when idx is given)."""
     lib = _lib_()
     n, d = work.n, work.d
-    _lib.check(lib.mmssl_infonce_grad(ptr(work.a), ptr(work.b), n, d, float(inv_tau), ptr(work.coef), ptr(work.ga), ptr(work.gb), stream()))
+    if work.tc:
+        _lib.check(lib.mmssl_infonce_grad_tc(ptr(work.a), ptr(work.b), n, d, float(inv_tau), ptr(work.coef), ptr(work.stats), ptr(work.ga),
+                                             ptr(work.gb), ptr(work.ws), work.ws.numel(), stream()))
+    else:
+        _lib.check(lib.mmssl_infonce_grad(ptr(work.a), ptr(work.b), n, d, float(inv_tau), ptr(work.coef), ptr(work.ga), ptr(work.gb), stream()))
     _lib.check(lib.mmssl_infonce_scatter(ptr(work.ga), ptr(work.gb), ptr(work.a), ptr(work.b), ptr(work.na), ptr(work.nb),
                                          ptr(idx), n, d, ptr(g_z1), _ld(g_z1), ptr(g_z2), _ld(g_z2), stream()))
 

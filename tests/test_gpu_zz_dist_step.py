@@ -24,4 +24,4 @@ def test_row_sharded_whole_step_two_gpus(exchange):
     assert out.returncode == 0, out.stderr[-2000:]
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert res["n_gpus"] == 2 and res["max_rel_err_vs_1gpu"] < 1e-4 and res["gathers_per_step"] > 0
-    assert ("NCCL" in res["exchange"]) == (exchange == "nccl")
+    assert res["exchange"].startswith("NCCL") == (exchange == "nccl")
