@@ -469,6 +469,30 @@ def extra_config(name, a, dev, hbm_peak, peak_src):
     return out
 
 
+def nvlink_counters(index: int):
+    """(rx_kib, tx_kib) summed over the NVLink links of GPU `index` from the driver's throughput counters
+    (`nvidia-smi nvlink -gt d`), or None where the query is not supported."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+    except Exception:
+        return None
+    rx = tx = 0
+    seen = False
+    for ln in out.splitlines():
+        ln = ln.strip()
+        if "Data Rx:" in ln or "Data Tx:" in ln:
+            try:
+                val = int(ln.split(":")[-1].strip().split()[0])
+            except (ValueError, IndexError):
+                continue
+            seen = True
+            if "Rx" in ln:
+                rx += val
+            else:
+                tx += val
+    return (rx, tx) if seen else None
+
+
 def _fixed_masks(I, d, drop, seed, dev):
     g = torch.Generator().manual_seed(seed)
     return tuple(((torch.rand(I, d, generator=g) >= drop) / (1 - drop)).float().to(dev) for _ in range(2))
@@ -639,12 +663,14 @@ def row_shard_report(name, a, rank, world, dev):
     torch.cuda.synchronize()
     dist.barrier()
     sh.n_gathers = sh.gathered_bytes = sh.n_reduce_scatters = 0
+    nv0 = nvlink_counters(dev.index) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(steps):
         sh.set_indices(*batches[s % 8]); step()
     e1.record()
     torch.cuda.synchronize()
+    nv1 = nvlink_counters(dev.index) if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
@@ -659,6 +685,13 @@ def row_shard_report(name, a, rank, world, dev):
                 "all_gathers_per_step": int(gath), "reduce_scatters_per_step": int(rsc), "bytes_received_per_rank_per_step": int(gbytes),
                 "nvlink_GBps_per_rank_if_serial": round(gbytes / (ms * 1e-3) / 1e9, 1),
                 "build_s": round(time.perf_counter() - t0, 1)})
+    if rank == 0:
+        if nv0 is not None and nv1 is not None:      # the driver's NVLink throughput counters around the timed loop (rank 0's GPU)
+            rx, tx = (nv1[0] - nv0[0]) * 1024 / steps, (nv1[1] - nv0[1]) * 1024 / steps
+            out["nvlink_counter"] = {"rx_bytes_per_step": int(rx), "tx_bytes_per_step": int(tx), "rx_GBps_over_the_step": round(rx / (ms * 1e-3) / 1e9, 1),
+                                     "tx_GBps_over_the_step": round(tx / (ms * 1e-3) / 1e9, 1), "source": "nvidia-smi nvlink -gt d (sum over links, rank 0)"}
+        else:
+            out["nvlink_counter"] = None
     if rank == 0 and ms_1gpu is not None:
         out["ms_per_step_1gpu"] = round(ms_1gpu, 4)
         out["speedup_vs_1gpu"] = round(ms_1gpu / ms, 3)

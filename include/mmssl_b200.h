@@ -221,8 +221,13 @@ int mmssl_infonce_tc_supported(int64_t n, int d);
 int64_t mmssl_infonce_tc_workspace_bytes(int64_t n, int d);
 int mmssl_infonce_stats_tc(const float* a, const float* b, int64_t n, int d, float inv_tau, float* stats, float* coef,
                            const float* g_loss, float* loss_part, void* workspace, int64_t workspace_bytes, void* stream);
+/* prepare (gather + normalise, as mmssl_infonce_prepare) + operand split + statistics in one call */
+int mmssl_infonce_forward_tc(const float* z1, int64_t ldz1, const float* z2, int64_t ldz2, const int64_t* idx, int64_t n, int d,
+                             float inv_tau, float* a, float* b, float* na, float* nb, float* stats, float* coef, const float* g_loss,
+                             float* loss_part, void* workspace, int64_t workspace_bytes, void* stream);
+/* phase: -1 all on `stream`; 0 operands, 1..3 the three products (independent of each other), 4 combine */
 int mmssl_infonce_grad_tc(const float* a, const float* b, int64_t n, int d, float inv_tau, const float* coef, const float* stats,
-                          float* ga, float* gb, void* workspace, int64_t workspace_bytes, void* stream);
+                          float* ga, float* gb, void* workspace, int64_t workspace_bytes, int phase, void* stream);
 int mmssl_infonce_scatter(const float* ga, const float* gb, const float* a, const float* b, const float* na,
                           const float* nb, const int64_t* idx, int64_t n, int d, float* g_z1, int64_t ldg1, float* g_z2,
                           int64_t ldg2, void* stream);

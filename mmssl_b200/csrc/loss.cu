@@ -3,6 +3,8 @@
 // Gather + dot + log-sigmoid / exp-softmax with warp-level reductions; forward value and the
 // gradient w.r.t. the embedding tables come out of the same pass (the gradient seeds of the scalar
 // losses are read from device scalars so nothing syncs with the host).
+#include <cuda_bf16.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -89,7 +91,9 @@ __global__ void __launch_bounds__(256) nce_prepare_kernel(const float* __restric
                                                           const int64_t* __restrict__ idx, int64_t n,
                                                           float* __restrict__ a, float* __restrict__ b,
                                                           float* __restrict__ na, float* __restrict__ nb,
-                                                          float* __restrict__ ga, float* __restrict__ gb) {
+                                                          float* __restrict__ ga, float* __restrict__ gb,
+                                                          uint16_t* __restrict__ a_hi = nullptr, uint16_t* __restrict__ a_lo = nullptr,
+                                                          uint16_t* __restrict__ b_hi = nullptr, uint16_t* __restrict__ b_lo = nullptr) {
     pdl_wait();
     const unsigned mask = group_mask<G>();
     const int lane = threadIdx.x & (G - 1);
@@ -112,10 +116,27 @@ __global__ void __launch_bounds__(256) nce_prepare_kernel(const float* __restric
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const int col = lane * 4 + c * 4 * G;
-        st4(a + i * d + col, scale4(v[c], i1));
-        st4(b + i * d + col, scale4(w[c], i2));
+        const float4 av = scale4(v[c], i1), bv = scale4(w[c], i2);
+        st4(a + i * d + col, av);
+        st4(b + i * d + col, bv);
         if (ga) st4(ga + i * d + col, f4zero());
         if (gb) st4(gb + i * d + col, f4zero());
+        if (a_hi) {     // bf16 hi / lo operands of the tensor-core path (loss_tc.cu), [n][d] K-major
+            auto split4 = [](const float4& x, uint16_t* hi, uint16_t* lo) {
+                const float xs[4] = {x.x, x.y, x.z, x.w};
+                uint16_t h[4], l[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const __nv_bfloat16 hb = __float2bfloat16_rn(xs[q]);
+                    h[q] = __bfloat16_as_ushort(hb);
+                    l[q] = __bfloat16_as_ushort(__float2bfloat16_rn(xs[q] - __bfloat162float(hb)));
+                }
+                *reinterpret_cast<uint2*>(hi) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+                *reinterpret_cast<uint2*>(lo) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+            };
+            split4(av, a_hi + i * d + col, a_lo + i * d + col);
+            split4(bv, b_hi + i * d + col, b_lo + i * d + col);
+        }
     }
     if (lane == 0) { na[i] = n1; nb[i] = n2; }
 }
@@ -470,13 +491,15 @@ extern "C" int mmssl_infonce_prepare(const float* z1, int64_t ldz1, const float*
     if (n == 0) return 0;
     return dispatch_d(d, [&](auto G, auto C) {
         const unsigned blocks = (unsigned)((n * GV(G) + 255) / 256);
-        MMSSL_CUDA_LAUNCH((nce_prepare_kernel<GV(G), GV(C)>), dim3(blocks), dim3(256), 0, st, z1, ldz1, z2, ldz2, idx, n, a, b, na, nb, ga, gb);
+        MMSSL_CUDA_LAUNCH((nce_prepare_kernel<GV(G), GV(C)>), dim3(blocks), dim3(256), 0, st, z1, ldz1, z2, ldz2, idx, n, a, b, na, nb, ga, gb,
+                          (uint16_t*)nullptr, (uint16_t*)nullptr, (uint16_t*)nullptr, (uint16_t*)nullptr);
         MMSSL_LAUNCH_OK();
         return 0;
     });
 }
 
-extern "C" int64_t mmssl_infonce_stats_floats(int64_t n) { return 4 * n + 2 * n * ((n + NT - 1) / NT); }
+// [diagR n][diagB n][loss n][unused n][partR ntj*n][partB ntj*n]; ntj <= ceil(n / 64) + 1 (the tensor-core path uses 2 per 128-tile)
+extern "C" int64_t mmssl_infonce_stats_floats(int64_t n) { return 4 * n + 2 * n * ((n + NT - 1) / NT + 1); }
 extern "C" int64_t mmssl_infonce_loss_blocks(int64_t n) { return (n + 255) / 256; }
 
 static int nce_smem_attr() {
@@ -504,6 +527,21 @@ extern "C" int mmssl_infonce_stats(const float* a, const float* b, int64_t n, in
 }
 
 namespace mmssl {
+// nce_prepare + bf16 hi / lo split of the normalised rows in one launch (tensor-core path, loss_tc.cu); ga / gb are not zeroed
+// there (the tensor-core backward writes them)
+int nce_prepare_split_launch(const float* z1, int64_t ldz1, const float* z2, int64_t ldz2, const int64_t* idx, int64_t n, int d, float* a,
+                             float* b, float* na, float* nb, uint16_t* a_hi, uint16_t* a_lo, uint16_t* b_hi, uint16_t* b_lo, cudaStream_t st) {
+    MMSSL_REQUIRE(aligned16(z1) && aligned16(z2) && ldz1 % 4 == 0 && ldz2 % 4 == 0 && aligned16(a) && aligned16(b), "alignment");
+    if (n == 0) return 0;
+    return dispatch_d(d, [&](auto G, auto C) {
+        const unsigned blocks = (unsigned)((n * GV(G) + 255) / 256);
+        MMSSL_CUDA_LAUNCH((nce_prepare_kernel<GV(G), GV(C)>), dim3(blocks), dim3(256), 0, st, z1, ldz1, z2, ldz2, idx, n, a, b, na, nb,
+                          (float*)nullptr, (float*)nullptr, a_hi, a_lo, b_hi, b_lo);
+        MMSSL_LAUNCH_OK();
+        return 0;
+    });
+}
+
 // loss rows + backward coefficients from the row sums of `ntj` column tiles (used by the tensor-core path, loss_tc.cu)
 int nce_finalize_launch(int64_t n, int64_t ntj, float* stats, float* coef, const float* g_loss, float* loss_part, cudaStream_t st) {
     MMSSL_CUDA_LAUNCH((nce_finalize_kernel), dim3((unsigned)mmssl_infonce_loss_blocks(n)), dim3(256), 0, st, n, ntj, stats, coef, g_loss, loss_part);

@@ -26,6 +26,8 @@
 namespace mmssl {
 
 int nce_finalize_launch(int64_t n, int64_t ntj, float* stats, float* coef, const float* g_loss, float* loss_part, cudaStream_t st);   // loss.cu
+int nce_prepare_split_launch(const float* z1, int64_t ldz1, const float* z2, int64_t ldz2, const int64_t* idx, int64_t n, int d, float* a,
+                             float* b, float* na, float* nb, uint16_t* a_hi, uint16_t* a_lo, uint16_t* b_hi, uint16_t* b_lo, cudaStream_t st);   // loss.cu
 
 constexpr int kNceTile = 128;
 constexpr int kNceMaxN = 2048;
@@ -33,12 +35,21 @@ constexpr uint32_t kNceIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(
 constexpr int kNceStageBytes = 8 * kTileABytes;                     // Ai, Aj, Bj, Bi  x  hi, lo : 128 KB
 constexpr int kNceSmemBytes = kNceStageBytes + 1024 + 256;
 
+// bf16 pair (x in the low half) with one cvt.rn.bf16x2; its two halves widened back to fp32 are shifts
 __device__ __forceinline__ uint32_t pack_bf16(float x, float y) {
-    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(y)) << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float fast_exp2(float x) {      // MUFU.EX2: |x| <= 2.9 here (|s / tau| <= 2), relative error ~2e-7
+    float y;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
-// stats layout (loss.cu): [diagR n][diagB n][loss n][unused n][partR ntj*n][partB ntj*n],  ntj = gridDim.y
-__global__ void __launch_bounds__(kThreads, 1)
+// stats layout (loss.cu): [diagR n][diagB n][loss n][unused n][partR ntj*n][partB ntj*n],  ntj = 2 * gridDim.y
+constexpr int kNceThreads = 320;       // warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue
+
+__global__ void __launch_bounds__(kNceThreads, 1)
 nce_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, int64_t n, int nkb,
                     float inv_tau, float* __restrict__ stats, uint16_t* __restrict__ e_hi, uint16_t* __restrict__ e_lo, int64_t lde) {
@@ -118,10 +129,11 @@ nce_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             umma_commit(accum_bar);
         }
     } else {
-        const int q = warp & 3;
+        // 8 epilogue warps: lane quarter q = warp & 3 (the TMEM lanes a warp may read), column half h of every accumulator
+        const int q = warp & 3, h = (warp - 2) >> 2;
         const int64_t i = (int64_t)it * kNceTile + q * 32 + lane;
         const int64_t j0 = (int64_t)jt * kNceTile;
-        const int64_t ntj = gridDim.y;
+        const int64_t ntj = 2 * (int64_t)gridDim.y;                   // row-sum partials: one per (column tile, half)
         const float scale = inv_tau * 1.4426950408889634f;          // exp(x) = exp2(x log2 e)
         mbar_wait(accum_bar, 0);
         tc_fence_after();
@@ -131,7 +143,7 @@ nce_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             uint16_t* hi = e_hi + (int64_t)mat * lde * lde + i * lde + j0;
             uint16_t* lo = e_lo + (int64_t)mat * lde * lde + i * lde + j0;
 #pragma unroll 1
-            for (int c = 0; c < kNceTile; c += 32) {
+            for (int c = h * (kNceTile / 2); c < (h + 1) * (kNceTile / 2); c += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mat * kNceTile + c), v);
                 uint32_t ph[16], pl[16];
@@ -139,16 +151,16 @@ nce_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 #pragma unroll
                 for (int t = 0; t < 32; t += 2) {
                     float e0 = 0.f, e1 = 0.f;
-                    if (i < n && j0 + c + t < n) e0 = exp2f(__uint_as_float(v[t]) * scale);
-                    if (i < n && j0 + c + t + 1 < n) e1 = exp2f(__uint_as_float(v[t + 1]) * scale);
+                    if (i < n && j0 + c + t < n) e0 = fast_exp2(__uint_as_float(v[t]) * scale);
+                    if (i < n && j0 + c + t + 1 < n) e1 = fast_exp2(__uint_as_float(v[t + 1]) * scale);
                     part += e0 + e1;
                     if (mat < 2 && i < n) {
                         if (i == j0 + c + t) stats[mat * n + i] = e0;
                         if (i == j0 + c + t + 1) stats[mat * n + i] = e1;
                     }
-                    const float h0 = __bfloat162float(__float2bfloat16_rn(e0)), h1 = __bfloat162float(__float2bfloat16_rn(e1));
-                    ph[t / 2] = pack_bf16(e0, e1);
-                    pl[t / 2] = pack_bf16(e0 - h0, e1 - h1);
+                    const uint32_t hp = pack_bf16(e0, e1);
+                    ph[t / 2] = hp;
+                    pl[t / 2] = pack_bf16(e0 - __uint_as_float(hp << 16), e1 - __uint_as_float(hp & 0xffff0000u));
                 }
                 if (mat == 0) sum_r += part; else if (mat == 1) sum_b += part;
                 if (i < lde) {      // rows up to the padded height are written (zeros beyond n): the GEMMs read them as K padding
@@ -161,8 +173,8 @@ nce_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             }
         }
         if (i < n) {
-            stats[4 * n + jt * n + i] = sum_r;
-            stats[4 * n + ntj * n + jt * n + i] = sum_b;
+            stats[4 * n + (2 * jt + h) * n + i] = sum_r;
+            stats[4 * n + ntj * n + (2 * jt + h) * n + i] = sum_b;
         }
     }
     tc_fence_before();
@@ -217,13 +229,28 @@ __global__ void __launch_bounds__(256) nce_combine_kernel(const float* __restric
     const int c = (int)(t - i * d4) * 4;
     const int d = d4 * 4;
     float4 xa = f4zero(), xua = f4zero(), x2 = f4zero(), x3 = f4zero();
-    for (int s = 0; s < s1; ++s) {
-        const float* p = g1 + ((int64_t)s * n + i) * (2 * d);
-        xa = add4(xa, ld4(p + c));
-        xua = add4(xua, ld4(p + d + c));
+    for (int s0 = 0; s0 < s1; s0 += 4) {            // 8 independent loads in flight, summed in slice order
+        float4 pa[4], pu[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool ok = s0 + q < s1;
+            const float* p = g1 + ((int64_t)(ok ? s0 + q : 0) * n + i) * (2 * d);
+            pa[q] = ok ? ld4(p + c) : f4zero();
+            pu[q] = ok ? ld4(p + d + c) : f4zero();
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { xa = add4(xa, pa[q]); xua = add4(xua, pu[q]); }
     }
-    for (int s = 0; s < s2; ++s) x2 = add4(x2, ld4(g2 + ((int64_t)s * n + i) * d + c));
-    for (int s = 0; s < s3; ++s) x3 = add4(x3, ld4(g3 + ((int64_t)s * n + i) * d + c));
+    for (int s0 = 0; s0 < max(s2, s3); s0 += 4) {
+        float4 p2[4], p3[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            p2[q] = (s0 + q < s2) ? ld4(g2 + ((int64_t)(s0 + q) * n + i) * d + c) : f4zero();
+            p3[q] = (s0 + q < s3) ? ld4(g3 + ((int64_t)(s0 + q) * n + i) * d + c) : f4zero();
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { x2 = add4(x2, p2[q]); x3 = add4(x3, p3[q]); }
+    }
     const float u = coef[i], v = coef[n + i], rii = stats[i], bii = stats[n + i];
     const float4 av = ld4(a + i * d + c), bv = ld4(b + i * d + c);
     float4 o, w;
@@ -282,16 +309,18 @@ extern "C" int64_t mmssl_infonce_tc_workspace_bytes(int64_t n, int d) {
 }
 
 // a, b: the normalised rows written by mmssl_infonce_prepare; stats / coef / loss_part as for mmssl_infonce_stats.
-extern "C" int mmssl_infonce_stats_tc(const float* a, const float* b, int64_t n, int d, float inv_tau, float* stats, float* coef,
-                                      const float* g_loss, float* loss_part, void* workspace, int64_t workspace_bytes, void* stream_) {
+static int nce_stats_tc_impl(const float* a, const float* b, int64_t n, int d, float inv_tau, float* stats, float* coef,
+                             const float* g_loss, float* loss_part, void* workspace, int64_t workspace_bytes, int presplit, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     MMSSL_REQUIRE(mmssl_infonce_tc_supported(n, d), "tensor-core InfoNCE: n <= 2048 and d in {64, 128} (use mmssl_infonce_stats)");
     MMSSL_REQUIRE(workspace != nullptr && aligned16(workspace), "workspace missing");
     NceWs w;
     nce_carve(n, d, workspace, &w);
     MMSSL_REQUIRE((int64_t)w.total <= workspace_bytes, "workspace too small (mmssl_infonce_tc_workspace_bytes)");
-    if (int rc = mmssl_split_bf16(a, d, n, d, w.a_hi, w.a_lo, d, stream_)) return rc;
-    if (int rc = mmssl_split_bf16(b, d, n, d, w.b_hi, w.b_lo, d, stream_)) return rc;
+    if (!presplit) {
+        if (int rc = mmssl_split_bf16(a, d, n, d, w.a_hi, w.a_lo, d, stream_)) return rc;
+        if (int rc = mmssl_split_bf16(b, d, n, d, w.b_hi, w.b_lo, d, stream_)) return rc;
+    }
     CUtensorMap ah, al, bh, bl;
     if (int rc = make_map(&ah, w.a_hi, n, d, kNceTile)) return rc;
     if (int rc = make_map(&al, w.a_lo, n, d, kNceTile)) return rc;
@@ -303,29 +332,57 @@ extern "C" int mmssl_infonce_stats_tc(const float* a, const float* b, int64_t n,
         attr_done = true;
     }
     const unsigned nt = (unsigned)(w.lde / kNceTile);
-    nce_stats_tc_kernel<<<dim3(nt, nt), kThreads, kNceSmemBytes, st>>>(ah, al, bh, bl, n, d / kBlockK, inv_tau, stats, w.e_hi, w.e_lo, w.lde);
+    nce_stats_tc_kernel<<<dim3(nt, nt), kNceThreads, kNceSmemBytes, st>>>(ah, al, bh, bl, n, d / kBlockK, inv_tau, stats, w.e_hi, w.e_lo, w.lde);
     MMSSL_LAUNCH_OK();
-    return nce_finalize_launch(n, nt, stats, coef, g_loss, loss_part, st);
+    return nce_finalize_launch(n, 2 * (int64_t)nt, stats, coef, g_loss, loss_part, st);
+}
+
+extern "C" int mmssl_infonce_stats_tc(const float* a, const float* b, int64_t n, int d, float inv_tau, float* stats, float* coef,
+                                      const float* g_loss, float* loss_part, void* workspace, int64_t workspace_bytes, void* stream_) {
+    return nce_stats_tc_impl(a, b, n, d, inv_tau, stats, coef, g_loss, loss_part, workspace, workspace_bytes, 0, stream_);
+}
+
+// mmssl_infonce_prepare + operand split in one kernel, then the statistics: z1 / z2 rows (gathered through idx) -> a, b, norms,
+// bf16 hi / lo of a and b in the workspace -> mmssl_infonce_stats_tc's work.
+extern "C" int mmssl_infonce_forward_tc(const float* z1, int64_t ldz1, const float* z2, int64_t ldz2, const int64_t* idx, int64_t n,
+                                        int d, float inv_tau, float* a, float* b, float* na, float* nb, float* stats, float* coef,
+                                        const float* g_loss, float* loss_part, void* workspace, int64_t workspace_bytes, void* stream_) {
+    MMSSL_REQUIRE(mmssl_infonce_tc_supported(n, d), "tensor-core InfoNCE: n <= 2048 and d in {64, 128}");
+    MMSSL_REQUIRE(workspace != nullptr && aligned16(workspace), "workspace missing");
+    NceWs w;
+    nce_carve(n, d, workspace, &w);
+    MMSSL_REQUIRE((int64_t)w.total <= workspace_bytes, "workspace too small (mmssl_infonce_tc_workspace_bytes)");
+    if (int rc = nce_prepare_split_launch(z1, ldz1, z2, ldz2, idx, n, d, a, b, na, nb, w.a_hi, w.a_lo, w.b_hi, w.b_lo, (cudaStream_t)stream_)) return rc;
+    return nce_stats_tc_impl(a, b, n, d, inv_tau, stats, coef, g_loss, loss_part, workspace, workspace_bytes, 1, stream_);
 }
 
 // ga, gb (written, not accumulated) from the exponentials mmssl_infonce_stats_tc left in `workspace`.
+// phase: -1 everything on `stream`; 0 transposed operands; 1, 2, 3 one product each (independent: may run on three streams);
+// 4 combine.
 extern "C" int mmssl_infonce_grad_tc(const float* a, const float* b, int64_t n, int d, float inv_tau, const float* coef,
-                                     const float* stats, float* ga, float* gb, void* workspace, int64_t workspace_bytes, void* stream_) {
+                                     const float* stats, float* ga, float* gb, void* workspace, int64_t workspace_bytes, int phase,
+                                     void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     MMSSL_REQUIRE(mmssl_infonce_tc_supported(n, d), "tensor-core InfoNCE: n <= 2048 and d in {64, 128} (use mmssl_infonce_grad)");
     NceWs w;
     nce_carve(n, d, workspace, &w);
     MMSSL_REQUIRE(workspace != nullptr && (int64_t)w.total <= workspace_bytes, "workspace too small");
-    dim3 grid((unsigned)((w.lde + 31) / 32), (unsigned)(d / 32));
-    nce_operands_kernel<<<grid, dim3(32, 8), 0, st>>>(a, b, coef, n, d, w.op1_hi, w.op1_lo, w.op2_hi, w.op2_lo, w.lde);
-    MMSSL_LAUNCH_OK();
+    MMSSL_REQUIRE(phase >= -1 && phase <= 4, "phase");
+    const auto on = [&](int p) { return phase == -1 || phase == p; };
+    if (on(0)) {
+        dim3 grid((unsigned)((w.lde + 31) / 32), (unsigned)(d / 32));
+        nce_operands_kernel<<<grid, dim3(32, 8), 0, st>>>(a, b, coef, n, d, w.op1_hi, w.op1_lo, w.op2_hi, w.op2_lo, w.lde);
+        MMSSL_LAUNCH_OK();
+    }
     const int64_t ee = w.lde * w.lde;
-    if (int rc = mmssl_gemm_bf16x3(w.e_hi, w.e_lo, w.lde, w.op1_hi, w.op1_lo, w.lde, n, 2 * d, n, w.s1, w.g1, stream_)) return rc;
-    if (int rc = mmssl_gemm_bf16x3(w.e_hi + ee, w.e_lo + ee, w.lde, w.op2_hi, w.op2_lo, w.lde, n, d, n, w.s2, w.g2, stream_)) return rc;
-    if (int rc = mmssl_gemm_bf16x3(w.e_hi + 2 * ee, w.e_lo + 2 * ee, w.lde, w.op1_hi + (int64_t)d * w.lde, w.op1_lo + (int64_t)d * w.lde, w.lde,
-                                   n, d, n, w.s3, w.g3, stream_)) return rc;
-    const int64_t tot = n * (d / 4);
-    nce_combine_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w.g1, w.s1, w.g2, w.s2, w.g3, w.s3, a, b, coef, stats, n, d / 4, inv_tau, ga, gb);
-    MMSSL_LAUNCH_OK();
+    if (on(1)) if (int rc = mmssl_gemm_bf16x3(w.e_hi, w.e_lo, w.lde, w.op1_hi, w.op1_lo, w.lde, n, 2 * d, n, w.s1, w.g1, stream_)) return rc;
+    if (on(2)) if (int rc = mmssl_gemm_bf16x3(w.e_hi + ee, w.e_lo + ee, w.lde, w.op2_hi, w.op2_lo, w.lde, n, d, n, w.s2, w.g2, stream_)) return rc;
+    if (on(3)) if (int rc = mmssl_gemm_bf16x3(w.e_hi + 2 * ee, w.e_lo + 2 * ee, w.lde, w.op1_hi + (int64_t)d * w.lde, w.op1_lo + (int64_t)d * w.lde,
+                                              w.lde, n, d, n, w.s3, w.g3, stream_)) return rc;
+    if (on(4)) {
+        const int64_t tot = n * (d / 4);
+        nce_combine_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w.g1, w.s1, w.g2, w.s2, w.g3, w.s3, a, b, coef, stats, n, d / 4, inv_tau, ga, gb);
+        MMSSL_LAUNCH_OK();
+    }
     return 0;
 }

@@ -59,6 +59,16 @@ def weights_changed() -> None:
             del _split_bufs[b]
 
 
+def refresh_weight_splits() -> None:
+    """For writers of the registered weights other than `adam` (a checkpoint load, a test copying state in) when a captured
+    graph is in use: recompute, IN PLACE, every split the graph reads (the graph itself only re-splits after its own Adam step)."""
+    weights_changed()
+    for (p_, shape, transposed) in list(_split_bufs):
+        ref = _weights.get(p_)
+        if ref is not None and ref() is not None:
+            _split(ref(), transposed)
+
+
 def _split(t, transposed: bool):
     ref = _weights.get(t.data_ptr())
     if ref is None or ref() is not t:

@@ -21,3 +21,7 @@ static inline float __bfloat162float(__nv_bfloat16 h) {
 }
 static inline unsigned short __bfloat16_as_ushort(__nv_bfloat16 h) { return h.bits; }
 static inline __nv_bfloat16 __ushort_as_bfloat16(unsigned short b) { __nv_bfloat16 r; r.bits = b; return r; }
+
+// packed pair (x in the low half), as cvt.rn.bf16x2.f32 produces it
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return __nv_bfloat162{__float2bfloat16_rn(a), __float2bfloat16_rn(b)}; }

@@ -77,6 +77,8 @@ def test_full_step_cuda_graph_replay_equals_eager():
     for k in gan.PARAMS:
         fg.D.m[k].copy_(fe.D.m[k]); fg.D.v[k].copy_(fe.D.v[k])
     fg.D.step_dev.copy_(fe.D.step_dev); fg.D.step = fe.D.step
+    from mmssl_b200 import gan_ops
+    gan_ops.refresh_weight_splits()        # the weights were overwritten from outside: the graph reads their bf16 splits in place
     g = torch.Generator().manual_seed(5)
     B, I, d = c["B"], c["I"], c["d"]
     for s in range(3):

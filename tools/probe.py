@@ -175,10 +175,12 @@ def kernels(name="baby"):
     gu, gi = torch.zeros(U, d, **f), torch.zeros(I, d, **f)
     part = torch.empty(2 * 64, **f)
     out["bpr_us"] = round(graph_time(lambda: ops.bpr(uf, itf, itf, users, pos, neg, mode=3, reg_coef=1e-8, part=part, g_u=gu, g_p=gi, g_n=gi), inner=10), 2)
-    wk = ops.InfoNCEWork(B, d, dev)
     seed = torch.ones(1, **f)
-    out["nce_fwd_us"] = round(graph_time(lambda: ops.infonce_forward(ya, uf, users, 2.0, wk, g_loss=seed), inner=10), 2)
-    out["nce_bwd_us"] = round(graph_time(lambda: ops.infonce_backward(users, 2.0, wk, gu, gu), inner=10), 2)
+    for impl in ("auto", "simt"):      # auto = tensor cores at this size (csrc/loss_tc.cu)
+        wk = ops.InfoNCEWork(B, d, dev, impl=impl)
+        tag = "tc" if wk.tc else "simt"
+        out[f"nce_fwd_{tag}_us"] = round(graph_time(lambda: ops.infonce_forward(ya, uf, users, 2.0, wk, g_loss=seed), inner=10), 2)
+        out[f"nce_bwd_{tag}_us"] = round(graph_time(lambda: ops.infonce_backward(users, 2.0, wk, gu, gu), inner=10), 2)
     s = torch.randn(U, d, **f); a2 = torch.randn(U, 2 * d, **f); o2 = torch.empty(U, d, **f)
     out["combine_fwd_us"] = round(graph_time(lambda: ops.combine_fwd(s, a2[:, :d], a2[:, d:], 1 / 3, 0.55, o2), inner=10), 2)
     out["fill_us"] = round(graph_time(lambda: gu.zero_(), inner=20), 2)
