@@ -33,7 +33,8 @@ constexpr int kNceTile = 128;
 constexpr int kNceMaxN = 2048;
 constexpr uint32_t kNceIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNceTile >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 constexpr int kNceStageBytes = 8 * kTileABytes;                     // Ai, Aj, Bj, Bi  x  hi, lo : 128 KB
-constexpr int kNceSmemBytes = kNceStageBytes + 1024 + 256;
+constexpr int kNceRows = 32, kNceRowPitch = 144;                    // epilogue staging: 32 rows x (128 B + 16 B pad) per warp, hi and lo
+constexpr int kNceSmemBytes = kNceStageBytes + 256 + 8 * 2 * kNceRows * kNceRowPitch + 1024;
 
 // bf16 pair (x in the low half) with one cvt.rn.bf16x2; its two halves widened back to fp32 are shifts
 __device__ __forceinline__ uint32_t pack_bf16(float x, float y) {
@@ -138,16 +139,21 @@ nce_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         float sum_r = 0.f, sum_b = 0.f;
+        // A warp owns 32 rows x 64 columns of every accumulator.  Its exponentials go to global memory through a shared-memory
+        // staging tile (row stride 144 B: conflict-free 128-bit accesses both ways) so that 8 lanes write one 128-byte row
+        // segment: 4 cache lines per store instruction instead of 32 (the thread-per-row stores cost 12 us, round 2 trace).
+        uint8_t* stage_hi = smem + kNceStageBytes + 256 + (warp - 2) * (2 * kNceRows * kNceRowPitch);
+        uint8_t* stage_lo = stage_hi + kNceRows * kNceRowPitch;
+        const int c0 = h * (kNceTile / 2);
 #pragma unroll 1
         for (int mat = 0; mat < 3; ++mat) {
-            uint16_t* hi = e_hi + (int64_t)mat * lde * lde + i * lde + j0;
-            uint16_t* lo = e_lo + (int64_t)mat * lde * lde + i * lde + j0;
-#pragma unroll 1
-            for (int c = h * (kNceTile / 2); c < (h + 1) * (kNceTile / 2); c += 32) {
+            float part = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < kNceTile / 2; cc += 32) {
+                const int c = c0 + cc;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mat * kNceTile + c), v);
                 uint32_t ph[16], pl[16];
-                float part = 0.f;
 #pragma unroll
                 for (int t = 0; t < 32; t += 2) {
                     float e0 = 0.f, e1 = 0.f;
@@ -162,15 +168,25 @@ nce_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                     ph[t / 2] = hp;
                     pl[t / 2] = pack_bf16(e0 - __uint_as_float(hp << 16), e1 - __uint_as_float(hp & 0xffff0000u));
                 }
-                if (mat == 0) sum_r += part; else if (mat == 1) sum_b += part;
-                if (i < lde) {      // rows up to the padded height are written (zeros beyond n): the GEMMs read them as K padding
 #pragma unroll
-                    for (int t = 0; t < 16; t += 4) {
-                        *reinterpret_cast<uint4*>(hi + c + 2 * t) = make_uint4(ph[t], ph[t + 1], ph[t + 2], ph[t + 3]);
-                        *reinterpret_cast<uint4*>(lo + c + 2 * t) = make_uint4(pl[t], pl[t + 1], pl[t + 2], pl[t + 3]);
-                    }
+                for (int t = 0; t < 16; t += 4) {
+                    *reinterpret_cast<uint4*>(stage_hi + lane * kNceRowPitch + cc * 2 + t * 4) = make_uint4(ph[t], ph[t + 1], ph[t + 2], ph[t + 3]);
+                    *reinterpret_cast<uint4*>(stage_lo + lane * kNceRowPitch + cc * 2 + t * 4) = make_uint4(pl[t], pl[t + 1], pl[t + 2], pl[t + 3]);
                 }
             }
+            if (mat == 0) sum_r += part; else if (mat == 1) sum_b += part;
+            __syncwarp();
+            // rows up to the padded height are written (zeros beyond n): the backward's GEMMs read them as K padding
+            const int64_t row_base = (int64_t)it * kNceTile + q * 32;
+            uint16_t* ghi = e_hi + (int64_t)mat * lde * lde + row_base * lde + j0 + c0;
+            uint16_t* glo = e_lo + (int64_t)mat * lde * lde + row_base * lde + j0 + c0;
+#pragma unroll
+            for (int r0 = 0; r0 < kNceRows; r0 += 4) {
+                const int r = r0 + (lane >> 3), ch = lane & 7;
+                *reinterpret_cast<uint4*>(ghi + (int64_t)r * lde + ch * 8) = *reinterpret_cast<const uint4*>(stage_hi + r * kNceRowPitch + ch * 16);
+                *reinterpret_cast<uint4*>(glo + (int64_t)r * lde + ch * 8) = *reinterpret_cast<const uint4*>(stage_lo + r * kNceRowPitch + ch * 16);
+            }
+            __syncwarp();
         }
         if (i < n) {
             stats[4 * n + (2 * jt + h) * n + i] = sum_r;
@@ -229,27 +245,29 @@ __global__ void __launch_bounds__(256) nce_combine_kernel(const float* __restric
     const int c = (int)(t - i * d4) * 4;
     const int d = d4 * 4;
     float4 xa = f4zero(), xua = f4zero(), x2 = f4zero(), x3 = f4zero();
-    for (int s0 = 0; s0 < s1; s0 += 4) {            // 8 independent loads in flight, summed in slice order
-        float4 pa[4], pu[4];
+    const bool do_a = blockIdx.y == 0;             // blockIdx.y: 0 -> ga, 1 -> gb (independent halves of the work)
+    if (do_a) {
+        for (int s0 = 0; s0 < s1; s0 += 4) {        // 12 independent loads in flight, summed in slice order
+            float4 pa[4], pu[4], p2[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const bool ok = s0 + q < s1;
-            const float* p = g1 + ((int64_t)(ok ? s0 + q : 0) * n + i) * (2 * d);
-            pa[q] = ok ? ld4(p + c) : f4zero();
-            pu[q] = ok ? ld4(p + d + c) : f4zero();
+            for (int q = 0; q < 4; ++q) {
+                const bool ok = s0 + q < s1;
+                const float* p = g1 + ((int64_t)(ok ? s0 + q : 0) * n + i) * (2 * d);
+                pa[q] = ok ? ld4(p + c) : f4zero();
+                pu[q] = ok ? ld4(p + d + c) : f4zero();
+                p2[q] = (s0 + q < s2) ? ld4(g2 + ((int64_t)(s0 + q) * n + i) * d + c) : f4zero();
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { xa = add4(xa, pa[q]); xua = add4(xua, pu[q]); x2 = add4(x2, p2[q]); }
         }
+    } else {
+        for (int s0 = 0; s0 < s3; s0 += 8) {
+            float4 p3[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { xa = add4(xa, pa[q]); xua = add4(xua, pu[q]); }
-    }
-    for (int s0 = 0; s0 < max(s2, s3); s0 += 4) {
-        float4 p2[4], p3[4];
+            for (int q = 0; q < 8; ++q) p3[q] = (s0 + q < s3) ? ld4(g3 + ((int64_t)(s0 + q) * n + i) * d + c) : f4zero();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            p2[q] = (s0 + q < s2) ? ld4(g2 + ((int64_t)(s0 + q) * n + i) * d + c) : f4zero();
-            p3[q] = (s0 + q < s3) ? ld4(g3 + ((int64_t)(s0 + q) * n + i) * d + c) : f4zero();
+            for (int q = 0; q < 8; ++q) x3 = add4(x3, p3[q]);
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { x2 = add4(x2, p2[q]); x3 = add4(x3, p3[q]); }
     }
     const float u = coef[i], v = coef[n + i], rii = stats[i], bii = stats[n + i];
     const float4 av = ld4(a + i * d + c), bv = ld4(b + i * d + c);
@@ -262,8 +280,7 @@ __global__ void __launch_bounds__(256) nce_combine_kernel(const float* __restric
     w.y = -inv_tau * x3.y + inv_tau * v * bii * av.y;
     w.z = -inv_tau * x3.z + inv_tau * v * bii * av.z;
     w.w = -inv_tau * x3.w + inv_tau * v * bii * av.w;
-    st4(ga + i * d + c, o);
-    st4(gb + i * d + c, w);
+    if (do_a) st4(ga + i * d + c, o); else st4(gb + i * d + c, w);
 }
 
 struct NceWs {
@@ -288,10 +305,15 @@ static void nce_carve(int64_t n, int d, void* base, NceWs* w) {
     w->e_hi = (uint16_t*)take(2 * 3 * lde * lde); w->e_lo = (uint16_t*)take(2 * 3 * lde * lde);
     w->op1_hi = (uint16_t*)take(2 * 2 * d * lde); w->op1_lo = (uint16_t*)take(2 * 2 * d * lde);
     w->op2_hi = (uint16_t*)take(2 * d * lde); w->op2_lo = (uint16_t*)take(2 * d * lde);
-    const int64_t f1 = mmssl_gemm_bf16x3_workspace_floats(n, 2 * d, n, &w->s1);
-    const int64_t f2 = mmssl_gemm_bf16x3_workspace_floats(n, d, n, &w->s2);
-    w->s3 = w->s2;
-    w->g1 = (float*)take(4 * f1); w->g2 = (float*)take(4 * f2); w->g3 = (float*)take(4 * f2);
+    // K slices of the backward products: the three run side by side (8 M-tiles each), so 8 slices each fill the machine; more
+    // slices only add partial-sum traffic for the combine kernel
+    int sk = 0;
+    mmssl_gemm_bf16x3_workspace_floats(n, d, n, &sk);
+    const int64_t total_kb = (n + kBlockK - 1) / kBlockK;
+    if (sk > 8) sk = 8;
+    { const int64_t per = (total_kb + sk - 1) / sk; sk = (int)((total_kb + per - 1) / per); }
+    w->s1 = w->s2 = w->s3 = sk;
+    w->g1 = (float*)take(4 * (size_t)sk * n * 2 * d); w->g2 = (float*)take(4 * (size_t)sk * n * d); w->g3 = (float*)take(4 * (size_t)sk * n * d);
     w->total = off + 256;
 }
 
@@ -381,7 +403,7 @@ extern "C" int mmssl_infonce_grad_tc(const float* a, const float* b, int64_t n, 
                                               w.lde, n, d, n, w.s3, w.g3, stream_)) return rc;
     if (on(4)) {
         const int64_t tot = n * (d / 4);
-        nce_combine_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w.g1, w.s1, w.g2, w.s2, w.g3, w.s3, a, b, coef, stats, n, d / 4, inv_tau, ga, gb);
+        nce_combine_kernel<<<dim3((unsigned)((tot + 255) / 256), 2), 256, 0, st>>>(w.g1, w.s1, w.g2, w.s2, w.g3, w.s3, a, b, coef, stats, n, d / 4, inv_tau, ga, gb);
         MMSSL_LAUNCH_OK();
     }
     return 0;
