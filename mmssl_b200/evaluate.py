@@ -58,6 +58,9 @@ class Evaluator:
             ia = ia.contiguous().clone()
         if ia.shape[0] != self.n_items or ua.shape[1] != ia.shape[1]:
             raise ValueError("embedding tables do not match the evaluator's shapes")
+        ids = torch.as_tensor(list(users_to_test) if not torch.is_tensor(users_to_test) else users_to_test)
+        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= min(self.n_users, ua.shape[0])):
+            raise ValueError("users_to_test holds an id outside [0, n_users): the ranking kernel indexes the CSR row pointers with it")
         users = torch.as_tensor(np.asarray(list(users_to_test), np.int64)).to(self.device)
         n, kmax, nk, d = users.numel(), max(self.Ks), len(self.Ks), ua.shape[1]
         dev = self.device

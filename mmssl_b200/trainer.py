@@ -117,7 +117,11 @@ class Trainer:
         self.decay = eval(args.regs)[0]                           # main.py:51-52
         self.Ks = eval(args.Ks)
         R = data.train_mat.tocsr().astype(np.float32)
+        R.sum_duplicates()             # the device GAN path reads rows as sorted, duplicate-free index lists ...
         R.sort_indices()
+        if R.nnz and not bool((R.data == 1).all()):
+            raise ValueError("train_mat must be a 0/1 interaction matrix (the reference's todense() path would use its values; "
+                             "the device path of the GAN side reads the sparsity pattern)")
         self.ui_graph_raw = R
         self.n_users, self.n_items = R.shape                      # main.py:63-64 (from train_mat, not from the json files)
         # main.py:70-74: model, .cuda(), discriminator, kaiming init of its Linear layers
@@ -197,8 +201,11 @@ class Trainer:
                 self.log("ERROR: loss is nan.")
                 raise FloatingPointError("loss is nan")                                         # main.py:439-441 exits
             if (epoch + 1) % args.verbose != 0:
+                # the reference prints its `contrastive_loss` variable here, which is initialised to 0. and never updated
+                # (main.py:326, :443): the slot always reads 0.00000 -- kept for log parity; the accumulated value is in self.history
                 self.log("Epoch %d [%.1fs]: train==[%.5f=%.5f + %.5f + %.5f  + %.5f]" % (epoch, time() - t1, loss, mf_loss, emb_loss,
-                                                                                        reg_loss, cl_loss))
+                                                                                        reg_loss, 0.0))
+                self.last_cl_loss = cl_loss
             t2 = time()
             ret = self.test(list(data.val_set.keys()), is_val=True)                            # main.py:451-452 (every epoch)
             t3 = time()
