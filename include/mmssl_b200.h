@@ -91,6 +91,9 @@ typedef struct {
  * gathers in flight, 16 = registers capped for 6 resident blocks/SM (8|16 = both with 4 blocks/SM). */
 int mmssl_spmm_csr_f32(const mmssl_csr_t* a /*host*/, int d, int nrhs, const mmssl_spmm_rhs_t* rhs /*host*/,
                        int epilogue, float alpha, int s_mode, float* partials, int64_t partials_floats, int impl, void* stream);
+/* Tuning / test knob of the software-pipelined small-graph variant (impl bit 9 = 512, spmm.cu): the grid size in blocks of 128
+ * threads; 0 (default) = as many as one device holds at once.  Every lane group walks items g, g + groups, g + 2 groups, ... */
+int mmssl_spmm_pipe_set_blocks(int blocks);
 
 /* TMA-staged variant for large power-law graphs: the X rows of the `n_hot` highest-degree columns
  * (hot_ids, by decreasing degree) are staged once per CTA into shared memory with cp.async.bulk and

@@ -6,9 +6,11 @@
 // chained MMAs at most, far below the lengths where the accumulate error shows, gemm_wide.cu).  |s / tau| <= 2, so a 1e-5
 // error in s is 2e-5 in exp(s / tau).
 //
-//   forward  nce_stats_tc_kernel: CTA (it, jt) owns the 128 x 128 tiles  S_R = A_i A_j^T,  S_B = A_i B_j^T  and  S_T = B_i A_j^T
-//            (the transposed block of a b^T that the backward needs row-major) in three TMEM accumulators; operands by TMA
-//            (SWIZZLE_128B), single-thread tcgen05.mma issue, four epilogue warps: tcgen05.ld -> exp -> row sums, diagonal,
+//   forward  nce_stats_tc_kernel: CTA (it, jt, m) owns ONE 128 x 128 tile of  S_R = A_i A_j^T (m = 0),  S_B = A_i B_j^T (1)  or
+//            S_T = B_i A_j^T (2: the transposed block of a b^T that the backward needs row-major) in a TMEM accumulator -- 192 CTAs
+//            at n = 1024, two per SM, all resident at once (the first version kept the three tiles in one CTA: 64 CTAs on 148 SMs,
+//            21.7 us, epilogue-bound); operands by TMA
+//            (SWIZZLE_128B), single-thread tcgen05.mma issue, eight epilogue warps: tcgen05.ld -> exp -> row sums, diagonal,
 //            and the exponentials themselves stored as bf16 hi / lo matrices E_R, E_B, E_T (12 MB at n = 1024: L2-resident).
 //            nce_finalize_kernel (loss.cu) turns the sums into loss rows and backward coefficients u, v as before.
 //   backward with P_ij = -(u_i + u_j) R_ij / tau (i != j), Q_ij = B_ij (-u_i + [i == j] v_i) / tau:
@@ -32,9 +34,10 @@ int nce_prepare_split_launch(const float* z1, int64_t ldz1, const float* z2, int
 constexpr int kNceTile = 128;
 constexpr int kNceMaxN = 2048;
 constexpr uint32_t kNceIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNceTile >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
-constexpr int kNceStageBytes = 8 * kTileABytes;                     // Ai, Aj, Bj, Bi  x  hi, lo : 128 KB
+constexpr int kNceStageBytes = 4 * kTileABytes;                     // row operand, column operand  x  hi, lo : 64 KB
 constexpr int kNceRows = 32, kNceRowPitch = 144;                    // epilogue staging: 32 rows x (128 B + 16 B pad) per warp, hi and lo
-constexpr int kNceSmemBytes = kNceStageBytes + 256 + 8 * 2 * kNceRows * kNceRowPitch + 1024;
+constexpr int kNceEpiBytes = 8 * 2 * kNceRows * kNceRowPitch;       // 72 KB, laid over the operand tiles (dead once the MMAs completed)
+constexpr int kNceSmemBytes = kNceEpiBytes + 256 + 1024;            // 2 CTAs per SM
 
 // bf16 pair (x in the low half) with one cvt.rn.bf16x2; its two halves widened back to fp32 are shifts
 __device__ __forceinline__ uint32_t pack_bf16(float x, float y) {
@@ -47,21 +50,51 @@ __device__ __forceinline__ float fast_exp2(float x) {      // MUFU.EX2: |x| <= 2
     return y;
 }
 
+// 32 accumulator columns of one row -> exponentials (bf16 hi / lo pairs) and their sum.  CHECK: rows / columns beyond n give 0 and
+// the diagonal element (row i == column) is stored to diag[i].
+template <bool CHECK>
+__device__ __forceinline__ float nce_exp32(const uint32_t (&v)[32], float scale, int64_t i, int64_t jbase, int64_t n, float* diag,
+                                           uint32_t (&ph)[16], uint32_t (&pl)[16]) {
+    float part = 0.f;
+#pragma unroll
+    for (int t = 0; t < 32; t += 2) {
+        float e0, e1;
+        if (CHECK) {
+            e0 = (i < n && jbase + t < n) ? fast_exp2(__uint_as_float(v[t]) * scale) : 0.f;
+            e1 = (i < n && jbase + t + 1 < n) ? fast_exp2(__uint_as_float(v[t + 1]) * scale) : 0.f;
+            if (diag != nullptr && i < n) {
+                if (i == jbase + t) diag[i] = e0;
+                if (i == jbase + t + 1) diag[i] = e1;
+            }
+        } else {
+            e0 = fast_exp2(__uint_as_float(v[t]) * scale);
+            e1 = fast_exp2(__uint_as_float(v[t + 1]) * scale);
+        }
+        part += e0 + e1;
+        const uint32_t hp = pack_bf16(e0, e1);
+        ph[t / 2] = hp;
+        pl[t / 2] = pack_bf16(e0 - __uint_as_float(hp << 16), e1 - __uint_as_float(hp & 0xffff0000u));
+    }
+    return part;
+}
+
 // stats layout (loss.cu): [diagR n][diagB n][loss n][unused n][partR ntj*n][partB ntj*n],  ntj = 2 * gridDim.y
 constexpr int kNceThreads = 320;       // warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue
 
-__global__ void __launch_bounds__(kNceThreads, 1)
+__global__ void __launch_bounds__(kNceThreads, 2)
 nce_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, int64_t n, int nkb,
                     float inv_tau, float* __restrict__ stats, uint16_t* __restrict__ e_hi, uint16_t* __restrict__ e_lo, int64_t lde) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kNceStageBytes);
+    static_assert(kNceEpiBytes >= kNceStageBytes, "staging lies over the operand tiles");
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kNceEpiBytes);
     uint64_t* empty_bar = full_bar + 1;
     uint64_t* accum_bar = empty_bar + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int it = blockIdx.x, jt = blockIdx.y;
+    const int mat = blockIdx.z;                                   // 0: S_R = A_i A_j^T   1: S_B = A_i B_j^T   2: S_T = B_i A_j^T
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
@@ -75,7 +108,7 @@ nce_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -89,14 +122,14 @@ nce_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                 mbar_wait(empty_bar, ((uint32_t)kb & 1u) ^ 1u);
                 mbar_expect_tx(full_bar, kNceStageBytes);
                 const int kx = kb * kBlockK;
-                tma_load_2d(&tm_a_hi, full_bar, smem + 0 * kTileABytes, kx, it * kNceTile, kEvictLast);   // A_i
-                tma_load_2d(&tm_a_lo, full_bar, smem + 1 * kTileABytes, kx, it * kNceTile, kEvictLast);
-                tma_load_2d(&tm_a_hi, full_bar, smem + 2 * kTileABytes, kx, jt * kNceTile, kEvictLast);   // A_j
-                tma_load_2d(&tm_a_lo, full_bar, smem + 3 * kTileABytes, kx, jt * kNceTile, kEvictLast);
-                tma_load_2d(&tm_b_hi, full_bar, smem + 4 * kTileABytes, kx, jt * kNceTile, kEvictLast);   // B_j
-                tma_load_2d(&tm_b_lo, full_bar, smem + 5 * kTileABytes, kx, jt * kNceTile, kEvictLast);
-                tma_load_2d(&tm_b_hi, full_bar, smem + 6 * kTileABytes, kx, it * kNceTile, kEvictLast);   // B_i
-                tma_load_2d(&tm_b_lo, full_bar, smem + 7 * kTileABytes, kx, it * kNceTile, kEvictLast);
+                const CUtensorMap* rh = (mat == 2) ? &tm_b_hi : &tm_a_hi;      // row operand (tile it)
+                const CUtensorMap* rl = (mat == 2) ? &tm_b_lo : &tm_a_lo;
+                const CUtensorMap* ch = (mat == 1) ? &tm_b_hi : &tm_a_hi;      // column operand (tile jt)
+                const CUtensorMap* cl = (mat == 1) ? &tm_b_lo : &tm_a_lo;
+                tma_load_2d(rh, full_bar, smem + 0 * kTileABytes, kx, it * kNceTile, kEvictLast);
+                tma_load_2d(rl, full_bar, smem + 1 * kTileABytes, kx, it * kNceTile, kEvictLast);
+                tma_load_2d(ch, full_bar, smem + 2 * kTileABytes, kx, jt * kNceTile, kEvictLast);
+                tma_load_2d(cl, full_bar, smem + 3 * kTileABytes, kx, jt * kNceTile, kEvictLast);
             }
         }
     } else if (warp == 1) {
@@ -108,22 +141,13 @@ nce_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
                     const uint32_t off = k * 32;
-                    uint64_t dsc[8];
+                    uint64_t dsc[4];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) dsc[q] = make_sw128_kmajor_desc(t0 + q * kTileABytes + off);
+                    for (int q = 0; q < 4; ++q) dsc[q] = make_sw128_kmajor_desc(t0 + q * kTileABytes + off);
                     const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                    // S_R = A_i A_j^T
-                    umma_bf16(tmem_base + 0 * kNceTile, dsc[0], dsc[2], kNceIdesc, acc);
-                    umma_bf16(tmem_base + 0 * kNceTile, dsc[0], dsc[3], kNceIdesc, 1u);
-                    umma_bf16(tmem_base + 0 * kNceTile, dsc[1], dsc[2], kNceIdesc, 1u);
-                    // S_B = A_i B_j^T
-                    umma_bf16(tmem_base + 1 * kNceTile, dsc[0], dsc[4], kNceIdesc, acc);
-                    umma_bf16(tmem_base + 1 * kNceTile, dsc[0], dsc[5], kNceIdesc, 1u);
-                    umma_bf16(tmem_base + 1 * kNceTile, dsc[1], dsc[4], kNceIdesc, 1u);
-                    // S_T = B_i A_j^T   (= the transposed block of a b^T)
-                    umma_bf16(tmem_base + 2 * kNceTile, dsc[6], dsc[2], kNceIdesc, acc);
-                    umma_bf16(tmem_base + 2 * kNceTile, dsc[6], dsc[3], kNceIdesc, 1u);
-                    umma_bf16(tmem_base + 2 * kNceTile, dsc[7], dsc[2], kNceIdesc, 1u);
+                    umma_bf16(tmem_base, dsc[0], dsc[2], kNceIdesc, acc);      // hi hi + hi lo + lo hi
+                    umma_bf16(tmem_base, dsc[0], dsc[3], kNceIdesc, 1u);
+                    umma_bf16(tmem_base, dsc[1], dsc[2], kNceIdesc, 1u);
                 }
                 umma_commit(empty_bar);
             }
@@ -138,43 +162,31 @@ nce_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         const float scale = inv_tau * 1.4426950408889634f;          // exp(x) = exp2(x log2 e)
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-        float sum_r = 0.f, sum_b = 0.f;
         // A warp owns 32 rows x 64 columns of every accumulator.  Its exponentials go to global memory through a shared-memory
         // staging tile (row stride 144 B: conflict-free 128-bit accesses both ways) so that 8 lanes write one 128-byte row
         // segment: 4 cache lines per store instruction instead of 32 (the thread-per-row stores cost 12 us, round 2 trace).
-        uint8_t* stage_hi = smem + kNceStageBytes + 256 + (warp - 2) * (2 * kNceRows * kNceRowPitch);
+        uint8_t* stage_hi = smem + (warp - 2) * (2 * kNceRows * kNceRowPitch);
         uint8_t* stage_lo = stage_hi + kNceRows * kNceRowPitch;
         const int c0 = h * (kNceTile / 2);
-#pragma unroll 1
-        for (int mat = 0; mat < 3; ++mat) {
+        const bool plain = (int64_t)(it + 1) * kNceTile <= n && (int64_t)(jt + 1) * kNceTile <= n && it != jt;   // CTA-uniform
+        {
             float part = 0.f;
 #pragma unroll
             for (int cc = 0; cc < kNceTile / 2; cc += 32) {
                 const int c = c0 + cc;
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mat * kNceTile + c), v);
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
                 uint32_t ph[16], pl[16];
-#pragma unroll
-                for (int t = 0; t < 32; t += 2) {
-                    float e0 = 0.f, e1 = 0.f;
-                    if (i < n && j0 + c + t < n) e0 = fast_exp2(__uint_as_float(v[t]) * scale);
-                    if (i < n && j0 + c + t + 1 < n) e1 = fast_exp2(__uint_as_float(v[t + 1]) * scale);
-                    part += e0 + e1;
-                    if (mat < 2 && i < n) {
-                        if (i == j0 + c + t) stats[mat * n + i] = e0;
-                        if (i == j0 + c + t + 1) stats[mat * n + i] = e1;
-                    }
-                    const uint32_t hp = pack_bf16(e0, e1);
-                    ph[t / 2] = hp;
-                    pl[t / 2] = pack_bf16(e0 - __uint_as_float(hp << 16), e1 - __uint_as_float(hp & 0xffff0000u));
-                }
+                // interior tiles off the diagonal (most of them) skip the bounds and diagonal tests: 6 instead of 11 instructions
+                // per exponential
+                if (plain) part += nce_exp32<false>(v, scale, i, j0 + c, n, nullptr, ph, pl);
+                else part += nce_exp32<true>(v, scale, i, j0 + c, n, mat < 2 ? stats + mat * n : nullptr, ph, pl);
 #pragma unroll
                 for (int t = 0; t < 16; t += 4) {
                     *reinterpret_cast<uint4*>(stage_hi + lane * kNceRowPitch + cc * 2 + t * 4) = make_uint4(ph[t], ph[t + 1], ph[t + 2], ph[t + 3]);
                     *reinterpret_cast<uint4*>(stage_lo + lane * kNceRowPitch + cc * 2 + t * 4) = make_uint4(pl[t], pl[t + 1], pl[t + 2], pl[t + 3]);
                 }
             }
-            if (mat == 0) sum_r += part; else if (mat == 1) sum_b += part;
             __syncwarp();
             // rows up to the padded height are written (zeros beyond n): the backward's GEMMs read them as K padding
             const int64_t row_base = (int64_t)it * kNceTile + q * 32;
@@ -186,17 +198,13 @@ nce_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                 *reinterpret_cast<uint4*>(ghi + (int64_t)r * lde + ch * 8) = *reinterpret_cast<const uint4*>(stage_hi + r * kNceRowPitch + ch * 16);
                 *reinterpret_cast<uint4*>(glo + (int64_t)r * lde + ch * 8) = *reinterpret_cast<const uint4*>(stage_lo + r * kNceRowPitch + ch * 16);
             }
-            __syncwarp();
-        }
-        if (i < n) {
-            stats[4 * n + (2 * jt + h) * n + i] = sum_r;
-            stats[4 * n + ntj * n + (2 * jt + h) * n + i] = sum_b;
+            if (i < n && mat < 2) stats[4 * n + mat * ntj * n + (2 * jt + h) * n + i] = part;
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128) : "memory");
     }
 }
 
@@ -354,7 +362,7 @@ static int nce_stats_tc_impl(const float* a, const float* b, int64_t n, int d, f
         attr_done = true;
     }
     const unsigned nt = (unsigned)(w.lde / kNceTile);
-    nce_stats_tc_kernel<<<dim3(nt, nt), kNceThreads, kNceSmemBytes, st>>>(ah, al, bh, bl, n, d / kBlockK, inv_tau, stats, w.e_hi, w.e_lo, w.lde);
+    nce_stats_tc_kernel<<<dim3(nt, nt, 3), kNceThreads, kNceSmemBytes, st>>>(ah, al, bh, bl, n, d / kBlockK, inv_tau, stats, w.e_hi, w.e_lo, w.lde);
     MMSSL_LAUNCH_OK();
     return nce_finalize_launch(n, 2 * (int64_t)nt, stats, coef, g_loss, loss_part, st);
 }

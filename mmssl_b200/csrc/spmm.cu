@@ -38,20 +38,16 @@ namespace mmssl {
 // at 1M x 200k because a 102 MB table shares the L2 with 670 MB of streams); 2 = additionally the column indices carry a
 // "hot" flag in the sign bit (the head of the column-degree distribution, graph.py:hot_flag_plan) and hot rows are loaded
 // with L1::evict_last, cold ones with L1::no_allocate, so that the ~200 KB of L1 serve the popular rows.
-template <int G, int C, int R, int UMUL, int MINB, bool PRE = false, int HINT = 0>
-__global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p) {
-    pdl_wait();
+// One work item, from its descriptor and the first chunk of (col, val) pairs (one per lane, 0 beyond the item's end) to the
+// stored output row.  `return` = this group is done with the item.
+template <int G, int C, int R, int UMUL, bool PRE, int HINT>
+__device__ __forceinline__ void spmm_item(const SpmmParams& p, const int4 item, int c_nxt, float v_nxt, const int lane,
+                                          const unsigned gmask) {
     constexpr int RC = R * C;
     constexpr bool PRE_ON = PRE && RC <= 2;
     constexpr int UNR0 = ((8 / RC) >= 2 ? (8 / RC) : 2) * UMUL;
     constexpr int UNR = UNR0 > G ? G : UNR0;
-    const unsigned gmask = group_mask<G>();
-    const int lane = threadIdx.x & (G - 1);
-    const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
-    int4 item = make_int4(-1, 0, 0, -1);
-    if (gid < p.n_items) item = __ldg(&p.items[gid]);
     const int row = item.x;
-    if (row < 0) return;   // whole group exits together (items are per group)
     const int begin = item.y, end = item.z;
 
     float4 pre_c[PRE_ON ? R : 1][PRE_ON ? C : 1], pre_e[PRE_ON ? R : 1][PRE_ON ? C : 1];
@@ -75,12 +71,6 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[r][c] = f4zero();
 
-    int c_nxt = 0;
-    float v_nxt = 0.f;
-    if (begin + lane < end) {
-        c_nxt = HINT ? ldg_i32_stream(p.colidx + begin + lane) : __ldg(p.colidx + begin + lane);
-        v_nxt = HINT ? ldg_f32_stream(p.vals + begin + lane) : __ldg(p.vals + begin + lane);
-    }
     for (int base = begin; base < end; base += G) {
         const int c_l = c_nxt;
         const float v_l = v_nxt;
@@ -261,6 +251,82 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
     }
 }
 
+// first chunk of an item's (col, val) pairs: one per lane
+template <int HINT>
+__device__ __forceinline__ void spmm_first_chunk(const SpmmParams& p, const int4 item, const int lane, int& c, float& v) {
+    c = 0; v = 0.f;
+    if (item.x >= 0 && item.y + lane < item.z) {
+        c = HINT ? ldg_i32_stream(p.colidx + item.y + lane) : __ldg(p.colidx + item.y + lane);
+        v = HINT ? ldg_f32_stream(p.vals + item.y + lane) : __ldg(p.vals + item.y + lane);
+    }
+}
+
+// one item per lane group (the grid covers the plan)
+template <int G, int C, int R, int UMUL, int MINB, bool PRE = false, int HINT = 0>
+__global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p) {
+    pdl_wait();
+    const unsigned gmask = group_mask<G>();
+    const int lane = threadIdx.x & (G - 1);
+    const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    int4 item = make_int4(-1, 0, 0, -1);
+    if (gid < p.n_items) item = __ldg(&p.items[gid]);
+    if (item.x < 0) return;   // whole group exits together (items are per group)
+    int c0; float v0;
+    spmm_first_chunk<HINT>(p, item, lane, c0, v0);
+    spmm_item<G, C, R, UMUL, PRE, HINT>(p, item, c0, v0, lane, gmask);
+}
+
+// Software-pipelined walk for small (latency-bound) graphs: the grid is one resident wave of lane groups and every group walks
+// items gid, gid + stride, ... .  While item k is gathered, the (col, val) chunk of item k+1 and the descriptor of item k+2 are
+// already in flight (and, PRE, the row-indexed epilogue operands of item k are requested before its gathers), so that an item
+// costs about one memory round trip (its gathers) instead of the four of the one-item kernel (descriptor -> indices ->
+// gathers -> epilogue operands), and a plan of 2.4 waves no longer pays them per wave (ncu, round 2: 66 registers -> 7 blocks
+// per SM -> 2452 blocks = 2.37 waves, SMs 62 % active).  Per-item arithmetic is spmm_item's: results are identical.
+template <int G, int C, int R, bool PRE>
+__global__ void __launch_bounds__(128) spmm_csr_pipe_kernel(const SpmmParams p) {
+    pdl_wait();
+    const unsigned gmask = group_mask<G>();
+    const int lane = threadIdx.x & (G - 1);
+    const int64_t stride = (int64_t)gridDim.x * (blockDim.x / G);
+    int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    const int4 none = make_int4(-1, 0, 0, -1);
+    int4 it0 = gid < p.n_items ? __ldg(&p.items[gid]) : none;
+    int4 it1 = gid + stride < p.n_items ? __ldg(&p.items[gid + stride]) : none;
+    int c0; float v0;
+    spmm_first_chunk<0>(p, it0, lane, c0, v0);
+    while (it0.x >= 0) {
+        int c1; float v1;
+        spmm_first_chunk<0>(p, it1, lane, c1, v1);
+        const int4 it2 = gid + 2 * stride < p.n_items ? __ldg(&p.items[gid + 2 * stride]) : none;
+        spmm_item<G, C, R, 1, PRE, 0>(p, it0, c0, v0, lane, gmask);
+        it0 = it1; c0 = c1; v0 = v1; it1 = it2; gid += stride;
+    }
+}
+
+static int g_pipe_blocks = 0;        // mmssl_spmm_pipe_set_blocks: 0 = one resident wave
+
+template <int G, int C, int R, bool PRE>
+static int launch_spmm_pipe(const SpmmParams& p, cudaStream_t stream) {
+    constexpr int T = 128;
+    static int resident = 0;                         // blocks of this instantiation one device holds at once
+    if (resident == 0) {
+        int per_sm = 0, dev = 0, sms = 0;
+        MMSSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmm_csr_pipe_kernel<G, C, R, PRE>, T, 0));
+        MMSSL_CUDA(cudaGetDevice(&dev));
+        MMSSL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        resident = per_sm * sms;
+        if (resident <= 0) return fail("mmssl_spmm_csr_f32", "pipelined kernel does not fit an SM");
+    }
+    const int64_t groups_per_block = T / G;
+    int64_t blocks = (p.n_items + groups_per_block - 1) / groups_per_block;
+    if (blocks == 0) return 0;
+    const int64_t cap = g_pipe_blocks > 0 ? g_pipe_blocks : resident;
+    if (blocks > cap) blocks = cap;
+    MMSSL_CUDA_LAUNCH((spmm_csr_pipe_kernel<G, C, R, PRE>), dim3((unsigned)blocks), dim3(T), 0, stream, p);
+    MMSSL_LAUNCH_OK();
+    return 0;
+}
+
 template <int G, int C, int R, int UMUL, int MINB, bool PRE = false, int HINT = 0>
 static int launch_spmm_v(const SpmmParams& p, cudaStream_t stream, int T) {
     const int64_t groups_per_block = T / G;
@@ -276,6 +342,7 @@ static int launch_spmm_v(const SpmmParams& p, cudaStream_t stream, int T) {
 // bit 6 (64): early epilogue-operand prefetch (only with the two policy defaults, i.e. bit 3 clear)
 template <int G, int C, int R>
 static int launch_spmm(const SpmmParams& p, cudaStream_t stream, int T, int impl) {
+    if (impl & 512) return (impl & 64) ? launch_spmm_pipe<G, C, R, true>(p, stream) : launch_spmm_pipe<G, C, R, false>(p, stream);
     if (impl & 256) return launch_spmm_v<G, C, R, 1, 6, false, 2>(p, stream, T);       // L2 streams + L1 hot / cold rows
     if (impl & 128) return launch_spmm_v<G, C, R, 1, 6, false, 1>(p, stream, T);       // L2 streams
     if ((impl & 64) && R * C <= 2 && !(impl & 8))
@@ -334,6 +401,12 @@ int fill_spmm_params(SpmmParams& p, const mmssl_csr_t* a, int d, int nrhs, const
 }  // namespace mmssl
 
 using namespace mmssl;
+
+extern "C" int mmssl_spmm_pipe_set_blocks(int blocks) {
+    MMSSL_REQUIRE(blocks >= 0, "blocks must be >= 0 (0 = one resident wave)");
+    g_pipe_blocks = blocks;
+    return 0;
+}
 
 extern "C" int mmssl_spmm_csr_f32(const mmssl_csr_t* a, int d, int nrhs, const mmssl_spmm_rhs_t* rhs, int epilogue,
                                   float alpha, int s_mode, float* partials, int64_t partials_floats, int impl,

@@ -15,6 +15,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict, Optional, Sequence, Tuple
 
+import os
+
 import torch
 
 from . import ops
@@ -62,6 +64,11 @@ class FwdState:
 
 
 
+def _prio(name: str, default: int) -> int:
+    """Stream priority of one branch of the step (0 = lowest .. -5); MMSSL_PRIO_<NAME> overrides the measured default."""
+    return int(os.environ.get("MMSSL_PRIO_" + name, default))
+
+
 class Engine:
     def __init__(self, embed_size: int, n_layers: int, head_num: int = 4, id_cat_rate: float = 0.36,
                  model_cat_rate: float = 0.55, proj_impl: str = "tc"):
@@ -102,7 +109,7 @@ class Engine:
         key = (dev.type, dev.index, "pair")
         st = self._side.get(key)
         if st is None:
-            st = torch.cuda.Stream(device=dev, priority=-1)      # twin of the critical id / GCN chain: ahead of the projection branch
+            st = torch.cuda.Stream(device=dev, priority=_prio("PAIR", -1))      # twin of the critical id / GCN chain: ahead of the projection branch
             self._side[key] = st
         main = torch.cuda.current_stream(dev)
         st.wait_stream(main)
@@ -121,7 +128,7 @@ class Engine:
         key = (dev.type, dev.index, name)
         st = self._side.get(key)
         if st is None:
-            st = torch.cuda.Stream(device=dev)
+            st = torch.cuda.Stream(device=dev, priority=_prio("FORK", 0))
             self._side[key] = st
         cur = torch.cuda.current_stream(dev)
         st.wait_stream(cur)
@@ -134,7 +141,7 @@ class Engine:
         key = (dev.type, dev.index)
         st = self._side.get(key)
         if st is None:
-            st = torch.cuda.Stream(device=dev)
+            st = torch.cuda.Stream(device=dev, priority=_prio("SIDE", 0))
             self._side[key] = st
         return st
 
@@ -358,22 +365,32 @@ class Engine:
                 t = self._spmm(g_ui, "bwd", [tu], "u", [g_ei] if k == 0 else None, cs=[g_if], alpha=inv)[0]
             return t
 
-        self._pair(dev, chain, lambda: ops.axpby(g_uf, inv, 0.0, g_eu))
         # ---- id fusion backward (Models.py:188-197)
         uvid, utid, ivid, itid = st.id_out
         g_wcat = slot(P_WCAT, P[P_WCAT])
         dwcat_args = None
-        if st.fused and d in (64, 128):
+        fused2 = st.fused and d in (64, 128)
+        if fused2:
             def fuse_bwd2(g0, zn, nrm, ya, yb, g_ya, g_yb):
                 same = ya is yb
                 oa, ob, part = ops.id_fuse2_bwd(g0, zn, nrm, ya, None if same else yb, 1.0 if same else 0.5, st.wsum_t,
                                                 self.id_rate, g_ya, g_yb, two_outputs=not same)
                 return oa, (oa if same else ob), part
 
-            (gt_uvid, gt_utid, part_u), (gt_ivid, gt_itid, part_i) = self._pair(
-                dev, lambda: fuse_bwd2(g_eu, st.zn_u, st.nrm_u, uvid, utid, g_uvid, g_utid),
-                lambda: fuse_bwd2(g_ei, st.zn_i, st.nrm_i, ivid, itid, g_ivid, g_itid))
+            # The user-side fusion backward needs only g_eu = inv * g_uf, not the chain: it runs beside the chain on the pair
+            # stream (after the chain it had to share the SMs with the weight-gradient GEMMs' 200 KB CTAs: 36 us instead of 10,
+            # round-2 trace); only the item side, which reads the chain's result g_ei, follows the chain.
+            def user_side():
+                ops.axpby(g_uf, inv, 0.0, g_eu)
+                return fuse_bwd2(g_eu, st.zn_u, st.nrm_u, uvid, utid, g_uvid, g_utid)
+
+            _, (gt_uvid, gt_utid, part_u) = self._pair(dev, chain, user_side)
+            gt_ivid, gt_itid, part_i = fuse_bwd2(g_ei, st.zn_i, st.nrm_i, ivid, itid, g_ivid, g_itid)
             dwcat_args = (part_u, part_i)
+        else:
+            self._pair(dev, chain, lambda: ops.axpby(g_uf, inv, 0.0, g_eu))
+        if fused2:
+            pass
         elif st.fused:
             d_wsum = torch.zeros(d, d, dtype=torch.float32, device=dev)
 

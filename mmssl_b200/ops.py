@@ -4,6 +4,7 @@ library kernels on torch's current CUDA stream."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -14,9 +15,11 @@ from .graph import SparseOperand
 
 EPI_NONE, EPI_SOFTMAX, EPI_SOFTMAX_BWD = 0, 1, 2
 SPMM_IMPL_LDG, SPMM_IMPL_TMA = 0, 1     # TMA = shared-memory hot rows staged by cp.async.bulk (large graphs)
+SPMM_IMPL_PIPE = 512          # software-pipelined walk of the plan by one resident wave (small graphs; | 64: early operand prefetch)
 SPMM_IMPL_BULK = 0x100000               # staged gather pipeline (csrc/spmm_bulk.cu); low 20 bits = its variant word
 SPMM_BULK_TMA = 0x10000                 # ... with one TMA bulk copy per neighbour row instead of warp-wide 16-byte cp.async
 _default_spmm_impl = SPMM_IMPL_LDG
+_small_spmm_impl = int(os.environ.get("MMSSL_SPMM_SMALL_IMPL", "0"), 0)     # experiment knob: impl for graphs under 2^21 non-zeros
 
 
 def set_default_spmm_impl(impl: int) -> None:
@@ -78,7 +81,8 @@ def spmm(a: SparseOperand, xs: Sequence[torch.Tensor], ys: Optional[Sequence[tor
                 rhs[r].y_peers[k] = int(pp)
     # split-row work area (partial sums + arrival counters), private to (operand, total width): launches
     # of different widths may run concurrently on two streams, and heavy rows need zeroed slots
-    impl = _default_spmm_impl if impl is None else impl
+    if impl is None:
+        impl = _small_spmm_impl if (_small_spmm_impl and a.nnz < (1 << 21)) else _default_spmm_impl
     if impl & SPMM_IMPL_BULK and nrhs <= 2 and not (epilogue == EPI_SOFTMAX_BWD and s_mode != 0):
         b = a.bulk_plan()
         part, counters = a.bulk_work_area(nrhs * d)
@@ -413,6 +417,11 @@ def gemm_bf16x3_wide(a_hi, a_lo, b_hi, b_lo, m, n, k, out, alpha: float = 1.0, a
 def gemm_wide_set_chunk(k_blocks: int) -> None:
     """k-blocks (64 of K) accumulated in TMEM before a pass is folded into C in fp32 (default 16; csrc/gemm_wide.cu)."""
     _lib.check(_lib_().mmssl_gemm_wide_set_chunk(int(k_blocks)))
+
+
+def spmm_pipe_set_blocks(blocks: int) -> None:
+    """Grid size (blocks of 128 threads) of the software-pipelined SpMM (impl bit SPMM_IMPL_PIPE); 0 = one resident wave."""
+    _lib.check(_lib_().mmssl_spmm_pipe_set_blocks(int(blocks)))
 
 
 def gemm_bf16x3_plan(m, n, k):

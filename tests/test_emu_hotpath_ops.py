@@ -73,6 +73,12 @@ def test_spmm_early_prefetch_variant(emu, d, nrhs, base_impl):
     Z.test_spmm_early_prefetch_variant_matches_default(d, nrhs, base_impl)
 
 
+@pytest.mark.parametrize("d,nrhs,blocks,pre", [(64, 1, 0, 0), (64, 1, 7, 64), (64, 2, 5, 0), (128, 1, 3, 64), (128, 2, 11, 0), (256, 1, 2, 64), (64, 3, 4, 0)])
+def test_spmm_pipelined_walk(emu, d, nrhs, blocks, pre):
+    from tests import test_gpu_zz_more_ops as Z
+    Z.test_spmm_pipelined_walk_matches_default(d, nrhs, blocks, pre)
+
+
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
 def test_sgemm_large_tiles(emu, ta, tb):
     from tests import test_gpu_zz_more_ops as Z

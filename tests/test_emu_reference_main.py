@@ -48,7 +48,18 @@ class _Replay(nn.Module):
         return x * m
 
 
-def test_reference_trainer_runs_on_the_drop_in_and_reproduces_its_own_trace(monkeypatch):
+@pytest.fixture
+def forget_reference_modules():
+    """Modules the test imports from the reference tree (main, utility.*, Models) must not outlive it: a later test's
+    `from utility.parser import parse_args` would otherwise get the reference's parser (and its parse of pytest's argv)."""
+    before = set(sys.modules)
+    yield
+    for k in set(sys.modules) - before:
+        if k in ("main", "Models") or k.split(".")[0] == "utility":
+            del sys.modules[k]
+
+
+def test_reference_trainer_runs_on_the_drop_in_and_reproduces_its_own_trace(forget_reference_modules, monkeypatch):
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     from make_golden import make_dataset
     from make_golden_gan import CASE as c

@@ -41,6 +41,45 @@ def test_spmm_early_prefetch_variant_matches_default(d, nrhs, base_impl):
         assert rel_err(b, a) < 1e-6        # the same operations in the same order (bitwise equal under the CPU emulator)
 
 
+@pytest.mark.parametrize("d,nrhs,blocks", [(64, 1, 0), (64, 1, 7), (64, 2, 5), (128, 1, 3), (128, 2, 11), (256, 1, 2), (64, 3, 4)])
+@pytest.mark.parametrize("pre", [0, 64])
+def test_spmm_pipelined_walk_matches_default(d, nrhs, blocks, pre):
+    """impl bit 9 (ops.SPMM_IMPL_PIPE): one resident wave of lane groups walks the plan, item k+1's indices and item k+2's
+    descriptor in flight while item k is gathered.  Per-item arithmetic is the one-item kernel's -> identical results, for every
+    epilogue, with split rows, with C aliasing Y, for grids from 2 blocks (every group walks dozens of items) to one item per
+    group (blocks = 0: a resident wave covers this small plan)."""
+    from mmssl_b200 import ops
+    g, _ = _graph(500, 300, 12000, seed=d + nrhs, heavy_rows=30)     # ~130 nnz in each of 30 rows: split, not heavy
+    assert g.fwd.n_split_rows > 0
+    torch.manual_seed(3)
+    xs = [torch.randn(300, d, device="cuda") for _ in range(nrhs)]
+    cs = [torch.randn(500, d, device="cuda") for _ in range(nrhs)]
+    sb = [torch.randn(500, d, device="cuda") for _ in range(nrhs)]
+    ysv = [torch.softmax(torch.randn(500, d, device="cuda"), -1) for _ in range(nrhs)]
+
+    def run(impl):
+        out = []
+        s = [torch.empty(500, d, device="cuda") for _ in range(nrhs)]
+        out += ops.spmm(g.fwd, xs, cs=cs, alpha=0.25, epilogue=ops.EPI_SOFTMAX, ss=s, s_mode=2, sbases=sb, impl=impl)
+        ops.spmm(g.fwd, xs, cs=cs, alpha=0.5, epilogue=ops.EPI_NONE, ss=s, s_mode=1, impl=impl)
+        out += [t.clone() for t in s]
+        out += ops.spmm(g.fwd, xs, cs=cs, alpha=0.25, epilogue=ops.EPI_SOFTMAX_BWD, ysaved=ysv, impl=impl)
+        acc = [c.clone() for c in cs]
+        ops.spmm(g.fwd, xs, acc, cs=acc, alpha=1.0, impl=impl)      # in place: C aliases Y
+        out += acc
+        out += ops.spmm(g.fwd, xs, impl=impl)
+        out += ops.spmm(g.bwd, [torch.ones(500, d, device="cuda")] * nrhs, impl=impl)      # A^T: other row-length profile
+        return out
+    want = run(4)
+    ops.spmm_pipe_set_blocks(blocks)
+    try:
+        got = run(ops.SPMM_IMPL_PIPE | pre)
+    finally:
+        ops.spmm_pipe_set_blocks(0)
+    for a, b in zip(want, got):
+        assert rel_err(b, a) < 1e-6        # the same operations in the same order (bitwise equal under the CPU emulator)
+
+
 @pytest.mark.parametrize("n,d", [(1500, 64), (2304, 128)])
 def test_infonce_beyond_one_block(n, d):
     """More rows than one 1024-block of main.py:228-246 and not a multiple of it (SURVEY 8c edge case): the reference's double

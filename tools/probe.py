@@ -187,5 +187,40 @@ def kernels(name="baby"):
     print(json.dumps(out))
 
 
+def pipe(name="baby"):
+    """The software-pipelined SpMM walk (impl bit 9) against the one-item-per-group kernel at small scale: plain products,
+    two right-hand sides, the GCN-layer forms; grid sizes from 2 to 8 blocks per SM."""
+    ds = make_dataset(name)
+    d = ds.embed_size
+    g_ui = BipartiteGraph.from_scipy(ds.ui_norm); g_iu = BipartiteGraph.from_scipy(ds.iu_norm)
+    U, I = ds.n_users, ds.n_items
+    xi = torch.randn(I, d, device=dev); yu = torch.empty(U, d, device=dev); yi = torch.empty(I, d, device=dev)
+    x2 = torch.randn(I, 2 * d, device=dev); y2 = torch.empty(U, 2 * d, device=dev)
+    su = torch.zeros(U, d, device=dev); cu = torch.randn(U, d, device=dev); ysv = torch.softmax(torch.randn(U, d, device=dev), -1)
+    out = {"config": name, "ui_items": g_ui.fwd.desc.n_items, "iu_items": g_iu.fwd.desc.n_items}
+
+    def forms(impl):
+        return {"ui": round(graph_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu], impl=impl), inner=20), 2),
+                "iu": round(graph_time(lambda: ops.spmm(g_iu.fwd, [yu], [yi], impl=impl), inner=20), 2),
+                "ui2": round(graph_time(lambda: ops.spmm(g_ui.fwd, [x2[:, :d], x2[:, d:]], [y2[:, :d], y2[:, d:]], impl=impl), inner=20), 2),
+                "gcn_fwd": round(graph_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu], epilogue=ops.EPI_SOFTMAX, ss=[su], s_mode=1, impl=impl), inner=20), 2),
+                "gcn_bwd": round(graph_time(lambda: ops.spmm(g_iu.bwd, [xi], [yu], cs=[cu], alpha=0.33, epilogue=ops.EPI_SOFTMAX_BWD,
+                                                             ysaved=[ysv], impl=impl), inner=20), 2)}
+    for impl in (4, 6, 2):
+        out[f"impl{impl}"] = forms(impl)
+    for per_sm in (0, 2, 3, 4, 6, 8):
+        ops.spmm_pipe_set_blocks(per_sm * 148)
+        for pre in (0, 64):
+            out[f"pipe_b{per_sm}_pre{pre}"] = forms(ops.SPMM_IMPL_PIPE | pre)
+    ops.spmm_pipe_set_blocks(0)
+    ya = ops.spmm(g_ui.fwd, [xi], impl=4)[0]; yb = ops.spmm(g_ui.fwd, [xi], impl=ops.SPMM_IMPL_PIPE)[0]
+    out["pipe_vs_default_max_abs_diff"] = float((ya - yb).abs().max())
+    print(json.dumps(out))
+
+
+if __name__ == "__main__" and "pipe" in sys.argv[1:]:
+    pipe("baby"); pipe("sports")
+    sys.exit(0)
+
 if __name__ == "__main__" and "kernels" in sys.argv[1:]:
     kernels("baby")
