@@ -40,6 +40,10 @@ int mmssl_csr_from_coo(const int64_t* rows, const int64_t* cols, const float* va
 /* vals[e] *= (rowsum + 1e-8)^-1/2  -- csr_norm(mean_flag=True), main.py:89-103 */
 int mmssl_csr_row_normalize(const int32_t* rowptr, int64_t n_rows, float* vals, void* stream);
 
+/* Where mmssl_spmm_plan cuts rows (tuning / test knob; applies to plans built afterwards, call before the *_cap functions):
+ * rows above split_threshold non-zeros become segments of seg_len (deterministic ordered reduction), rows above heavy_threshold
+ * segments of heavy_seg_len accumulated with vector atomics. */
+int mmssl_spmm_plan_set_cuts(int split_threshold, int seg_len, int heavy_threshold, int heavy_seg_len);
 /* nnz-balanced work plan: rows longer than 64 non-zeros are cut into 32-nnz segments (64-nnz for rows over
  * 1024, which accumulate atomically) that different lane groups process concurrently. */
 int64_t mmssl_spmm_plan_items_cap(int64_t n_rows, int64_t nnz);

@@ -134,6 +134,7 @@ _SIGS = {
     "mmssl_gemm_bf16x3_wide": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_i32, c_vp, c_i64, c_vp]),
     "mmssl_gemm_wide_set_chunk": (C.c_int, [c_i32]),
     "mmssl_spmm_pipe_set_blocks": (C.c_int, [c_i32]),
+    "mmssl_spmm_plan_set_cuts": (C.c_int, [c_i32, c_i32, c_i32, c_i32]),
     "mmssl_proj_epilogue": (C.c_int, [c_vp, c_i32, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "mmssl_wgrad_epilogue": (C.c_int, [c_vp, c_i32, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp]),
     "mmssl_colsum": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_vp, c_i32, c_vp]),

@@ -91,18 +91,20 @@ static cudaError_t carve_csr_ws(int64_t nnz, int64_t n_rows, void* base, CsrWs* 
 // Heavier rows (the head of a power-law degree distribution): segments of 64 that accumulate with
 // 128-bit float atomics into a dedicated zeroed row -- a serial reduction over hundreds of partials
 // would otherwise be the kernel's critical path.  (Summation order of those few rows is not fixed.)
-constexpr int kSplitThreshold = 64;
-constexpr int kHeavyThreshold = 1024;
-__host__ __device__ __forceinline__ int plan_seg_len(int len) { return len <= kHeavyThreshold ? 32 : 64; }
+// Defaults from the round-2 measurement (tools/probe.py plan): the kernel's duration on a small graph is its longest item --
+// an item of 64 non-zeros is 8 dependent gather batches of 8 -- so rows are cut earlier than the first version did (64 / 32).
+struct PlanCuts { int split_threshold, seg_len, heavy_threshold, heavy_seg_len; };
+static PlanCuts g_cuts = {64, 32, 1024, 64};
+__host__ __device__ __forceinline__ int plan_seg_len(int len, const PlanCuts c) { return len <= c.heavy_threshold ? c.seg_len : c.heavy_seg_len; }
 
 __global__ void plan_count_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows,
                                   int32_t* __restrict__ n_items, int32_t* __restrict__ is_split,
-                                  int32_t* __restrict__ n_segs) {
+                                  int32_t* __restrict__ n_segs, const PlanCuts cuts) {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     const int len = rowptr[r + 1] - rowptr[r];
-    const bool split = len > kSplitThreshold;
-    const int sl = plan_seg_len(len);
+    const bool split = len > cuts.split_threshold;
+    const int sl = plan_seg_len(len, cuts);
     const int segs = split ? (len + sl - 1) / sl : 0;
     n_items[r] = split ? segs : 1;
     is_split[r] = split ? 1 : 0;
@@ -112,12 +114,13 @@ __global__ void plan_count_kernel(const int32_t* __restrict__ rowptr, int64_t n_
 __global__ void plan_fill_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows,
                                  const int32_t* __restrict__ item_off, const int32_t* __restrict__ split_off,
                                  const int32_t* __restrict__ seg_off, const int32_t* __restrict__ is_split,
-                                 int4* __restrict__ items, int4* __restrict__ split_table, int32_t* __restrict__ totals) {
+                                 int4* __restrict__ items, int4* __restrict__ split_table, int32_t* __restrict__ totals,
+                                 const PlanCuts cuts) {
     const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= n_rows) return;
     const int b = rowptr[r], e = rowptr[r + 1];
-    const int sl = plan_seg_len(e - b);
+    const int sl = plan_seg_len(e - b, cuts);
     const int segs = is_split[r] ? (e - b + sl - 1) / sl : 0;
     if (!is_split[r]) {
         if (lane == 0) items[item_off[r]] = make_int4((int)r, b, e, -1);
@@ -127,7 +130,7 @@ __global__ void plan_fill_kernel(const int32_t* __restrict__ rowptr, int64_t n_r
             const int sb = b + k * sl;
             items[item_off[r] + k] = make_int4((int)r, sb, min(e, sb + sl), s);
         }
-        if (lane == 0) split_table[s] = make_int4(seg_off[r], segs, sl, (e - b) > kHeavyThreshold ? 1 : 0);
+        if (lane == 0) split_table[s] = make_int4(seg_off[r], segs, sl, (e - b) > cuts.heavy_threshold ? 1 : 0);
     }
     if (r == n_rows - 1 && lane == 0) {
         totals[0] = item_off[r] + (is_split[r] ? segs : 1);   // number of work items
@@ -280,8 +283,15 @@ extern "C" int mmssl_csr_from_coo(const int64_t* rows, const int64_t* cols, cons
     return 0;
 }
 
-extern "C" int64_t mmssl_spmm_plan_segs_cap(int64_t nnz) { return nnz / 32 + nnz / kSplitThreshold + 2; }
-extern "C" int64_t mmssl_spmm_plan_splits_cap(int64_t nnz) { return nnz / kSplitThreshold + 2; }
+extern "C" int mmssl_spmm_plan_set_cuts(int split_threshold, int seg_len, int heavy_threshold, int heavy_seg_len) {
+    MMSSL_REQUIRE(split_threshold >= 1 && seg_len >= 1 && heavy_seg_len >= 1 && heavy_threshold >= split_threshold, "bad cuts");
+    g_cuts = {split_threshold, seg_len, heavy_threshold, heavy_seg_len};
+    return 0;
+}
+static int64_t min_seg() { return g_cuts.seg_len < g_cuts.heavy_seg_len ? g_cuts.seg_len : g_cuts.heavy_seg_len; }
+// a split row of len non-zeros has <= len / seg + 1 segments and there are <= nnz / (threshold + 1) split rows
+extern "C" int64_t mmssl_spmm_plan_segs_cap(int64_t nnz) { return nnz / min_seg() + nnz / g_cuts.split_threshold + 2; }
+extern "C" int64_t mmssl_spmm_plan_splits_cap(int64_t nnz) { return nnz / g_cuts.split_threshold + 2; }
 extern "C" int64_t mmssl_spmm_plan_items_cap(int64_t n_rows, int64_t nnz) { return n_rows + mmssl_spmm_plan_segs_cap(nnz); }
 
 extern "C" int64_t mmssl_spmm_plan_workspace_bytes(int64_t n_rows) {
@@ -316,7 +326,7 @@ extern "C" int mmssl_spmm_plan(const int32_t* rowptr, int64_t n_rows, int64_t nn
     int32_t* split_off = (int32_t*)(b + 4 * arr);
     int32_t* seg_off = (int32_t*)(b + 5 * arr);
     void* cub_tmp = (void*)(b + 6 * arr);
-    plan_count_kernel<<<(unsigned)((n_rows + T - 1) / T), T, 0, stream>>>(rowptr, n_rows, n_items, is_split, n_segs);
+    plan_count_kernel<<<(unsigned)((n_rows + T - 1) / T), T, 0, stream>>>(rowptr, n_rows, n_items, is_split, n_segs, g_cuts);
     MMSSL_LAUNCH_OK();
     MMSSL_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, n_items, item_off, (int)n_rows, stream));
     MMSSL_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, is_split, split_off, (int)n_rows, stream));
@@ -324,7 +334,7 @@ extern "C" int mmssl_spmm_plan(const int32_t* rowptr, int64_t n_rows, int64_t nn
     const int64_t threads = n_rows * 32;
     plan_fill_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, stream>>>(rowptr, n_rows, item_off, split_off, seg_off,
                                                                          is_split, (int4*)items4, (int4*)split_table4,
-                                                                         totals3);
+                                                                         totals3, g_cuts);
     MMSSL_LAUNCH_OK();
     return 0;
 }

@@ -4,17 +4,22 @@
 //             dWsum += m^T dz  (one partial tile per block, reduced in a fixed order)
 // with Wsum = sum_h Wcat[h*d:(h+1)*d, :]   and dWcat[h] = dWsum for every head.
 //
-// Each block owns a tile of 64 rows and runs register-tiled (4x4 per thread) products against the
+// Each block owns a tile of TR = 32 rows and runs register-tiled (4x4 per thread) products against the
 // d x d matrix staged in shared memory, with the row-wise normalisation / its backward fused as
 // prologue / epilogue.  (A first version walked rows one by one and re-read the whole matrix from
 // shared memory per row: shared-memory-bandwidth bound, 16-34 us; this one is ~4x faster.)
+// Shared memory is 24 KB per block at d = 64 (matrix 16 KB + one 8 KB row tile; the backward keeps its second tile in the
+// matrix's place until the matrix is needed): these kernels run beside the projection GEMMs, whose two 99.5 KB CTAs leave 27 KB
+// of an SM -- with 32 / 48 KB blocks they waited for the GEMM to drain (round-2 trace: 29-44 us instead of 10-17).
 #include "common.cuh"
 #include "../../include/mmssl_b200.h"
 
 namespace mmssl {
 
 constexpr float kNormEps = 1e-12f;
-constexpr int TR = 64;   // rows per block tile; 256 threads = 16 (ty: rows ty*4..+3) x 16 (tx: columns)
+constexpr int TR = 32;          // rows per block tile
+constexpr int NTY = TR / 4;     // 128 threads = 8 (ty: rows ty*4..+3) x 16 (tx: columns)
+constexpr int NT = NTY * 16;
 
 // wsum[k][c] = sum_h wcat[h][k][c] ; wsum_t[c][k] = the same transposed
 __global__ void wsum_kernel(const float* __restrict__ wcat, int d, int heads, float* __restrict__ wsum,
@@ -58,7 +63,7 @@ __device__ __forceinline__ float row16_sum(float v) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(256) id_fuse2_fwd_kernel(const float* __restrict__ ya, int64_t lda,
+__global__ void __launch_bounds__(NT) id_fuse2_fwd_kernel(const float* __restrict__ ya, int64_t lda,
                                                            const float* __restrict__ yb, int64_t ldb, float coef,
                                                            const float* __restrict__ wsum, const float* __restrict__ e,
                                                            int64_t lde, int64_t n, float rate, float* __restrict__ out,
@@ -68,9 +73,9 @@ __global__ void __launch_bounds__(256) id_fuse2_fwd_kernel(const float* __restri
     float* Ws = sm;              // [D][D]
     float* Ms = sm + D * D;      // [TR][D]
     const int64_t r0 = blockIdx.x * (int64_t)TR;
-    for (int i = threadIdx.x; i < D * D / 4; i += 256)
+    for (int i = threadIdx.x; i < D * D / 4; i += NT)
         reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(wsum) + i);
-    for (int i = threadIdx.x; i < TR * D / 4; i += 256) {
+    for (int i = threadIdx.x; i < TR * D / 4; i += NT) {
         const int r = i / (D / 4), c = (i - r * (D / 4)) * 4;
         float4 m = f4zero();
         if (r0 + r < n) {
@@ -111,27 +116,26 @@ __global__ void __launch_bounds__(256) id_fuse2_fwd_kernel(const float* __restri
 }
 
 template <int D>
-__global__ void __launch_bounds__(256) id_fuse2_bwd_kernel(const float* __restrict__ g, int64_t ldg,
-                                                           const float* __restrict__ zn, const float* __restrict__ nrm,
-                                                           const float* __restrict__ ya, int64_t lda,
-                                                           const float* __restrict__ yb, int64_t ldb, float coef,
-                                                           const float* __restrict__ wsum_t, int64_t n, float rate,
-                                                           const float* __restrict__ ext_a, int64_t ldea,
-                                                           const float* __restrict__ ext_b, int64_t ldeb,
-                                                           float* __restrict__ out_a, int64_t ldoa,
-                                                           float* __restrict__ out_b, int64_t ldob,
-                                                           float* __restrict__ dw_part) {
+__global__ void __launch_bounds__(NT) id_fuse2_bwd_kernel(const float* __restrict__ g, int64_t ldg,
+                                                          const float* __restrict__ zn, const float* __restrict__ nrm,
+                                                          const float* __restrict__ ya, int64_t lda,
+                                                          const float* __restrict__ yb, int64_t ldb, float coef,
+                                                          const float* __restrict__ wsum_t, int64_t n, float rate,
+                                                          const float* __restrict__ ext_a, int64_t ldea,
+                                                          const float* __restrict__ ext_b, int64_t ldeb,
+                                                          float* __restrict__ out_a, int64_t ldoa,
+                                                          float* __restrict__ out_b, int64_t ldob,
+                                                          float* __restrict__ dw_part) {
     pdl_wait();
     extern __shared__ __align__(16) float sm[];
-    float* Wt = sm;                   // [D][D]: Wt[c][k] = Wsum[k][c]
-    float* Ms = sm + D * D;           // [TR][D]  m rows
-    float* Zs = Ms + TR * D;          // [TR][D]  dz rows
+    float* Zs = sm;                   // [TR][D]  dz rows
+    float* Xs = sm + TR * D;          // first [TR][D] m rows (dWsum product), then [D][D]: Wt[c][k] = Wsum[k][c] (dY product)
+    float* Ms = Xs;
+    float* Wt = Xs;
     const int64_t r0 = blockIdx.x * (int64_t)TR;
-    for (int i = threadIdx.x; i < D * D / 4; i += 256)
-        reinterpret_cast<float4*>(Wt)[i] = __ldg(reinterpret_cast<const float4*>(wsum_t) + i);
     // dz (normalize backward) and m, one 16-lane group per row: lane owns float4 slices c = cc*64 + tx*4
     const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
-    for (int rl = ty; rl < TR; rl += 16) {
+    for (int rl = ty; rl < TR; rl += NTY) {
         const int64_t row = r0 + rl;
         float4 gv[D / 64], nv[D / 64];
         float dot = 0.f;
@@ -167,6 +171,36 @@ __global__ void __launch_bounds__(256) id_fuse2_bwd_kernel(const float* __restri
         }
     }
     __syncthreads();
+    // partial dWsum tile = M^T DZ : thread owns k = kc*TR + ty*4 + i, c = cc*64 + tx*4 + j
+    float* part = dw_part + (int64_t)blockIdx.x * D * D;
+#pragma unroll 1
+    for (int kc = 0; kc < D / TR; ++kc) {
+        float acc[4][D / 64][4] = {};
+#pragma unroll 4
+        for (int r = 0; r < TR; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(Ms + r * D + kc * TR + ty * 4);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int cc = 0; cc < D / 64; ++cc) {
+                const float4 b = *reinterpret_cast<const float4*>(Zs + r * D + cc * 64 + tx * 4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][cc][0] = fmaf(av[i], b.x, acc[i][cc][0]); acc[i][cc][1] = fmaf(av[i], b.y, acc[i][cc][1]);
+                    acc[i][cc][2] = fmaf(av[i], b.z, acc[i][cc][2]); acc[i][cc][3] = fmaf(av[i], b.w, acc[i][cc][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int cc = 0; cc < D / 64; ++cc)
+                st4(part + (kc * TR + ty * 4 + i) * D + cc * 64 + tx * 4,
+                    make_float4(acc[i][cc][0], acc[i][cc][1], acc[i][cc][2], acc[i][cc][3]));
+    }
+    __syncthreads();                  // every thread is done with the m rows: the matrix takes their place
+    for (int i = threadIdx.x; i < D * D / 4; i += NT)
+        reinterpret_cast<float4*>(Wt)[i] = __ldg(reinterpret_cast<const float4*>(wsum_t) + i);
+    __syncthreads();
     // dY tile = coef * DZ * Wsum^T
     {
         float acc[4][D / 64][4] = {};
@@ -192,47 +226,23 @@ __global__ void __launch_bounds__(256) id_fuse2_bwd_kernel(const float* __restri
             }
         }
     }
-    // partial dWsum tile = M^T DZ : thread owns k = kc*64 + ty*4 + i, c = cc*64 + tx*4 + j
-    float* part = dw_part + (int64_t)blockIdx.x * D * D;
-#pragma unroll 1
-    for (int kc = 0; kc < D / 64; ++kc) {
-        float acc[4][D / 64][4] = {};
-#pragma unroll 4
-        for (int r = 0; r < TR; ++r) {
-            const float4 a = *reinterpret_cast<const float4*>(Ms + r * D + kc * 64 + ty * 4);
-            const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-            for (int cc = 0; cc < D / 64; ++cc) {
-                const float4 b = *reinterpret_cast<const float4*>(Zs + r * D + cc * 64 + tx * 4);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    acc[i][cc][0] = fmaf(av[i], b.x, acc[i][cc][0]); acc[i][cc][1] = fmaf(av[i], b.y, acc[i][cc][1]);
-                    acc[i][cc][2] = fmaf(av[i], b.z, acc[i][cc][2]); acc[i][cc][3] = fmaf(av[i], b.w, acc[i][cc][3]);
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int cc = 0; cc < D / 64; ++cc)
-                st4(part + (kc * 64 + ty * 4 + i) * D + cc * 64 + tx * 4,
-                    make_float4(acc[i][cc][0], acc[i][cc][1], acc[i][cc][2], acc[i][cc][3]));
-    }
 }
 
 // dWcat[h*d*d + i] = sum over the partial tiles of both sides (fixed order), for every head h.
-// block = 64 outputs x 4 slices of the partial-tile list; slices are combined in order.
-__global__ void __launch_bounds__(256) dwcat_reduce_kernel(const float* __restrict__ part_u, int nu,
-                                                           const float* __restrict__ part_i, int ni, int d, int heads,
-                                                           float* __restrict__ dwcat) {
+// block = 32 outputs x 32 slices of the partial-tile list (a slice walks its ~26 tiles of Baby's 829 in batches of 8 independent
+// loads); slices are combined in order.  (First version: 64 outputs x 4 slices, 13 dependent batches per thread, 7.7 us.)
+constexpr int kRedOut = 32, kRedSlices = 32;
+__global__ void __launch_bounds__(kRedOut * kRedSlices) dwcat_reduce_kernel(const float* __restrict__ part_u, int nu,
+                                                                            const float* __restrict__ part_i, int ni, int d, int heads,
+                                                                            float* __restrict__ dwcat) {
     pdl_wait();
-    __shared__ float red[4][64];
-    const int o = threadIdx.x & 63, sl = threadIdx.x >> 6;
-    const int i = blockIdx.x * 64 + o;
+    __shared__ float red[kRedSlices][kRedOut];
+    const int o = threadIdx.x % kRedOut, sl = threadIdx.x / kRedOut;
+    const int i = blockIdx.x * kRedOut + o;
     const int64_t dd = (int64_t)d * d;
     const int nt = nu + ni;
-    const int per = (nt + 3) / 4;
-    const int b0 = sl * per, b1 = min(nt, b0 + per);
+    const int per = (nt + kRedSlices - 1) / kRedSlices;
+    const int b0 = min(nt, sl * per), b1 = min(nt, b0 + per);
     float s = 0.f;
     if (i < dd) {
         int b = b0;
@@ -251,7 +261,9 @@ __global__ void __launch_bounds__(256) dwcat_reduce_kernel(const float* __restri
     red[sl][o] = s;
     __syncthreads();
     if (sl == 0 && i < dd) {
-        const float tot = ((red[0][o] + red[1][o]) + red[2][o]) + red[3][o];
+        float tot = red[0][o];
+#pragma unroll
+        for (int q = 1; q < kRedSlices; ++q) tot += red[q][o];
         for (int h = 0; h < heads; ++h) dwcat[h * dd + i] = tot;
     }
 }
@@ -276,7 +288,7 @@ static int launch_fwd(const float* ya, int64_t lda, const float* yb, int64_t ldb
     const int smem = (D * D + TR * D) * 4;
     static bool attr = false;
     if (!attr) { MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-    MMSSL_CUDA_LAUNCH((id_fuse2_fwd_kernel<D>), dim3((unsigned)((n + TR - 1) / TR)), dim3(256), smem, st, ya, lda, yb, ldb, coef, wsum, e, lde, n, rate, out, ldo, zn, nrm);
+    MMSSL_CUDA_LAUNCH((id_fuse2_fwd_kernel<D>), dim3((unsigned)((n + TR - 1) / TR)), dim3(NT), smem, st, ya, lda, yb, ldb, coef, wsum, e, lde, n, rate, out, ldo, zn, nrm);
     MMSSL_LAUNCH_OK();
     return 0;
 }
@@ -298,10 +310,10 @@ static int launch_bwd(const float* g, int64_t ldg, const float* zn, const float*
                       const float* yb, int64_t ldb, float coef, const float* wsum_t, int64_t n, float rate, const float* ext_a,
                       int64_t ldea, const float* ext_b, int64_t ldeb, float* out_a, int64_t ldoa, float* out_b, int64_t ldob,
                       float* dw_part, cudaStream_t st) {
-    const int smem = (D * D + 2 * TR * D) * 4;
+    const int smem = (TR * D + (D * D > TR * D ? D * D : TR * D)) * 4;
     static bool attr = false;
     if (!attr) { MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-    MMSSL_CUDA_LAUNCH((id_fuse2_bwd_kernel<D>), dim3((unsigned)((n + TR - 1) / TR)), dim3(256), smem, st, g, ldg, zn, nrm, ya, lda, yb, ldb, coef, wsum_t, n, rate,
+    MMSSL_CUDA_LAUNCH((id_fuse2_bwd_kernel<D>), dim3((unsigned)((n + TR - 1) / TR)), dim3(NT), smem, st, g, ldg, zn, nrm, ya, lda, yb, ldb, coef, wsum_t, n, rate,
                                                                             ext_a, ldea, ext_b, ldeb, out_a, ldoa, out_b, ldob, dw_part);
     MMSSL_LAUNCH_OK();
     return 0;
@@ -326,7 +338,7 @@ extern "C" int mmssl_id_fuse2_bwd(const float* g, int64_t ldg, const float* zn, 
 extern "C" int mmssl_dwcat_reduce(const float* part_u, int nu, const float* part_i, int ni, int d, int heads, float* dwcat,
                                   void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
-    MMSSL_CUDA_LAUNCH((dwcat_reduce_kernel), dim3((d * d + 63) / 64), dim3(256), 0, st, part_u, nu, part_i, ni, d, heads, dwcat);
+    MMSSL_CUDA_LAUNCH((dwcat_reduce_kernel), dim3((d * d + kRedOut - 1) / kRedOut), dim3(kRedOut * kRedSlices), 0, st, part_u, nu, part_i, ni, d, heads, dwcat);
     MMSSL_LAUNCH_OK();
     return 0;
 }

@@ -24,6 +24,19 @@ from . import _lib
 from ._lib import CsrDesc, ptr, stream
 
 
+_cuts_applied = False
+
+
+def _env_cuts(lib) -> None:
+    """MMSSL_SPMM_CUTS="split_threshold,seg_len,heavy_threshold,heavy_seg_len": experiment knob for where the plan cuts rows."""
+    global _cuts_applied
+    if not _cuts_applied:
+        _cuts_applied = True
+        v = os.environ.get("MMSSL_SPMM_CUTS")
+        if v:
+            _lib.check(lib.mmssl_spmm_plan_set_cuts(*[int(x) for x in v.split(",")]))
+
+
 class SparseOperand:
     """CSR matrix + SpMM work plan living on one CUDA device."""
 
@@ -50,6 +63,7 @@ class SparseOperand:
         _lib.check(lib.mmssl_csr_from_coo(ptr(rows), ptr(cols), ptr(vals), nnz, n_rows, n_cols, int(transpose),
                                           ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), ptr(ws), ws_bytes, stream()))
         # work plan
+        _env_cuts(lib)
         self.items_cap = lib.mmssl_spmm_plan_items_cap(n_rows, nnz)
         self.splits_cap = lib.mmssl_spmm_plan_splits_cap(nnz)
         self.segs_cap = lib.mmssl_spmm_plan_segs_cap(nnz)

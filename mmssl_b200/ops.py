@@ -419,6 +419,11 @@ def gemm_wide_set_chunk(k_blocks: int) -> None:
     _lib.check(_lib_().mmssl_gemm_wide_set_chunk(int(k_blocks)))
 
 
+def spmm_plan_set_cuts(split_threshold: int, seg_len: int, heavy_threshold: int = 1024, heavy_seg_len: int = 64) -> None:
+    """Where the SpMM work plan cuts rows (csrc/graph.cu); applies to graphs built afterwards."""
+    _lib.check(_lib_().mmssl_spmm_plan_set_cuts(int(split_threshold), int(seg_len), int(heavy_threshold), int(heavy_seg_len)))
+
+
 def spmm_pipe_set_blocks(blocks: int) -> None:
     """Grid size (blocks of 128 threads) of the software-pipelined SpMM (impl bit SPMM_IMPL_PIPE); 0 = one resident wave."""
     _lib.check(_lib_().mmssl_spmm_pipe_set_blocks(int(blocks)))

@@ -79,6 +79,12 @@ def test_spmm_pipelined_walk(emu, d, nrhs, blocks, pre):
     Z.test_spmm_pipelined_walk_matches_default(d, nrhs, blocks, pre)
 
 
+@pytest.mark.parametrize("cuts,d,nrhs", [((16, 8, 64, 16), 64, 1), ((32, 16, 1024, 64), 128, 2), ((24, 24, 48, 5), 256, 1), ((16, 8, 64, 16), 128, 2)])
+def test_spmm_plan_cuts(emu, cuts, d, nrhs):
+    from tests import test_gpu_zz_more_ops as Z
+    Z.test_spmm_plan_cuts(cuts, d, nrhs)
+
+
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
 def test_sgemm_large_tiles(emu, ta, tb):
     from tests import test_gpu_zz_more_ops as Z

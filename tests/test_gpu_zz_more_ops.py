@@ -80,6 +80,33 @@ def test_spmm_pipelined_walk_matches_default(d, nrhs, blocks, pre):
         assert rel_err(b, a) < 1e-6        # the same operations in the same order (bitwise equal under the CPU emulator)
 
 
+@pytest.mark.parametrize("cuts", [(16, 8, 64, 16), (32, 16, 1024, 64), (24, 24, 48, 5), (64, 32, 1024, 64)])
+@pytest.mark.parametrize("d,nrhs", [(64, 1), (128, 2), (256, 1)])
+def test_spmm_plan_cuts(cuts, d, nrhs):
+    """ops.spmm_plan_set_cuts: wherever the plan cuts rows (split threshold, segment length, heavy threshold, heavy segment length)
+    the product is the same; ordered reductions are deterministic, both operands of the graph, epilogue included."""
+    from mmssl_b200 import ops
+    ops.spmm_plan_set_cuts(*cuts)
+    try:
+        g, ref = _graph(700, 300, 30000, seed=d + nrhs + cuts[0], heavy_rows=25)     # ~400 nnz in each of 25 rows
+        assert g.fwd.n_split_rows >= 25
+        torch.manual_seed(5)
+        xs = [torch.randn(300, d, device="cuda") for _ in range(nrhs)]
+        cs = [torch.randn(700, d, device="cuda") for _ in range(nrhs)]
+        for x, y in zip(xs, ops.spmm(g.fwd, xs)):
+            assert rel_err(y, torch.from_numpy(ref @ x.double().cpu().numpy())) < 3e-6
+        xt = torch.randn(700, d, device="cuda")
+        assert rel_err(ops.spmm(g.bwd, [xt])[0], torch.from_numpy(ref.T @ xt.double().cpu().numpy())) < 3e-6
+        got = ops.spmm(g.fwd, xs, cs=cs, alpha=0.5, epilogue=ops.EPI_SOFTMAX)
+        for x, c, y in zip(xs, cs, got):
+            want = torch.softmax(torch.from_numpy(ref @ x.double().cpu().numpy()) + 0.5 * c.double().cpu(), -1)
+            assert rel_err(y, want) < 3e-5
+        if cuts[2] >= 1024:      # no atomically reduced rows: bitwise repeatable
+            assert torch.equal(ops.spmm(g.fwd, xs)[0], ops.spmm(g.fwd, xs)[0])
+    finally:
+        ops.spmm_plan_set_cuts(64, 32, 1024, 64)
+
+
 @pytest.mark.parametrize("n,d", [(1500, 64), (2304, 128)])
 def test_infonce_beyond_one_block(n, d):
     """More rows than one 1024-block of main.py:228-246 and not a multiple of it (SURVEY 8c edge case): the reference's double

@@ -218,6 +218,42 @@ def pipe(name="baby"):
     print(json.dumps(out))
 
 
+def plan(name="baby"):
+    """Where the work plan cuts rows (ops.spmm_plan_set_cuts): the longest item is the kernel's critical path on a small graph."""
+    ds = make_dataset(name)
+    d = ds.embed_size
+    U, I = ds.n_users, ds.n_items
+    xi = torch.randn(I, d, device=dev); yu = torch.empty(U, d, device=dev); yi = torch.empty(I, d, device=dev)
+    x2 = torch.randn(I, 2 * d, device=dev); y2 = torch.empty(U, 2 * d, device=dev)
+    su = torch.zeros(U, d, device=dev); cu = torch.randn(U, d, device=dev); ysv = torch.softmax(torch.randn(U, d, device=dev), -1)
+    out = {"config": name}
+    ref = None
+    for cuts in ((64, 32, 1024, 64), (48, 24, 1024, 64), (32, 32, 1024, 64), (32, 16, 1024, 64), (32, 16, 512, 32), (24, 12, 512, 32), (16, 16, 512, 32),
+                 (16, 8, 512, 32), (8, 8, 256, 16)):
+        ops.spmm_plan_set_cuts(*cuts)
+        g_ui = BipartiteGraph.from_scipy(ds.ui_norm); g_iu = BipartiteGraph.from_scipy(ds.iu_norm)
+        r = {"ui_items": g_ui.fwd.desc.n_items, "iu_items": g_iu.fwd.desc.n_items, "ui_split": g_ui.fwd.n_split_rows, "iu_split": g_iu.fwd.n_split_rows}
+        for impl in (4, 68):
+            r[f"impl{impl}"] = {
+                "ui": round(graph_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu], impl=impl), inner=20), 2),
+                "iu": round(graph_time(lambda: ops.spmm(g_iu.fwd, [yu], [yi], impl=impl), inner=20), 2),
+                "ui2": round(graph_time(lambda: ops.spmm(g_ui.fwd, [x2[:, :d], x2[:, d:]], [y2[:, :d], y2[:, d:]], impl=impl), inner=20), 2),
+                "gcn_fwd": round(graph_time(lambda: ops.spmm(g_ui.fwd, [xi], [yu], epilogue=ops.EPI_SOFTMAX, ss=[su], s_mode=1, impl=impl), inner=20), 2),
+                "gcn_bwd": round(graph_time(lambda: ops.spmm(g_iu.bwd, [xi], [yu], cs=[cu], alpha=0.33, epilogue=ops.EPI_SOFTMAX_BWD,
+                                                             ysaved=[ysv], impl=impl), inner=20), 2)}
+        y = ops.spmm(g_ui.fwd, [xi], impl=4)[0]
+        if ref is None:
+            ref = y.clone()
+        r["max_abs_diff_vs_first"] = float((y - ref).abs().max())
+        out["cuts_%d_%d_%d_%d" % cuts] = r
+    ops.spmm_plan_set_cuts(64, 32, 1024, 64)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__" and "plan" in sys.argv[1:]:
+    plan("baby"); plan("sports")
+    sys.exit(0)
+
 if __name__ == "__main__" and "pipe" in sys.argv[1:]:
     pipe("baby"); pipe("sports")
     sys.exit(0)
