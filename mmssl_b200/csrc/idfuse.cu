@@ -11,6 +11,8 @@
 // Shared memory is 24 KB per block at d = 64 (matrix 16 KB + one 8 KB row tile; the backward keeps its second tile in the
 // matrix's place until the matrix is needed): these kernels run beside the projection GEMMs, whose two 99.5 KB CTAs leave 27 KB
 // of an SM -- with 32 / 48 KB blocks they waited for the GEMM to drain (round-2 trace: 29-44 us instead of 10-17).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/mmssl_b200.h"
 
@@ -279,6 +281,11 @@ extern "C" int mmssl_wsum(const float* wcat, int d, int heads, float* wsum, floa
     return 0;
 }
 
+static int idfuse_carveout() {          // percent of the SM's L1 / shared array; MMSSL_IDFUSE_CARVEOUT overrides (experiment knob)
+    const char* e = getenv("MMSSL_IDFUSE_CARVEOUT");
+    return e ? atoi(e) : (int)cudaSharedmemCarveoutMaxShared;
+}
+
 extern "C" int mmssl_id_fuse2_blocks(int64_t n) { return (int)((n + TR - 1) / TR); }
 
 template <int D>
@@ -287,7 +294,13 @@ static int launch_fwd(const float* ya, int64_t lda, const float* yb, int64_t ldb
                       cudaStream_t st) {
     const int smem = (D * D + TR * D) * 4;
     static bool attr = false;
-    if (!attr) { MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    if (!attr) {
+        MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        // the same shared-memory configuration of the SM as the projection GEMMs': a kernel that prefers another carve-out
+        // waits until the SM is empty before its blocks can be placed there
+        MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_fwd_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, idfuse_carveout()));
+        attr = true;
+    }
     MMSSL_CUDA_LAUNCH((id_fuse2_fwd_kernel<D>), dim3((unsigned)((n + TR - 1) / TR)), dim3(NT), smem, st, ya, lda, yb, ldb, coef, wsum, e, lde, n, rate, out, ldo, zn, nrm);
     MMSSL_LAUNCH_OK();
     return 0;
@@ -312,7 +325,11 @@ static int launch_bwd(const float* g, int64_t ldg, const float* zn, const float*
                       float* dw_part, cudaStream_t st) {
     const int smem = (TR * D + (D * D > TR * D ? D * D : TR * D)) * 4;
     static bool attr = false;
-    if (!attr) { MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    if (!attr) {
+        MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_bwd_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, idfuse_carveout()));
+        attr = true;
+    }
     MMSSL_CUDA_LAUNCH((id_fuse2_bwd_kernel<D>), dim3((unsigned)((n + TR - 1) / TR)), dim3(NT), smem, st, g, ldg, zn, nrm, ya, lda, yb, ldb, coef, wsum_t, n, rate,
                                                                             ext_a, ldea, ext_b, ldeb, out_a, ldoa, out_b, ldob, dw_part);
     MMSSL_LAUNCH_OK();

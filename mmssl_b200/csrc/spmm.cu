@@ -22,6 +22,8 @@
 //    peer-mapped tables: the all-gather of the row-sharded scheme is part of the epilogue.
 //  * fused epilogues: + alpha*C[row], row softmax over d (last GCN layer, Models.py:203-204),
 //    softmax backward y*(g - <g,y>), running layer sum S (+)= out (Models.py:213-214).
+#include <cstdlib>
+
 #include "spmm_common.cuh"
 
 namespace mmssl {
@@ -339,6 +341,12 @@ static int launch_spmm_v(const SpmmParams& p, cudaStream_t stream, int T) {
     const int64_t blocks = (p.n_items + groups_per_block - 1) / groups_per_block;
     if (blocks == 0) return 0;
     if (blocks > 0x7fffffffll) return fail("mmssl_spmm_csr_f32", "grid too large");
+    static bool attr = false;
+    if (!attr) {                     // MMSSL_SPMM_CARVEOUT (percent): experiment knob, the SM's shared-memory configuration this kernel asks for
+        if (const char* e = getenv("MMSSL_SPMM_CARVEOUT"))
+            MMSSL_CUDA(cudaFuncSetAttribute(spmm_csr_kernel<G, C, R, UMUL, MINB, PRE, HINT>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+        attr = true;
+    }
     MMSSL_CUDA_LAUNCH((spmm_csr_kernel<G, C, R, UMUL, MINB, PRE, HINT>), dim3((unsigned)blocks), dim3(T), 0, stream, p);
     MMSSL_LAUNCH_OK();
     return 0;
