@@ -137,6 +137,15 @@ class Engine:
         fn_a()
         cur.wait_stream(st)
 
+    def _named_stream(self, dev, name: str) -> torch.cuda.Stream:
+        """One more branch of the step (the caller forks it from and joins it into the main stream)."""
+        key = (dev.type, dev.index, name)
+        st = self._side.get(key)
+        if st is None:
+            st = torch.cuda.Stream(device=dev, priority=_prio(name.upper(), 0))
+            self._side[key] = st
+        return st
+
     def _side_stream(self, dev) -> torch.cuda.Stream:
         key = (dev.type, dev.index)
         st = self._side.get(key)

@@ -130,8 +130,13 @@ class HotStep:
             main.wait_stream(side)
         nce1 = parts[0]
         nce2 = parts[0] if self.alias_id else parts[1]
-        ops.loss_assemble(bpr_part, n_bpr, self.batch, reg_coef, st.sumsq_u, st.sumsq_i, 0.5 * cfg.feat_reg_decay / self.I,
-                          nce1, nce2, self.batch, cfg.cl_rate, self.out5)
+        # the five loss VALUES feed nothing of the backward: assembled on a stream of their own, joined at the end of the step
+        loss_st = self.engine._named_stream(dev, "loss") if self.engine.two_streams else main
+        if loss_st is not main:
+            loss_st.wait_stream(main)
+        with torch.cuda.stream(loss_st):
+            ops.loss_assemble(bpr_part, n_bpr, self.batch, reg_coef, st.sumsq_u, st.sumsq_i, 0.5 * cfg.feat_reg_decay / self.I,
+                              nce1, nce2, self.batch, cfg.cl_rate, self.out5)
         extra = self.post_forward(outs, st) if self.post_forward is not None else (None, None, None, None)
         grads = [self.g_uf, self.g_if, extra[0], extra[1], extra[2], extra[3],
                  self.g_uvid if st.fused else None, (None if self.alias_id else self.g_utid) if st.fused else None, None, None]
@@ -143,6 +148,8 @@ class HotStep:
             keys = list(LIVE)
             ops.adamw([self.P[k] for k in keys], [self.grads[k] for k in keys], [self.m[k] for k in keys],
                       [self.v[k] for k in keys], self.step_dev, cfg.lr, cfg.beta1, cfg.beta2, cfg.eps, cfg.weight_decay)
+        if loss_st is not main:
+            main.wait_stream(loss_st)
         return self.out5
 
     # ------------------------------------------------------------------ CUDA graph
