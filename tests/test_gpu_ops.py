@@ -139,7 +139,10 @@ def test_spmm_tma_hot_rows(d, nrhs):
     a = ops.spmm(g.fwd, xs, cs=cs, alpha=0.5, epilogue=ops.EPI_SOFTMAX, impl=0)
     b = ops.spmm(g.fwd, xs, cs=cs, alpha=0.5, epilogue=ops.EPI_SOFTMAX, impl=ops.SPMM_IMPL_TMA)
     for u, w in zip(a, b):
-        assert rel_err(w, u) < 1e-5
+        # the three heavy rows (~6.7k non-zeros, |logit| ~ 80) are reduced with float atomics in arrival order: an fp32 sum of
+        # 6.7k terms moves by ~3e-4 between orders, and a softmax output by up to a quarter of that (measured on B200: 1.1e-5 in
+        # the suite, 7e-5 under compute-sanitizer's timing).  The plain products above are held to 1e-5.
+        assert rel_err(w, u) < 2e-4
     yt = ops.spmm(g.bwd, [torch.randn(n_rows, d, device="cuda")], impl=ops.SPMM_IMPL_TMA)[0]   # A^T: hot set = heavy rows of A
     assert yt.shape == (n_cols, d) and torch.isfinite(yt).all()
 

@@ -181,6 +181,8 @@ def test_spmm_bulk_heavy_rows_and_zipf_columns():
         for _ in range(2):
             y = ops.spmm(g.fwd, [x], cs=[cs], alpha=0.5, epilogue=ops.EPI_SOFTMAX, impl=_bulk(tma=_))[0]
             want = torch.softmax(torch.from_numpy(ref @ x.double().cpu().numpy()) + 0.5 * cs.double().cpu(), -1)
-            assert rel_err(y, want) < 1e-5
+            # heavy rows (~6.7k non-zeros, |logit| ~ 80) summed with float atomics in arrival order: the fp32 sum moves by ~3e-4
+            # between orders and a softmax output by up to a quarter of that (7e-5 under compute-sanitizer's timing)
+            assert rel_err(y, want) < 2e-4
         yt = ops.spmm(g.bwd, [torch.ones(n_rows, d, device="cuda")], impl=_bulk())[0]
         assert rel_err(yt, torch.from_numpy(np.asarray(ref.T.sum(1))).expand(-1, d)) < 1e-5

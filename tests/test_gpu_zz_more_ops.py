@@ -100,7 +100,7 @@ def test_spmm_plan_cuts(cuts, d, nrhs):
         got = ops.spmm(g.fwd, xs, cs=cs, alpha=0.5, epilogue=ops.EPI_SOFTMAX)
         for x, c, y in zip(xs, cs, got):
             want = torch.softmax(torch.from_numpy(ref @ x.double().cpu().numpy()) + 0.5 * c.double().cpu(), -1)
-            assert rel_err(y, want) < 3e-5
+            assert rel_err(y, want) < 1e-4      # ~400-term rows, atomically reduced under the small cuts: order-dependent fp32 sums
         if cuts[2] >= 1024:      # no atomically reduced rows: bitwise repeatable
             assert torch.equal(ops.spmm(g.fwd, xs)[0], ops.spmm(g.fwd, xs)[0])
     finally:
