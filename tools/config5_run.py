@@ -2,7 +2,7 @@
 row-sharded whole hot step on the GPUs of one box.  Everything is generated ON THE DEVICE, per rank: the host
 generator of mmssl_b200/synthetic.py would take minutes per rank at this size.
 
-    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/config5_run.py [--users N --items N --edges N --d D]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/config5_run.py [--users N --items N --edges N --embed-size D]
 
 Every rank draws the same edge list (same seed): user degrees ~ lognormal(sigma = 1), item endpoints ~ Zipf(1.0) over a random
 permutation, duplicate (u, i) pairs dropped (so the edge count ends slightly below the request); values = the reference's
@@ -25,7 +25,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--users", type=int, default=10_000_000)
 ap.add_argument("--items", type=int, default=1_000_000)
 ap.add_argument("--edges", type=int, default=200_000_000)
-ap.add_argument("--d", type=int, default=256)
+ap.add_argument("--embed-size", dest="d", type=int, default=256)
 ap.add_argument("--dv", type=int, default=4096)
 ap.add_argument("--dt", type=int, default=1024)
 ap.add_argument("--layers", type=int, default=2)

@@ -10,7 +10,7 @@ run() { local t=$1 log=$2; shift 2; echo "== $* (timeout ${t}s)" | tee -a gpurun
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29571"
 nvidia-smi --query-gpu=index,name,memory.total --format=csv > gpurun_out/${TAG}_gpus.txt 2>&1
 if [ "$WHAT" != full ]; then
-  run 300 ${TAG}_small.json $T tools/config5_run.py --users 400000 --items 80000 --edges 6000000 --d 256 --dv 512 --dt 256 --steps 5
+  run 300 ${TAG}_small.json $T tools/config5_run.py --users 400000 --items 80000 --edges 6000000 --embed-size 256 --dv 512 --dt 256 --steps 5
 fi
 if [ "$WHAT" != small ]; then
   run 600 ${TAG}_full.json $T tools/config5_run.py --steps 5
