@@ -4,7 +4,7 @@
 //             dWsum += m^T dz  (one partial tile per block, reduced in a fixed order)
 // with Wsum = sum_h Wcat[h*d:(h+1)*d, :]   and dWcat[h] = dWsum for every head.
 //
-// Each block owns a tile of TR = 32 rows and runs register-tiled (4x4 per thread) products against the
+// Each block owns a tile of TR = 32 or 64 rows and runs register-tiled (4x4 per thread) products against the
 // d x d matrix staged in shared memory, with the row-wise normalisation / its backward fused as
 // prologue / epilogue.  (A first version walked rows one by one and re-read the whole matrix from
 // shared memory per row: shared-memory-bandwidth bound, 16-34 us; this one is ~4x faster.)
@@ -19,9 +19,11 @@
 namespace mmssl {
 
 constexpr float kNormEps = 1e-12f;
-constexpr int TR = 32;          // rows per block tile
-constexpr int NTY = TR / 4;     // 128 threads = 8 (ty: rows ty*4..+3) x 16 (tx: columns)
-constexpr int NT = NTY * 16;
+// rows per block tile TR (template parameter): 32 for tables under kSmallRows rows (latency-bound: more, smaller blocks; 24 KB of
+// shared memory at d = 64), 64 above (throughput-bound: half as many matrix reloads and partial dWsum tiles -- at 1M rows, d = 128
+// the 32-row tiles cost 2 GB more of partial-tile traffic).  threads = (TR / 4) (ty: rows ty*4..+3) x 16 (tx: columns)
+constexpr int64_t kSmallRows = 100000;
+__host__ __device__ constexpr int tile_rows(int64_t n) { return n < kSmallRows ? 32 : 64; }
 
 // wsum[k][c] = sum_h wcat[h][k][c] ; wsum_t[c][k] = the same transposed
 __global__ void wsum_kernel(const float* __restrict__ wcat, int d, int heads, float* __restrict__ wsum,
@@ -64,13 +66,14 @@ __device__ __forceinline__ float row16_sum(float v) {
     return v;
 }
 
-template <int D>
-__global__ void __launch_bounds__(NT) id_fuse2_fwd_kernel(const float* __restrict__ ya, int64_t lda,
+template <int D, int TR>
+__global__ void __launch_bounds__(TR * 4) id_fuse2_fwd_kernel(const float* __restrict__ ya, int64_t lda,
                                                            const float* __restrict__ yb, int64_t ldb, float coef,
                                                            const float* __restrict__ wsum, const float* __restrict__ e,
                                                            int64_t lde, int64_t n, float rate, float* __restrict__ out,
                                                            int64_t ldo, float* __restrict__ zn, float* __restrict__ nrm) {
     pdl_wait();
+    constexpr int NT = TR * 4;
     extern __shared__ __align__(16) float sm[];
     float* Ws = sm;              // [D][D]
     float* Ms = sm + D * D;      // [TR][D]
@@ -117,8 +120,8 @@ __global__ void __launch_bounds__(NT) id_fuse2_fwd_kernel(const float* __restric
     }
 }
 
-template <int D>
-__global__ void __launch_bounds__(NT) id_fuse2_bwd_kernel(const float* __restrict__ g, int64_t ldg,
+template <int D, int TR>
+__global__ void __launch_bounds__(TR * 4) id_fuse2_bwd_kernel(const float* __restrict__ g, int64_t ldg,
                                                           const float* __restrict__ zn, const float* __restrict__ nrm,
                                                           const float* __restrict__ ya, int64_t lda,
                                                           const float* __restrict__ yb, int64_t ldb, float coef,
@@ -129,6 +132,7 @@ __global__ void __launch_bounds__(NT) id_fuse2_bwd_kernel(const float* __restric
                                                           float* __restrict__ out_b, int64_t ldob,
                                                           float* __restrict__ dw_part) {
     pdl_wait();
+    constexpr int NTY = TR / 4, NT = TR * 4;
     extern __shared__ __align__(16) float sm[];
     float* Zs = sm;                   // [TR][D]  dz rows
     float* Xs = sm + TR * D;          // first [TR][D] m rows (dWsum product), then [D][D]: Wt[c][k] = Wsum[k][c] (dY product)
@@ -286,22 +290,30 @@ static int idfuse_carveout() {          // percent of the SM's L1 / shared array
     return e ? atoi(e) : (int)cudaSharedmemCarveoutDefault;
 }
 
-extern "C" int mmssl_id_fuse2_blocks(int64_t n) { return (int)((n + TR - 1) / TR); }
+extern "C" int mmssl_id_fuse2_blocks(int64_t n) { return (int)((n + tile_rows(n) - 1) / tile_rows(n)); }
 
-template <int D>
-static int launch_fwd(const float* ya, int64_t lda, const float* yb, int64_t ldb, float coef, const float* wsum,
+template <int D, int TR>
+static int launch_fwd_t(const float* ya, int64_t lda, const float* yb, int64_t ldb, float coef, const float* wsum,
                       const float* e, int64_t lde, int64_t n, float rate, float* out, int64_t ldo, float* zn, float* nrm,
                       cudaStream_t st) {
     const int smem = (D * D + TR * D) * 4;
     static bool attr = false;
     if (!attr) {
-        MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_fwd_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, idfuse_carveout()));
+        MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_fwd_kernel<D, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_fwd_kernel<D, TR>, cudaFuncAttributePreferredSharedMemoryCarveout, idfuse_carveout()));
         attr = true;
     }
-    MMSSL_CUDA_LAUNCH((id_fuse2_fwd_kernel<D>), dim3((unsigned)((n + TR - 1) / TR)), dim3(NT), smem, st, ya, lda, yb, ldb, coef, wsum, e, lde, n, rate, out, ldo, zn, nrm);
+    MMSSL_CUDA_LAUNCH((id_fuse2_fwd_kernel<D, TR>), dim3((unsigned)((n + TR - 1) / TR)), dim3(TR * 4), smem, st, ya, lda, yb, ldb, coef, wsum, e, lde, n, rate, out, ldo, zn, nrm);
     MMSSL_LAUNCH_OK();
     return 0;
+}
+
+template <int D>
+static int launch_fwd(const float* ya, int64_t lda, const float* yb, int64_t ldb, float coef, const float* wsum,
+                      const float* e, int64_t lde, int64_t n, float rate, float* out, int64_t ldo, float* zn, float* nrm,
+                      cudaStream_t st) {
+    if (tile_rows(n) == 32) return launch_fwd_t<D, 32>(ya, lda, yb, ldb, coef, wsum, e, lde, n, rate, out, ldo, zn, nrm, st);
+    return launch_fwd_t<D, 64>(ya, lda, yb, ldb, coef, wsum, e, lde, n, rate, out, ldo, zn, nrm, st);
 }
 
 extern "C" int mmssl_id_fuse2_fwd(const float* ya, int64_t lda, const float* yb, int64_t ldb, float coef, const float* wsum,
@@ -316,22 +328,32 @@ extern "C" int mmssl_id_fuse2_fwd(const float* ya, int64_t lda, const float* yb,
     return launch_fwd<128>(ya, lda, yb, ldb, coef, wsum, e, lde, n, rate, out, ldo, zn, nrm, st);
 }
 
-template <int D>
-static int launch_bwd(const float* g, int64_t ldg, const float* zn, const float* nrm, const float* ya, int64_t lda,
+template <int D, int TR>
+static int launch_bwd_t(const float* g, int64_t ldg, const float* zn, const float* nrm, const float* ya, int64_t lda,
                       const float* yb, int64_t ldb, float coef, const float* wsum_t, int64_t n, float rate, const float* ext_a,
                       int64_t ldea, const float* ext_b, int64_t ldeb, float* out_a, int64_t ldoa, float* out_b, int64_t ldob,
                       float* dw_part, cudaStream_t st) {
     const int smem = (TR * D + (D * D > TR * D ? D * D : TR * D)) * 4;
     static bool attr = false;
     if (!attr) {
-        MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_bwd_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, idfuse_carveout()));
+        MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_bwd_kernel<D, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MMSSL_CUDA(cudaFuncSetAttribute(id_fuse2_bwd_kernel<D, TR>, cudaFuncAttributePreferredSharedMemoryCarveout, idfuse_carveout()));
         attr = true;
     }
-    MMSSL_CUDA_LAUNCH((id_fuse2_bwd_kernel<D>), dim3((unsigned)((n + TR - 1) / TR)), dim3(NT), smem, st, g, ldg, zn, nrm, ya, lda, yb, ldb, coef, wsum_t, n, rate,
+    MMSSL_CUDA_LAUNCH((id_fuse2_bwd_kernel<D, TR>), dim3((unsigned)((n + TR - 1) / TR)), dim3(TR * 4), smem, st, g, ldg, zn, nrm, ya, lda, yb, ldb, coef, wsum_t, n, rate,
                                                                             ext_a, ldea, ext_b, ldeb, out_a, ldoa, out_b, ldob, dw_part);
     MMSSL_LAUNCH_OK();
     return 0;
+}
+
+template <int D>
+static int launch_bwd(const float* g, int64_t ldg, const float* zn, const float* nrm, const float* ya, int64_t lda,
+                      const float* yb, int64_t ldb, float coef, const float* wsum_t, int64_t n, float rate, const float* ext_a,
+                      int64_t ldea, const float* ext_b, int64_t ldeb, float* out_a, int64_t ldoa, float* out_b, int64_t ldob,
+                      float* dw_part, cudaStream_t st) {
+    if (tile_rows(n) == 32)
+        return launch_bwd_t<D, 32>(g, ldg, zn, nrm, ya, lda, yb, ldb, coef, wsum_t, n, rate, ext_a, ldea, ext_b, ldeb, out_a, ldoa, out_b, ldob, dw_part, st);
+    return launch_bwd_t<D, 64>(g, ldg, zn, nrm, ya, lda, yb, ldb, coef, wsum_t, n, rate, ext_a, ldea, ext_b, ldeb, out_a, ldoa, out_b, ldob, dw_part, st);
 }
 
 extern "C" int mmssl_id_fuse2_bwd(const float* g, int64_t ldg, const float* zn, const float* nrm, const float* ya,

@@ -42,7 +42,7 @@ namespace mmssl {
 // with L1::evict_last, cold ones with L1::no_allocate, so that the ~200 KB of L1 serve the popular rows.
 // One work item, from its descriptor and the first chunk of (col, val) pairs (one per lane, 0 beyond the item's end) to the
 // stored output row.  `return` = this group is done with the item.
-template <int G, int C, int R, int UMUL, bool PRE, int HINT>
+template <int G, int C, int R, int UMUL, bool PRE, int HINT, bool EARLY>
 __device__ __forceinline__ void spmm_item(const SpmmParams& p, const int4 item, int c_nxt, float v_nxt, const int lane,
                                           const unsigned gmask) {
     constexpr int RC = R * C;
@@ -51,10 +51,11 @@ __device__ __forceinline__ void spmm_item(const SpmmParams& p, const int4 item, 
     constexpr int UNR = UNR0 > G ? G : UNR0;
     const int row = item.x;
     const int begin = item.y, end = item.z;
-    // split rows: the table entry and the row start are requested now, not after the gathers (one dependent trip less)
+    // split rows: the table entry and the row start are requested now, not after the gathers (one dependent trip less) -- EARLY:
+    // not in the register-capped variants of the large graphs, where the five extra live registers become spills
     int4 st = make_int4(0, 0, 0, 0);
     int row_begin = 0;
-    if (item.w >= 0) {
+    if (EARLY && item.w >= 0) {
         st = __ldg(&p.split_table[item.w]);   // {first partial slot, #segments, segment length, heavy}
         row_begin = __ldg(p.rowptr + row);
     }
@@ -125,6 +126,10 @@ __device__ __forceinline__ void spmm_item(const SpmmParams& p, const int4 item, 
 
     // ---- split rows: publish the partial, the last arriver reduces in segment order ----
     if (item.w >= 0) {
+        if (!EARLY) {
+            st = __ldg(&p.split_table[item.w]);
+            row_begin = __ldg(p.rowptr + row);
+        }
         const int W = R * C * G * 4;
         if (st.w != 0) {
             // heavy row: accumulate into the row's own zeroed slot with 128-bit reductions
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
     if (item.x < 0) return;   // whole group exits together (items are per group)
     int c0; float v0;
     spmm_first_chunk<HINT>(p, item, lane, c0, v0);
-    spmm_item<G, C, R, UMUL, PRE, HINT>(p, item, c0, v0, lane, gmask);
+    spmm_item<G, C, R, UMUL, PRE, HINT, MINB == 1>(p, item, c0, v0, lane, gmask);
 }
 
 // Software-pipelined walk for small (latency-bound) graphs: the grid is one resident wave of lane groups and every group walks
@@ -306,7 +311,7 @@ __global__ void __launch_bounds__(128) spmm_csr_pipe_kernel(const SpmmParams p) 
         int c1; float v1;
         spmm_first_chunk<0>(p, it1, lane, c1, v1);
         const int4 it2 = gid + 2 * stride < p.n_items ? __ldg(&p.items[gid + 2 * stride]) : none;
-        spmm_item<G, C, R, 1, PRE, 0>(p, it0, c0, v0, lane, gmask);
+        spmm_item<G, C, R, 1, PRE, 0, true>(p, it0, c0, v0, lane, gmask);
         it0 = it1; c0 = c1; v0 = v1; it1 = it2; gid += stride;
     }
 }

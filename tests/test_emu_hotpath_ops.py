@@ -85,6 +85,12 @@ def test_spmm_plan_cuts(emu, cuts, d, nrhs):
     Z.test_spmm_plan_cuts(cuts, d, nrhs)
 
 
+@pytest.mark.parametrize("n,d,two", [(777, 64, False), (777, 128, True), (100100, 64, True)])
+def test_id_fuse2_against_autograd(emu, n, d, two):
+    from tests import test_gpu_zz_more_ops as Z
+    Z.test_id_fuse2_against_autograd(n, d, two)
+
+
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
 def test_sgemm_large_tiles(emu, ta, tb):
     from tests import test_gpu_zz_more_ops as Z

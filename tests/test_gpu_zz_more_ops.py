@@ -107,6 +107,37 @@ def test_spmm_plan_cuts(cuts, d, nrhs):
         ops.spmm_plan_set_cuts(64, 32, 1024, 64)
 
 
+@pytest.mark.parametrize("n,d,two", [(777, 64, False), (777, 128, True), (100100, 64, True), (100070, 128, False)])
+def test_id_fuse2_against_autograd(n, d, two):
+    """The fused id-fusion kernels (Models.py:139-169 closed form + :188-197) against torch autograd in fp64, on both tile heights
+    (32 rows per block under 100k rows, 64 above), with one and two propagated inputs, external gradients, and the head
+    reduction of the partial dWsum tiles."""
+    from mmssl_b200 import ops
+    torch.manual_seed(n + d)
+    f = dict(device="cuda")
+    ya, yb, e, g = (torch.randn(n, d, **f) for _ in range(4))
+    ea, eb = torch.randn(n, d, **f), torch.randn(n, d, **f)
+    wcat = torch.randn(4 * d, d, **f) * 0.1
+    w, w_t = ops.wsum(wcat, d, 4)
+    coef, rate = (0.5 if two else 1.0), 0.36
+    out, zn, nrm = ops.id_fuse2_fwd(ya, yb if two else None, coef, w, e, rate)
+    oa, ob, part = ops.id_fuse2_bwd(g, zn, nrm, ya, yb if two else None, coef, w_t, rate, ea, eb, two)
+    dw = torch.empty(4 * d, d, **f)
+    ops.dwcat_reduce(part, part[:0], d, 4, dw)
+    # fp64 autograd reference of  out = e + rate * normalize(coef * (ya [+ yb]) @ Wsum),  Wsum = sum of the 4 head blocks
+    Ya, Yb, W4 = ya.double().requires_grad_(), yb.double().requires_grad_(), wcat.double().requires_grad_()
+    m = coef * (Ya + Yb) if two else coef * Ya
+    z = m @ W4.view(4, d, d).sum(0)
+    ref = e.double() + rate * torch.nn.functional.normalize(z, dim=1)
+    ref.backward(g.double())
+    assert rel_err(out, ref) < 1e-5
+    if two:
+        assert rel_err(oa, Ya.grad + ea.double()) < 1e-5 and rel_err(ob, Yb.grad + eb.double()) < 1e-5
+    else:
+        assert rel_err(oa, Ya.grad + ea.double() + eb.double()) < 1e-5 and ob is None
+    assert rel_err(dw, W4.grad) < 2e-5
+
+
 @pytest.mark.parametrize("n,d", [(1500, 64), (2304, 128)])
 def test_infonce_beyond_one_block(n, d):
     """More rows than one 1024-block of main.py:228-246 and not a multiple of it (SURVEY 8c edge case): the reference's double
