@@ -661,9 +661,12 @@ def row_shard_report(name, a, rank, world, dev):
     for s in range(3):
         sh.set_indices(*batches[s % 8]); step()
     torch.cuda.synchronize()
-    dist.barrier()
     sh.n_gathers = sh.gathered_bytes = sh.n_reduce_scatters = 0
+    # BEFORE the barrier: the query is a subprocess (~80 ms with 8 GPUs).  Between the barrier and the first event it made rank 0
+    # enter the loop late while the other ranks' clocks were already running at their first exchange barrier: +75 ms / steps on
+    # the max over ranks (round 2: 8 GPUs, Sports 1.31 ms reported vs 0.57 ms measured by tools/rowshard_ab.py, 1M x 200k 11.7 vs ~7.9).
     nv0 = nvlink_counters(dev.index) if rank == 0 else None
+    dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(steps):
