@@ -878,7 +878,9 @@ def main():
                                      "speedup_ours": round(sg["ms_per_step"] / (ms_total / a.steps), 2)}
             except Exception as e:
                 line["stock_gpu"] = {"unavailable": str(e)[:200]}
-        if world == 1:      # batches drawn on the device (no host sampler, no H2D)
+        if world == 1 and BATCH > 1024:
+            line["device_sampler_e2e"] = {"unavailable": "one device-sampler launch draws at most 1024 triples (csrc/sampler.cu)"}
+        elif world == 1:    # batches drawn on the device (no host sampler, no H2D)
             from mmssl_b200.sampler import DeviceTripleSampler
             P2 = {k: v.clone() for k, v in P.items()}
             tr2 = HotStepTrainer(P2, feats, graphs, cfg, BATCH, world=1, sampler=DeviceTripleSampler(ds.train, device=dev, seed=a.seed))
